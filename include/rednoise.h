@@ -1,0 +1,141 @@
+/* rednoise.h -- C ABI of rednoise_b200, the B200-native (sm_100a) drop-in for the
+ * red-noise field-synthesis hot path of TGlad/redNoise.
+ *
+ * The reference has no plugin/FFI layer; the de-facto boundary this library
+ * replaces is the field-synthesis half of the constructor
+ *     Terrain::Terrain(int depth, Length size, Scale amplitude)
+ *         renderEngine/include/Terrain.h:20, renderEngine/source/Terrain.cpp:15
+ * i.e. grid initialisation (Terrain.cpp:44-56), seeding (:58-59), the
+ * diamond-square level loop (:60-82 -> averageSquare :216-222, generateSquare
+ * :224-258, averageDiamond :144-168, generateDiamond :171-214) and the
+ * addVolcano epilogue (:88, :121-141).  INTEGRATION.md shows the adapter a
+ * maintainer would add inside Terrain::Terrain.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, POD structs, int status codes
+ *     (0 = ok).  Nothing throws across the boundary.  No CPU fallback: every
+ *     compute entry point fails with RN_ERR_NO_DEVICE / RN_ERR_CUDA when no
+ *     sm_100 device is usable.
+ *   - A field is a row-major array of rn_element (16 B = the reference's
+ *     Terrain::TerrainElement, Terrain.h:15-19), i-major: element (i,j) of the
+ *     reference's baseArray[i][j] lives at dst[(i-i0)*pitch_elems + (j-j0)].
+ *   - The caller owns dst; the library owns only its context and scratch.
+ *   - Calls are blocking unless a stream is supplied with dst_is_device != 0,
+ *     in which case work is enqueued on that stream and the call returns.
+ *   - libc rand()/srand() state is never touched (the reference shares its
+ *     rand() stream with later callers, Core.cpp:72,76; rn_terrain2d_draw_count
+ *     tells an adapter how far to advance the host stream).
+ */
+#ifndef REDNOISE_H
+#define REDNOISE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RN_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+enum {
+  RN_OK = 0,
+  RN_ERR_BAD_PARAM = 1,   /* NULL pointer, depth out of range, bad window, ... */
+  RN_ERR_UNSUPPORTED = 2, /* lacunarity != 2, ... */
+  RN_ERR_NO_DEVICE = 3,   /* no CUDA device / not sm_100 */
+  RN_ERR_CUDA = 4,        /* a CUDA runtime call failed (see rn_last_error_string) */
+  RN_ERR_OOM = 5          /* device scratch allocation failed */
+};
+
+#define RN_MIN_DEPTH 3  /* Terrain.cpp:60: step = W/4 must be >= 2 for a level to exist */
+#define RN_MAX_DEPTH 14 /* (2^14+1)^2 * 16 B = 4.3 GB; draw count stays < 2^32 */
+
+/* One finished sample == Terrain::TerrainElement {Vector3 pos; float shade}
+ * (renderEngine/include/Terrain.h:15-19), 16 bytes, written with one 128-bit store. */
+typedef struct rn_element {
+  float x, y, z, shade;
+} rn_element;
+
+/* The reference's generator call surface.  Defaults (rn_params_default) are the
+ * literals the reference hard-codes, so a default call == the reference. */
+typedef struct rn_params {
+  uint32_t seed;              /* srand() argument, Terrain.cpp:58-59 (reference: time(NULL)) */
+  int32_t depth;              /* "octave count": W = 1<<depth, depth-2 displacement levels (Terrain.h:20, Terrain.cpp:60-82) */
+  float amplitude;            /* Terrain.h:20; 0.2f at Core.cpp:65 */
+  float size;                 /* Terrain.h:20; 500 at Core.cpp:65; only scales volcano_pos (Terrain.cpp:89) */
+  float persistence;          /* per-level gain; the reference fixes 0.5 via step/maxWidth (Terrain.cpp:186,231) */
+  int32_t lacunarity;         /* per-level frequency ratio; the reference fixes 2 (Terrain.cpp:81). Only 2 is supported. */
+  float sideways_scale;       /* 0.5f, Terrain.cpp:142 */
+  float radiosity_strength;   /* 0.5f, Terrain.cpp:143 */
+  float feature_scale;        /* 80.0f, Terrain.cpp:169 */
+  float amplitude_variation;  /* 0.5f, Terrain.cpp:170 */
+  int32_t bulgy_rocks;        /* 1: #define BULGY_ROCKS, Terrain.cpp:189 */
+  int32_t apply_volcano;      /* 1: addVolcano runs, Terrain.cpp:88 */
+} rn_params;
+
+/* "grid extent and origin": a sub-window of the one global (W+1)x(W+1) lattice.
+ * The window is seam-exact: its samples are bit-identical to the same indices
+ * of the full field. */
+typedef struct rn_window {
+  int32_t i0, j0; /* first row (x index) and column (z index) */
+  int32_t ni, nj; /* rows and columns */
+} rn_window;
+
+typedef struct rn_context rn_context;
+
+/* ---- host-only helpers (no GPU needed) ---------------------------------- */
+int rn_version(void);
+const char* rn_last_error_string(void);
+const char* rn_status_string(int status);
+int rn_params_default(rn_params* p);
+/* number of samples per side: (1<<depth)+1 */
+int rn_terrain2d_side(int depth);
+/* rand() calls the reference consumes for one Terrain of this depth:
+ * sum over levels of 3n^2+2n. */
+uint64_t rn_terrain2d_draw_count(int depth);
+/* 0-based index of the rand() call that displaces lattice point (i,j) of a
+ * depth-`depth` field, or UINT64_MAX for the 25 undisplaced points at
+ * multiples of W/4 / out-of-range arguments. */
+uint64_t rn_terrain2d_call_index(int depth, int i, int j);
+/* MSVC CRT LCG (the reference's rand(), basics.h:18): state after `k` calls
+ * from srand(seed), by skip-ahead; and the k-th (0-based) 15-bit draw. */
+uint32_t rn_lcg_state_after(uint32_t seed, uint64_t k);
+uint32_t rn_lcg_draw(uint32_t seed, uint64_t k);
+
+/* ---- context ------------------------------------------------------------ */
+/* One context per CUDA device (one process per GPU is the intended
+ * deployment).  device < 0 selects the current device. */
+int rn_create(int device, rn_context** out_ctx);
+int rn_destroy(rn_context* ctx);
+/* Kernels launched by this context since creation (for the bench's claim). */
+uint64_t rn_launch_count(const rn_context* ctx);
+/* Select the synthesis algorithm: 0 = auto (fused tile kernels), 1 = level-synchronous
+ * global-memory kernels (one launch set per level), 2 = fused tile kernels. */
+int rn_set_algorithm(rn_context* ctx, int algo);
+
+/* ---- the hot path --------------------------------------------------------- */
+/* Synthesize the field of Terrain(depth,size,amplitude) with srand(p->seed).
+ *   win          NULL = whole (W+1)x(W+1) grid
+ *   dst          ni*pitch_elems rn_element, device memory if dst_is_device else host
+ *   pitch_elems  row pitch in elements (>= nj); 0 means nj
+ *   stream       cudaStream_t (as void*) or NULL for the context's own stream.
+ *   volcano_pos  optional float[3] (host): Terrain::volcanoPos after Terrain.cpp:89
+ *                (only meaningful when apply_volcano; requires a blocking call) */
+int rn_terrain2d(rn_context* ctx, const rn_params* p, const rn_window* win, rn_element* dst,
+                 size_t pitch_elems, int dst_is_device, void* stream, float* volcano_pos);
+
+/* `ntiles` independent full fields that share `p` except for the seed
+ * (seeds[t]); tile t is written at dst + t*tile_stride_elems (0 = side*side). */
+int rn_terrain2d_batch(rn_context* ctx, const rn_params* p, const uint32_t* seeds, int ntiles,
+                       rn_element* dst, size_t tile_stride_elems, int dst_is_device, void* stream);
+
+/* The integer part of the path, exposed for bit-exact parity tests: writes the
+ * 15-bit draws k = first .. first+n-1 of srand(seed) as uint16. */
+int rn_lcg_draws_device(rn_context* ctx, uint32_t seed, uint64_t first, uint64_t n, uint16_t* dst,
+                        int dst_is_device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REDNOISE_H */

@@ -1,0 +1,209 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Drives the reference's OWN, unmodified diamond-square code
+// (/root/reference/renderEngine/source/Terrain.cpp) so the C restatement in
+// rn_oracle.c and the CUDA path can be pinned against it.  Built by
+// oracle/Makefile into oracle/_ref/ (git-ignored; never copied into the repo).
+//
+// Two capture styles:
+//   ref_terrain_passes : Terrain's private pass methods driven in the loop order
+//                        of Terrain.cpp:60-82 on a caller-visible grid
+//                        (exported from libredref.so, used by tests and bench).
+//   ref_ctor_check     : the whole constructor Terrain::Terrain (Terrain.cpp:15)
+//                        with operator delete neutralised while the field is
+//                        captured (stand-alone executable only, RN_REF_CTOR_MAIN).
+//
+// The entropy source is the MSVC 2008 CRT LCG (not in the reference tree; the
+// project is VS2008/Win32, renderEngine.vcproj:4): state = state*214013+2531011,
+// draw = (state>>16)&0x7fff, srand(x): state = x, RAND_MAX = 0x7fff.
+#define private public
+#include "Terrain.h"
+#undef private
+#include "Cell.h"
+#include <stdint.h>
+#include <chrono>
+
+static unsigned int g_state = 1u;
+static unsigned long long g_calls = 0;
+static int g_seed_forced = 0;
+static unsigned int g_forced_seed = 0;
+
+extern "C" int rn_msvc_rand(void)
+{
+  g_state = g_state * 214013u + 2531011u;
+  ++g_calls;
+  return (int)((g_state >> 16) & 0x7fffu);
+}
+extern "C" void rn_msvc_srand(unsigned int s)
+{
+  // Terrain.cpp:58-59 seeds from time(NULL); the harness pins the seed instead.
+  g_state = g_seed_forced ? g_forced_seed : s;
+}
+
+// ---- Timer stand-in (reference Timer.cpp is Win32-only: <windows.h>, QPC) ----
+unsigned long GetTimerFrequency() { return 1000000000ul; }
+unsigned long GetCurrentTimerValue()
+{
+  return (unsigned long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+      std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static int g_quiet = 1;
+Timer::Timer() { m_frequency = GetTimerFrequency(); m_totalSectionTime = 0; }
+Timer::~Timer() {}
+void Timer::start() { m_sectionStartTime = GetCurrentTimerValue(); }
+TimePeriod Timer::stop()
+{
+  m_sectionEndTime = GetCurrentTimerValue();
+  TimePeriod e = getElapsedTime(m_sectionStartTime, m_sectionEndTime);
+  m_totalSectionTime += e;
+  return e;
+}
+void Timer::reset() { m_sectionEndTime = 0; m_totalSectionTime = 0; m_sectionStartTime = 0; }
+TimePeriod Timer::getTotalTime() { return m_totalSectionTime; }
+void Timer::print(const char* s) { if (!g_quiet) printf("Total for %s: %f ms\n", s, m_totalSectionTime); }
+TimePeriod Timer::getElapsedTime(const unsigned long a, const unsigned long b) const { return getTime(b - a); }
+TimePeriod Timer::getTime(unsigned long e) const { return TimePeriod(e * 1000.0 / m_frequency); }
+
+static double now_s()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" {
+
+// KAT helper: first n draws after srand(seed).
+void ref_lcg_draws(unsigned int seed, int n, int* out)
+{
+  g_seed_forced = 0;
+  rn_msvc_srand(seed);
+  for (int i = 0; i < n; i++) out[i] = rn_msvc_rand();
+}
+
+// basics.h:16-19 evaluated by the reference's own inline function.
+float ref_random_from_state(unsigned int state_before)
+{
+  g_state = state_before;
+  return random();
+}
+
+// Runs Terrain.cpp:44-56 (grid init, restated here because it is inline in the
+// ctor) + the reference's pass methods in the order of Terrain.cpp:60-82, then
+// optionally addVolcano (Terrain.cpp:88,121-141).
+//   out    : (W+1)^2 * 4 floats, i-major, {pos.x,pos.y,pos.z,shade}
+//   times  : optional double[3] = {alloc+init s, passes s, volcano s}
+// Returns the number of rand() calls consumed, or -1 on bad arguments.
+long long ref_terrain_passes(int depth, float amplitude, float size, unsigned int seed,
+                             int apply_volcano, float* out, double* times)
+{
+  if (depth < 2 || depth > 14 || !out) return -1;
+  double t0 = now_s();
+  Terrain* t = (Terrain*)calloc(1, sizeof(Terrain)); // ctor deliberately not run
+  t->depth = depth;
+  t->amplitude = amplitude;
+  const int maxWidth = 1 << depth;
+  t->maxWidth = maxWidth;
+  t->baseArray = new Terrain::TerrainElement*[maxWidth + 1];
+  for (int i = 0; i < maxWidth + 1; i++)
+  {
+    float x = 2.0f * (float)(i - maxWidth / 2) / (float)maxWidth;
+    t->baseArray[i] = new Terrain::TerrainElement[maxWidth + 1];
+    for (int j = 0; j < maxWidth + 1; j++)
+    {
+      float z = 2.0f * (float)(j - maxWidth / 2) / (float)maxWidth;
+      t->baseArray[i][j].pos.set(x, z * 0.04f, z);
+      t->baseArray[i][j].shade = 1.0f;
+    }
+  }
+  double t1 = now_s();
+  g_seed_forced = 0;
+  rn_msvc_srand(seed);
+  g_calls = 0;
+  int step = maxWidth / 4;
+  do
+  {
+    for (int x = 0; x < maxWidth; x += step)
+      for (int y = 0; y < maxWidth; y += step)
+        t->averageSquare(x, y, x + step, y + step);
+    for (int x = 0; x < maxWidth; x += step)
+      for (int y = 0; y < maxWidth; y += step)
+        t->generateSquare(x, y, x + step, y + step);
+    for (int x = -step / 2; x < maxWidth; x += step)
+      for (int y = 0; y < maxWidth; y += step)
+        t->averageDiamond(x, y, x + step, y + step);
+    for (int x = 0; x < maxWidth; x += step)
+      for (int y = -step / 2; y < maxWidth; y += step)
+        t->averageDiamond(x, y, x + step, y + step);
+    for (int x = -step / 2; x < maxWidth; x += step)
+      for (int y = 0; y < maxWidth; y += step)
+        t->generateDiamond(x, y, x + step, y + step);
+    for (int x = 0; x < maxWidth; x += step)
+      for (int y = -step / 2; y < maxWidth; y += step)
+        t->generateDiamond(x, y, x + step, y + step);
+    step /= 2;
+  } while (step > 1);
+  double t2 = now_s();
+  long long calls = (long long)g_calls;
+  if (apply_volcano) t->addVolcano(size);
+  double t3 = now_s();
+  const size_t rowBytes = (size_t)(maxWidth + 1) * sizeof(Terrain::TerrainElement);
+  for (int i = 0; i < maxWidth + 1; i++)
+  {
+    memcpy((char*)out + (size_t)i * rowBytes, t->baseArray[i], rowBytes);
+    delete[] t->baseArray[i];
+  }
+  delete[] t->baseArray;
+  free(t);
+  if (times) { times[0] = t1 - t0; times[1] = t2 - t1; times[2] = t3 - t2; }
+  return calls;
+}
+
+int ref_sizeof_element(void) { return (int)sizeof(Terrain::TerrainElement); }
+
+} // extern "C"
+
+#ifdef RN_REF_CTOR_MAIN
+// ---- whole-constructor capture (stand-alone executable only) ----
+// Terrain::Terrain frees the field before returning (Terrain.cpp:112-115), so
+// deletes are neutralised while the ctor runs and the public baseArray is read
+// afterwards.
+static int g_no_delete = 0;
+void operator delete(void* p) noexcept { if (!g_no_delete) free(p); }
+void operator delete[](void* p) noexcept { if (!g_no_delete) free(p); }
+void operator delete(void* p, size_t) noexcept { if (!g_no_delete) free(p); }
+void operator delete[](void* p, size_t) noexcept { if (!g_no_delete) free(p); }
+
+static uint64_t fnv64(const void* data, size_t n, uint64_t h)
+{
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 0x100000001b3ull; }
+  return h;
+}
+
+int main(int argc, char** argv)
+{
+  int depth = argc > 1 ? atoi(argv[1]) : 8;
+  unsigned int seed = argc > 2 ? (unsigned)strtoul(argv[2], 0, 10) : 12345u;
+  g_quiet = argc > 3 ? 0 : 1;
+  const int W = 1 << depth;
+  // (1) whole ctor
+  g_seed_forced = 1; g_forced_seed = seed; g_calls = 0;
+  g_no_delete = 1;
+  Terrain* t = new Terrain(depth, 500.0f, 0.2f);
+  g_no_delete = 0;
+  unsigned long long ctor_calls = g_calls;
+  uint64_t h1 = 0xcbf29ce484222325ull;
+  for (int i = 0; i <= W; i++) h1 = fnv64(t->baseArray[i], (size_t)(W + 1) * 16, h1);
+  // (2) pass-driven
+  float* buf = (float*)malloc((size_t)(W + 1) * (W + 1) * 16);
+  long long calls2 = ref_terrain_passes(depth, 0.2f, 500.0f, seed, 1, buf, 0);
+  uint64_t h2 = fnv64(buf, (size_t)(W + 1) * (W + 1) * 16, 0xcbf29ce484222325ull);
+  ref_terrain_passes(depth, 0.2f, 500.0f, seed, 0, buf, 0);
+  uint64_t h3 = fnv64(buf, (size_t)(W + 1) * (W + 1) * 16, 0xcbf29ce484222325ull);
+  printf("{\"depth\": %d, \"seed\": %u, \"ctor_calls\": %llu, \"pass_calls\": %lld, "
+         "\"ctor_post_volcano\": \"%016llx\", \"passes_post_volcano\": \"%016llx\", "
+         "\"passes_pre_volcano\": \"%016llx\", \"sizeof_element\": %d}\n",
+         depth, seed, ctor_calls, calls2, (unsigned long long)h1, (unsigned long long)h2,
+         (unsigned long long)h3, ref_sizeof_element());
+  return h1 == h2 ? 0 : 1;
+}
+#endif

@@ -1,0 +1,52 @@
+/* oracle/rn_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C) of the reference's field-synthesis path, used as the
+ * parity checker for the CUDA path.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may call into it.  The product
+ * (rednoise_b200/) never links or loads anything under oracle/.
+ *
+ * Parity status: PINNED for 2D -- the restatement is checked bit-for-bit against
+ * the reference's own unmodified sources compiled into oracle/_ref/ (see
+ * ref_harness.cpp, tests/test_oracle_vs_ref.py) and against the committed
+ * digests in tests/golden/ that were produced by that build.
+ * 3D (rno_volume3d*) has NO reference counterpart: parity unpinned by the
+ * reference, pinned only against this file's own golden digests.
+ */
+#ifndef RN_ORACLE_H
+#define RN_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+#include "../include/rednoise.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* MSVC CRT LCG (not in the reference tree; VS2008 runtime, renderEngine.vcproj:4). */
+uint32_t rno_lcg_next_state(uint32_t state);
+uint32_t rno_lcg_state_after(uint32_t seed, uint64_t k); /* skip-ahead */
+uint32_t rno_lcg_draw(uint32_t seed, uint64_t k);        /* k-th 15-bit draw, 0-based */
+float rno_random_from_draw(int r);                       /* basics.h:16-19 */
+
+uint64_t rno_draw_count(int depth);
+uint64_t rno_call_index(int depth, int i, int j);
+
+/* Sequential restatement: reference loop order, sequential LCG (Terrain.cpp:44-82). */
+int rno_terrain2d_seq(const rn_params* p, rn_element* grid);
+/* Index-addressed restatement: RNG by call index + skip-ahead, shade by
+ * ordered gather (A.3), samples of each stage visited in reversed order when
+ * `reverse` != 0.  Must equal rno_terrain2d_seq bit for bit. */
+int rno_terrain2d_indexed(const rn_params* p, rn_element* grid, int reverse);
+/* Terrain.cpp:121-141; volcano_pos (optional float[3]) = volcanoPos after Terrain.cpp:89. */
+void rno_add_volcano(const rn_params* p, rn_element* grid, float* volcano_pos);
+/* seq + optional volcano (p->apply_volcano). */
+int rno_terrain2d(const rn_params* p, rn_element* grid, float* volcano_pos);
+/* ntiles independent fields, one per seed, on up to `threads` host threads (OpenMP). */
+int rno_terrain2d_batch(const rn_params* p, const uint32_t* seeds, int ntiles, rn_element* grids, int threads);
+
+uint64_t rno_fnv64(const void* data, size_t nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- red-noise field synthesis throughput (Gsamples/s) on 1..8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one unit of work per GPU: by default one
+Terrain(depth=12, size=500, amplitude=0.2) field = 4097x4097 samples of 16 B (BASELINE.json
+configs[1]).  With N > 1 GPUs every rank synthesises its own field from its own seed
+(independent units, no data-path collective): weak scaling.  `--workload slab` instead shards
+ONE depth-14 field by row slabs across the ranks (strong scaling).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ELEM_BYTES = 16  # sizeof(Terrain::TerrainElement), Terrain.h:15-19: ALGORITHMIC bytes written per sample
+BASE_SEED = 12345
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)", d
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", {}
+
+
+# --------------------------------------------------------------------------- clocks ---
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------- reference arm ---
+def _ref_worker(args):
+    depth, seed = args
+    from tests import oracle_lib
+    ref = oracle_lib.load_ref()
+    t0 = time.perf_counter()
+    _, calls, times = ref.terrain2d(depth, seed, volcano=1, want_times=True)
+    return time.perf_counter() - t0, times
+
+
+def _port_worker(args):
+    depth, seed = args
+    from tests import oracle_lib
+    o = oracle_lib.load_oracle()
+    t0 = time.perf_counter()
+    o.terrain2d(oracle_lib.params(seed=seed, depth=depth, apply_volcano=1))
+    dt = time.perf_counter() - t0
+    return dt, (0.0, dt, 0.0)
+
+
+def cpu_fields_per_second(depth: int, procs: int, rounds: int, budget_s: float):
+    """Times the reference's own CPU generator (oracle/_ref, else the oracle port): `procs`
+    independent fields (distinct seeds) generated concurrently, one process each (the reference
+    is single-threaded with global rand() state), `rounds` times or until the budget is spent.
+    Returns (fields/s aggregate, kind, per-round seconds, pure-pass seconds of one field)."""
+    from concurrent.futures import ProcessPoolExecutor
+    from tests import oracle_lib
+    kind = "reference" if oracle_lib.load_ref() is not None else "port"
+    worker = _ref_worker if kind == "reference" else _port_worker
+    if kind == "port":
+        oracle_lib.load_oracle()
+    round_s, pass_s = [], []
+    t_start = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=procs) as ex:
+        list(ex.map(worker, [(min(depth, 8), 1)] * procs))  # warm the pool / page in the library
+        for r in range(rounds):
+            t0 = time.perf_counter()
+            res = list(ex.map(worker, [(depth, BASE_SEED + r * procs + q) for q in range(procs)]))
+            round_s.append(time.perf_counter() - t0)
+            pass_s.extend(t[1] for _, t in res)
+            if time.perf_counter() - t_start > budget_s:
+                break
+    fps = procs / statistics.median(round_s)
+    return fps, kind, round_s, statistics.median(pass_s)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    depth = args.depth
+    side = (1 << depth) + 1
+    samples = side * side
+    procs = max(1, min(os.cpu_count() or 1, args.cpu_procs))
+    fps, kind, round_s, pass_s = cpu_fields_per_second(depth, procs, args.warmup + args.steps, budget_s=240.0)
+    timed = round_s[args.warmup:] if len(round_s) > args.warmup else round_s
+    ms = 1e3 * statistics.mean(timed)
+    value = procs * samples / (ms * 1e-3) / 1e9
+    line = {
+        "impl": "reference", "metric": "red-noise field synthesis throughput", "value": value, "unit": "Gsamples/s",
+        "n_gpus": args.gpus, "steps": len(timed), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": procs, "kind": kind,
+                         "sample": f"{procs} independent Terrain(depth={depth}) fields per step, one single-threaded process each "
+                                   f"(grid init + diamond-square passes + addVolcano); pure passes of one field: {pass_s * 1e3:.0f} ms",
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args):
+    side = (1 << args.depth) + 1
+    return {
+        "workload": f"{side}x{side} 2D red-noise heightfield (Terrain depth={args.depth}: {args.depth - 2} displacement levels/'octaves'), "
+                    f"amplitude 0.2, size 500, seed {BASE_SEED}+rank, addVolcano on" if args.workload == "field" else
+                    f"row slabs of ONE {side}x{side} field (depth={args.depth}) sharded over the ranks",
+        "baseline_config": "configs[1]: 4096x4096 2D heightfield, 12 octaves, single B200" if args.depth == 12 else f"depth {args.depth}",
+        "fields_per_step_per_rank": 1,
+        "samples_per_field": side * side,
+        "bytes_per_sample": ELEM_BYTES,
+        "cache_policy": "output (268 MB at depth 12) is larger than the 126 MB L2 and there is no input; no explicit L2 flush",
+        "parallelism": f"dp{args.gpus}: one process per GPU, independent units, no collective" if args.workload == "field" else
+                       f"slab{args.gpus}: row slabs, halo recomputed, no collective",
+    }
+
+
+# ------------------------------------------------------------------------ our arm ---
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from rednoise_b200 import build, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    build.build()  # no-op when the in-tree .so is fresh
+    ctx = capi.Context(local_rank)
+    ctx.set_algorithm(args.algo)
+
+    depth = args.depth
+    side = (1 << depth) + 1
+    stream = torch.cuda.current_stream().cuda_stream
+    if args.workload == "field":
+        p = capi.default_params(seed=BASE_SEED + rank, depth=depth, apply_volcano=1)
+        win = None
+        ni, nj = side, side
+    else:  # one field, row slabs; the shared boundary row is produced by the lower rank only
+        p = capi.default_params(seed=BASE_SEED, depth=depth, apply_volcano=1)
+        rows = (side + world - 1) // world
+        i0 = rank * rows
+        ni, nj = max(0, min(rows, side - i0)), side
+        win = capi.Window(i0, 0, ni, nj)
+    my_samples = ni * nj
+    dst = torch.empty((ni, nj, 4), device="cuda", dtype=torch.float32)
+
+    def step():
+        ctx.terrain2d_ptr(p, dst.data_ptr(), window=win, dst_is_device=True, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record()
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    launches = ctx.launches - launches0
+    stage_ms = ctx.stage_times() if hasattr(ctx, "stage_times") else None
+
+    # ---- e2e: the same call with a HOST destination (pinned), D2H inside the timed region ----
+    host = torch.empty((ni, nj, 4), dtype=torch.float32, pin_memory=True)
+    e2e_steps = max(2, min(args.steps, 5))
+    ctx.terrain2d_ptr(p, host.data_ptr(), window=win, dst_is_device=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.terrain2d_ptr(p, host.data_ptr(), window=win, dst_is_device=False)  # blocking: synth + D2H + sync
+        _ = float(host[ni // 2, nj // 2, 1])  # the host reads the step's result
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([total_ms, e2e_s, float(my_samples)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_s, all_samples = float(tmax[0]), float(tmax[1]), float(tsum[2])
+    else:
+        all_samples = float(my_samples)
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = all_samples / (ms_per_step * 1e-3) / 1e9
+        peak, peak_src, _ = load_peaks()
+        # dominant kernel: the final fused stage when the library reports stage times, else the whole step
+        if stage_ms and stage_ms.get("final_ms"):
+            k_ms, k_name = stage_ms["final_ms"], stage_ms.get("final_name", "final stage")
+        else:
+            k_ms, k_name = statistics.mean(per_step), "whole step (all launches)"
+        achieved = my_samples * ELEM_BYTES / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": "red-noise field synthesis throughput", "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak" if args.workload == "field" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": k_name, "kernel_ms": k_ms, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": my_samples * ELEM_BYTES,
+                         "samples_per_s_bound_hbm": peak * 1e9 / ELEM_BYTES / 1e9},
+            "e2e": {"value": all_samples / e2e_s / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 48,
+                    "d2h_bytes_per_step": my_samples * ELEM_BYTES, "ms_per_step": e2e_s * 1e3,
+                    "note": "rn_terrain2d() with a pinned HOST destination: synthesis + D2H of the field + host read; "
+                            "the only input is the 48-byte rn_params"},
+            "gpu_launches": int(launches), "clocks": clocks, "algorithm": args.algo,
+            "per_step_ms": {"min": min(per_step), "median": statistics.median(per_step), "max": max(per_step)},
+        }
+        if stage_ms:
+            line["stage_ms"] = stage_ms
+        if world == 1 and not args.no_cpu:
+            try:
+                procs = 1
+                fps, kind, round_s, pass_s = cpu_fields_per_second(depth, procs, rounds=8, budget_s=20.0)
+                line["cpu_baseline"] = {
+                    "value": fps * side * side / 1e9, "unit": "Gsamples/s", "cores": procs, "kind": kind,
+                    "sample": f"{len(round_s)} x Terrain(depth={depth}) on one host thread (the reference is single-threaded): "
+                              f"grid init + passes + addVolcano; median {statistics.median(round_s) * 1e3:.0f} ms/field, "
+                              f"pure passes {pass_s * 1e3:.0f} ms",
+                    "host_cpus": os.cpu_count()}
+            except Exception as e:  # the bench line must still print
+                line["cpu_baseline"] = {"value": None, "unit": "Gsamples/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="field", choices=["field", "slab"])
+    ap.add_argument("--depth", type=int, default=None)
+    ap.add_argument("--algo", type=int, default=0)
+    ap.add_argument("--cpu-procs", type=int, default=16, help="reference arm: concurrent single-threaded generators")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.depth is None:
+        args.depth = 12 if args.workload == "field" else 14
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,171 @@
+"""ctypes binding of include/rednoise.h (the C ABI of librednoise_b200.so).
+
+This is plumbing for the tests and bench.py, mirroring the header one to one.  The
+product is the shared library; it has no CPU fallback, so loading fails loudly when
+the library has not been built (python -m rednoise_b200.build).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librednoise_b200.so")
+
+RN_OK, RN_ERR_BAD_PARAM, RN_ERR_UNSUPPORTED, RN_ERR_NO_DEVICE, RN_ERR_CUDA, RN_ERR_OOM = range(6)
+RN_MIN_DEPTH, RN_MAX_DEPTH = 3, 14
+
+# every symbol include/rednoise.h declares (tests/test_abi_symbols.py checks the two agree)
+SYMBOLS = [
+    "rn_version", "rn_last_error_string", "rn_status_string", "rn_params_default", "rn_terrain2d_side",
+    "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
+    "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device",
+]
+
+
+class Params(C.Structure):
+    """rn_params: the reference's generator call surface (Terrain.h:20 + the literals of Terrain.cpp)."""
+
+    _fields_ = [
+        ("seed", C.c_uint32), ("depth", C.c_int32), ("amplitude", C.c_float), ("size", C.c_float),
+        ("persistence", C.c_float), ("lacunarity", C.c_int32), ("sideways_scale", C.c_float),
+        ("radiosity_strength", C.c_float), ("feature_scale", C.c_float), ("amplitude_variation", C.c_float),
+        ("bulgy_rocks", C.c_int32), ("apply_volcano", C.c_int32),
+    ]
+
+
+class Window(C.Structure):
+    _fields_ = [("i0", C.c_int32), ("j0", C.c_int32), ("ni", C.c_int32), ("nj", C.c_int32)]
+
+
+class RedNoiseError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"rednoise status {status}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m rednoise_b200.build` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_size_t
+    L.rn_version.restype = i32
+    L.rn_last_error_string.restype = C.c_char_p
+    L.rn_status_string.restype = C.c_char_p
+    L.rn_status_string.argtypes = [i32]
+    L.rn_params_default.argtypes = [C.POINTER(Params)]
+    L.rn_terrain2d_side.argtypes = [i32]
+    L.rn_terrain2d_draw_count.restype = u64
+    L.rn_terrain2d_draw_count.argtypes = [i32]
+    L.rn_terrain2d_call_index.restype = u64
+    L.rn_terrain2d_call_index.argtypes = [i32, i32, i32]
+    L.rn_lcg_state_after.restype = u32
+    L.rn_lcg_state_after.argtypes = [u32, u64]
+    L.rn_lcg_draw.restype = u32
+    L.rn_lcg_draw.argtypes = [u32, u64]
+    L.rn_create.argtypes = [i32, C.POINTER(vp)]
+    L.rn_destroy.argtypes = [vp]
+    L.rn_launch_count.restype = u64
+    L.rn_launch_count.argtypes = [vp]
+    L.rn_set_algorithm.argtypes = [vp, i32]
+    L.rn_terrain2d.argtypes = [vp, C.POINTER(Params), C.POINTER(Window), vp, sz, i32, vp, C.POINTER(C.c_float)]
+    L.rn_terrain2d_batch.argtypes = [vp, C.POINTER(Params), C.POINTER(u32), i32, vp, sz, i32, vp]
+    L.rn_lcg_draws_device.argtypes = [vp, u32, u64, u64, vp, i32, vp]
+    _lib = L
+    return L
+
+
+def default_params(**overrides) -> Params:
+    p = Params()
+    lib().rn_params_default(C.byref(p))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _check(status: int):
+    if status != RN_OK:
+        raise RedNoiseError(status, (lib().rn_last_error_string() or b"").decode() or
+                            lib().rn_status_string(status).decode())
+
+
+def side(depth: int) -> int:
+    return lib().rn_terrain2d_side(depth)
+
+
+class Context:
+    """rn_context: one per CUDA device (one process per GPU)."""
+
+    def __init__(self, device: int = -1):
+        self._h = C.c_void_p()
+        _check(lib().rn_create(device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().rn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def launches(self) -> int:
+        return int(lib().rn_launch_count(self._h))
+
+    def set_algorithm(self, algo: int):
+        _check(lib().rn_set_algorithm(self._h, algo))
+
+    # -- raw pointer form (what the C ABI takes) ---------------------------------------
+    def terrain2d_ptr(self, p: Params, ptr: int, *, window: Window | None = None, pitch_elems: int = 0,
+                      dst_is_device: bool = True, stream: int = 0, want_volcano_pos: bool = False):
+        vpos = (C.c_float * 3)() if want_volcano_pos else None
+        _check(lib().rn_terrain2d(self._h, C.byref(p), C.byref(window) if window is not None else None,
+                                  C.c_void_p(ptr), pitch_elems, 1 if dst_is_device else 0,
+                                  C.c_void_p(stream) if stream else None, vpos))
+        return tuple(vpos) if want_volcano_pos else None
+
+    def terrain2d_batch_ptr(self, p: Params, seeds, ptr: int, *, tile_stride_elems: int = 0,
+                            dst_is_device: bool = True, stream: int = 0):
+        arr = (C.c_uint32 * len(seeds))(*[int(s) & 0xFFFFFFFF for s in seeds])
+        _check(lib().rn_terrain2d_batch(self._h, C.byref(p), arr, len(seeds), C.c_void_p(ptr), tile_stride_elems,
+                                        1 if dst_is_device else 0, C.c_void_p(stream) if stream else None))
+
+    # -- numpy conveniences (host destination) -----------------------------------------
+    def terrain2d_host(self, p: Params, window: Window | None = None, want_volcano_pos: bool = False):
+        s = side(p.depth)
+        ni, nj = (window.ni, window.nj) if window is not None else (s, s)
+        out = np.empty((ni, nj, 4), np.float32)
+        vp = self.terrain2d_ptr(p, out.ctypes.data, window=window, dst_is_device=False,
+                                want_volcano_pos=want_volcano_pos)
+        return (out, vp) if want_volcano_pos else out
+
+    def terrain2d_batch_host(self, p: Params, seeds):
+        s = side(p.depth)
+        out = np.empty((len(seeds), s, s, 4), np.float32)
+        self.terrain2d_batch_ptr(p, seeds, out.ctypes.data, dst_is_device=False)
+        return out
+
+    def lcg_draws_host(self, seed: int, first: int, n: int) -> np.ndarray:
+        out = np.empty(n, np.uint16)
+        _check(lib().rn_lcg_draws_device(self._h, seed & 0xFFFFFFFF, first, n, C.c_void_p(out.ctypes.data), 0, None))
+        return out

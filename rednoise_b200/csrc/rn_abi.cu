@@ -1,0 +1,359 @@
+// rn_abi.cu -- the extern "C" boundary declared in include/rednoise.h.
+//
+// Replaces the field-synthesis half of Terrain::Terrain (renderEngine/source/
+// Terrain.cpp:44-88).  Host logic only: parameter validation, scratch ownership,
+// algorithm dispatch, window extraction, host<->device copies.  There is no CPU
+// implementation behind any compute entry point.
+#include "../../include/rednoise.h"
+#include "rn_kernels.h"
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <new>
+
+using namespace rn;
+
+struct rn_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int algo = 0;
+  uint64_t launches = 0;
+  int sm_count = 0;
+  // grow-only scratch
+  void* field = nullptr;   size_t field_bytes = 0;    // full-field staging when dst is a window / host memory
+  void* plane = nullptr;   size_t plane_bytes = 0;    // algorithm 1: offset plane; algorithm 2: coarse grids
+  void* small = nullptr;   size_t small_bytes = 0;    // staging for rn_lcg_draws_device with a host dst
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const char* what)
+{
+  g_last_error = what ? what : "";
+  return status;
+}
+int fail_cuda(cudaError_t e, const char* where)
+{
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+  g_last_error = buf;
+  return (e == cudaErrorMemoryAllocation) ? RN_ERR_OOM : RN_ERR_CUDA;
+}
+#define RN_CUDA(call)                                    \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+  } while (0)
+
+int check_params(const rn_params* p)
+{
+  if (!p) return fail(RN_ERR_BAD_PARAM, "params is NULL");
+  if (p->depth < RN_MIN_DEPTH || p->depth > RN_MAX_DEPTH) return fail(RN_ERR_BAD_PARAM, "depth out of range [3,14]");
+  if (p->lacunarity != 2) return fail(RN_ERR_UNSUPPORTED, "only lacunarity 2 is supported (the reference halves the step, Terrain.cpp:81)");
+  if (!(p->persistence > 0.0f) || !(p->persistence <= 1.0f)) return fail(RN_ERR_BAD_PARAM, "persistence must be in (0,1]");
+  if (!(p->feature_scale != 0.0f)) return fail(RN_ERR_BAD_PARAM, "feature_scale must be non-zero");
+  return RN_OK;
+}
+
+Law law_of(const rn_params* p)
+{
+  Law l;
+  l.amplitude = p->amplitude;
+  l.sideways_scale = p->sideways_scale;
+  l.radiosity_strength = p->radiosity_strength;
+  l.amplitude_variation = p->amplitude_variation;
+  l.band_hi = 3.0f / p->feature_scale;  // Terrain.cpp:191,235
+  l.band_lo = 0.5f / p->feature_scale;
+  l.bulgy = p->bulgy_rocks != 0;
+  return l;
+}
+
+int ensure(void** buf, size_t* have, size_t want)
+{
+  if (*have >= want) return RN_OK;
+  if (*buf) {
+    cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+  }
+  cudaError_t e = cudaMalloc(buf, want);
+  if (e != cudaSuccess) {
+    *buf = nullptr;
+    return fail_cuda(e, "cudaMalloc(scratch)");
+  }
+  *have = want;
+  return RN_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev)
+  {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Synthesize the full (W+1)^2 field of `p` into device memory g (row pitch = pitch elements).
+int synth_full(rn_context* ctx, const rn_params* p, Elem* g, size_t pitch, cudaStream_t stream)
+{
+  const int W = 1 << p->depth;
+  const Law law = law_of(p);
+  int st = ensure(&ctx->plane, &ctx->plane_bytes, sizeof(float) * pitch * (size_t)(W + 1));
+  if (st != RN_OK) return st;
+  RN_CUDA(levelsync_generate(g, (float*)ctx->plane, pitch, p->depth, p->depth - 2, law, p->persistence, p->seed, stream, &ctx->launches));
+  return RN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rn_version(void) { return RN_VERSION; }
+const char* rn_last_error_string(void) { return g_last_error.c_str(); }
+
+const char* rn_status_string(int status)
+{
+  switch (status) {
+    case RN_OK: return "ok";
+    case RN_ERR_BAD_PARAM: return "bad parameter";
+    case RN_ERR_UNSUPPORTED: return "unsupported parameter value";
+    case RN_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required)";
+    case RN_ERR_CUDA: return "CUDA error";
+    case RN_ERR_OOM: return "out of device memory";
+    default: return "unknown status";
+  }
+}
+
+int rn_params_default(rn_params* p)
+{
+  if (!p) return fail(RN_ERR_BAD_PARAM, "params is NULL");
+  p->seed = 12345u;           // the reference seeds from time(NULL) (Terrain.cpp:58)
+  p->depth = 12;              // Core.cpp:63 (Release)
+  p->amplitude = 0.2f;        // Core.cpp:65
+  p->size = 500.0f;           // Core.cpp:65
+  p->persistence = 0.5f;      // Terrain.cpp:186,231: displacement ~ step/maxWidth
+  p->lacunarity = 2;          // Terrain.cpp:81
+  p->sideways_scale = 0.5f;   // Terrain.cpp:142
+  p->radiosity_strength = 0.5f;  // Terrain.cpp:143
+  p->feature_scale = 80.0f;   // Terrain.cpp:169
+  p->amplitude_variation = 0.5f;  // Terrain.cpp:170
+  p->bulgy_rocks = 1;         // Terrain.cpp:189
+  p->apply_volcano = 1;       // Terrain.cpp:88
+  return RN_OK;
+}
+
+int rn_terrain2d_side(int depth)
+{
+  if (depth < RN_MIN_DEPTH || depth > RN_MAX_DEPTH) return -1;
+  return (1 << depth) + 1;
+}
+
+uint64_t rn_terrain2d_draw_count(int depth)
+{
+  if (depth < RN_MIN_DEPTH || depth > 30) return 0;
+  uint64_t total = 0;
+  for (int l = 0; l < depth - 2; l++) {
+    const uint64_t n = 4ull << l;
+    total += 3 * n * n + 2 * n;  // n^2 generateSquare + 2n(n+1) generateDiamond calls (Terrain.cpp:66-80)
+  }
+  return total;
+}
+
+uint64_t rn_terrain2d_call_index(int depth, int i, int j)
+{
+  if (depth < RN_MIN_DEPTH || depth > 30) return UINT64_MAX;
+  const int W = 1 << depth;
+  if (i < 0 || j < 0 || i > W || j > W) return UINT64_MAX;
+  // The level that creates (i,j) is fixed by the lowest set bit of i|j.
+  const unsigned low = (unsigned)(i | j);
+  if (low == 0) return UINT64_MAX;
+  const int tz = __builtin_ctz(low);  // created at half-step h = 1<<tz
+  const int level = depth - 3 - tz;   // s = 2h = W >> (level+2)
+  if (level < 0) return UINT64_MAX;   // multiples of W/4: never displaced
+  uint64_t base = 0;
+  for (int l = 0; l < level; l++) {
+    const uint64_t n = 4ull << l;
+    base += 3 * n * n + 2 * n;
+  }
+  const uint64_t n = 4ull << level;
+  const int s = 2 << tz;
+  const uint64_t qi = (uint64_t)(i / s), qj = (uint64_t)(j / s);
+  const bool io = (i % s) != 0, jo = (j % s) != 0;
+  if (io && jo) return base + qi * n + qj;                      // generateSquare  (Terrain.cpp:66-68)
+  if (!io) return base + n * n + qi * n + qj;                   // generateDiamond loop 1 (:75-77)
+  return base + n * n + n * (n + 1) + qi * (n + 1) + qj;        // generateDiamond loop 2 (:78-80)
+}
+
+uint32_t rn_lcg_state_after(uint32_t seed, uint64_t k) { return lcg_state_after(seed, k); }
+uint32_t rn_lcg_draw(uint32_t seed, uint64_t k) { return lcg_draw_from_state(lcg_state_after(seed, k + 1)); }
+
+int rn_create(int device, rn_context** out_ctx)
+{
+  if (!out_ctx) return fail(RN_ERR_BAD_PARAM, "out_ctx is NULL");
+  *out_ctx = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(RN_ERR_NO_DEVICE, "no CUDA device visible; rednoise_b200 has no CPU fallback");
+  }
+  if (device < 0) RN_CUDA(cudaGetDevice(&device));
+  if (device >= count) return fail(RN_ERR_BAD_PARAM, "device index out of range");
+  cudaDeviceProp prop;
+  RN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(RN_ERR_NO_DEVICE, "device is not sm_100 (the library ships sm_100a code only)");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  rn_context* ctx = new (std::nothrow) rn_context();
+  if (!ctx) return fail(RN_ERR_OOM, "host allocation failed");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return fail_cuda(e, "cudaStreamCreateWithFlags");
+  }
+  *out_ctx = ctx;
+  return RN_OK;
+}
+
+int rn_destroy(rn_context* ctx)
+{
+  if (!ctx) return RN_OK;
+  DeviceGuard guard(ctx->device);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  cudaFree(ctx->field);
+  cudaFree(ctx->plane);
+  cudaFree(ctx->small);
+  delete ctx;
+  return RN_OK;
+}
+
+uint64_t rn_launch_count(const rn_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int rn_set_algorithm(rn_context* ctx, int algo)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  if (algo < 0 || algo > 2) return fail(RN_ERR_BAD_PARAM, "algorithm must be 0 (auto), 1 (level-synchronous) or 2 (fused tiles)");
+  ctx->algo = algo;
+  return RN_OK;
+}
+
+int rn_terrain2d(rn_context* ctx, const rn_params* p, const rn_window* win, rn_element* dst, size_t pitch_elems,
+                 int dst_is_device, void* stream_v, float* volcano_pos)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  int st = check_params(p);
+  if (st != RN_OK) return st;
+  if (!dst) return fail(RN_ERR_BAD_PARAM, "dst is NULL");
+  const int W = 1 << p->depth, side = W + 1;
+  rn_window w{0, 0, side, side};
+  if (win) w = *win;
+  if (w.i0 < 0 || w.j0 < 0 || w.ni <= 0 || w.nj <= 0 || w.i0 > side - w.ni || w.j0 > side - w.nj)
+    return fail(RN_ERR_BAD_PARAM, "window does not lie inside the (W+1)x(W+1) lattice");
+  if (pitch_elems == 0) pitch_elems = (size_t)w.nj;
+  if (pitch_elems < (size_t)w.nj) return fail(RN_ERR_BAD_PARAM, "pitch_elems < nj");
+  if (volcano_pos && stream_v && dst_is_device)
+    return fail(RN_ERR_BAD_PARAM, "volcano_pos requires a blocking call (stream == NULL or host dst)");
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+  const bool blocking = !(stream_v && dst_is_device);
+
+  const bool whole = (w.i0 == 0 && w.j0 == 0 && w.ni == side && w.nj == side);
+  const bool in_place = whole && dst_is_device && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
+  Elem* g;
+  size_t gpitch;
+  if (in_place) {
+    g = reinterpret_cast<Elem*>(dst);
+    gpitch = pitch_elems;
+  } else {
+    st = ensure(&ctx->field, &ctx->field_bytes, sizeof(Elem) * (size_t)side * (size_t)side);
+    if (st != RN_OK) return st;
+    g = reinterpret_cast<Elem*>(ctx->field);
+    gpitch = (size_t)side;
+  }
+  st = synth_full(ctx, p, g, gpitch, stream);
+  if (st != RN_OK) return st;
+  if (p->apply_volcano) {
+    // only the requested window needs the epilogue (plus the centre sample for volcano_pos)
+    Elem* wg = g + (size_t)w.i0 * gpitch + (size_t)w.j0;
+    RN_CUDA(volcano_apply(wg, gpitch, p->depth, w.i0, w.j0, w.ni, w.nj, p->amplitude, stream, &ctx->launches));
+  }
+  if (!in_place) {
+    const Elem* src = g + (size_t)w.i0 * gpitch + (size_t)w.j0;
+    RN_CUDA(cudaMemcpy2DAsync(dst, pitch_elems * sizeof(Elem), src, gpitch * sizeof(Elem), (size_t)w.nj * sizeof(Elem), (size_t)w.ni,
+                              dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+  }
+  if (volcano_pos) {
+    // Terrain.cpp:140 + :89: volcanoPos = baseArray[W/2][W/2].pos * size
+    const int c = W / 2;
+    Elem centre;
+    const bool inside = (c >= w.i0 && c < w.i0 + w.ni && c >= w.j0 && c < w.j0 + w.nj);
+    if (p->apply_volcano && !inside) {
+      // the centre sample was not covered by the window epilogue: apply it to a private copy
+      RN_CUDA(cudaMemcpyAsync(&centre, g + (size_t)c * gpitch + (size_t)c, sizeof(Elem), cudaMemcpyDeviceToHost, stream));
+      RN_CUDA(cudaStreamSynchronize(stream));
+      centre.y += volcano_height(c, c, W, p->amplitude);
+    } else {
+      RN_CUDA(cudaMemcpyAsync(&centre, g + (size_t)c * gpitch + (size_t)c, sizeof(Elem), cudaMemcpyDeviceToHost, stream));
+      RN_CUDA(cudaStreamSynchronize(stream));
+    }
+    volcano_pos[0] = centre.x * p->size;
+    volcano_pos[1] = centre.y * p->size;
+    volcano_pos[2] = centre.z * p->size;
+  }
+  if (blocking) RN_CUDA(cudaStreamSynchronize(stream));
+  return RN_OK;
+}
+
+int rn_terrain2d_batch(rn_context* ctx, const rn_params* p, const uint32_t* seeds, int ntiles, rn_element* dst,
+                       size_t tile_stride_elems, int dst_is_device, void* stream_v)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  int st = check_params(p);
+  if (st != RN_OK) return st;
+  if (!seeds || !dst) return fail(RN_ERR_BAD_PARAM, "seeds/dst is NULL");
+  if (ntiles < 0) return fail(RN_ERR_BAD_PARAM, "ntiles < 0");
+  const size_t side = (size_t)(1 << p->depth) + 1;
+  if (tile_stride_elems == 0) tile_stride_elems = side * side;
+  if (tile_stride_elems < side * side) return fail(RN_ERR_BAD_PARAM, "tile_stride_elems < side*side");
+  for (int t = 0; t < ntiles; t++) {
+    rn_params q = *p;
+    q.seed = seeds[t];
+    st = rn_terrain2d(ctx, &q, nullptr, dst + (size_t)t * tile_stride_elems, side, dst_is_device, stream_v, nullptr);
+    if (st != RN_OK) return st;
+  }
+  return RN_OK;
+}
+
+int rn_lcg_draws_device(rn_context* ctx, uint32_t seed, uint64_t first, uint64_t n, uint16_t* dst, int dst_is_device, void* stream_v)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  if (!dst && n) return fail(RN_ERR_BAD_PARAM, "dst is NULL");
+  if (n == 0) return RN_OK;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+  if (dst_is_device) {
+    RN_CUDA(lcg_draws(dst, seed, first, n, stream, &ctx->launches));
+    if (!stream_v) RN_CUDA(cudaStreamSynchronize(stream));
+    return RN_OK;
+  }
+  int st = ensure(&ctx->small, &ctx->small_bytes, n * sizeof(uint16_t));
+  if (st != RN_OK) return st;
+  RN_CUDA(lcg_draws((uint16_t*)ctx->small, seed, first, n, stream, &ctx->launches));
+  RN_CUDA(cudaMemcpyAsync(dst, ctx->small, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, stream));
+  RN_CUDA(cudaStreamSynchronize(stream));
+  return RN_OK;
+}
+
+}  // extern "C"

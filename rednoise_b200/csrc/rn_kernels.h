@@ -1,0 +1,22 @@
+// rn_kernels.h -- internal interface between the C ABI (rn_abi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "rn_math.cuh"
+
+namespace rn {
+
+// Algorithm 1 (rn_levelsync.cu): levels [0,nlevels) of a depth-`depth` field in global memory.
+cudaError_t levelsync_generate(Elem* g, float* off, size_t pitch, int depth, int nlevels, const Law& law, float persistence,
+                               uint32_t seed, cudaStream_t stream, uint64_t* launches);
+
+// Epilogues / utilities (rn_util.cu).
+// addVolcano (Terrain.cpp:121-141) over the window [i0,i0+ni) x [j0,j0+nj) of a depth-`depth` field
+// stored at g with row pitch `pitch` (g points at window element (i0,j0)).
+cudaError_t volcano_apply(Elem* g, size_t pitch, int depth, int i0, int j0, int ni, int nj, float amplitude, cudaStream_t stream,
+                          uint64_t* launches);
+// 15-bit draws first..first+n-1 of srand(seed) as uint16.
+cudaError_t lcg_draws(uint16_t* dst, uint32_t seed, uint64_t first, uint64_t n, cudaStream_t stream, uint64_t* launches);
+
+}  // namespace rn

@@ -1,0 +1,181 @@
+"""GPU (B200): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeds (bit-exact: integer draws AND FP32 fields), against the committed reference digests,
+and -- at BASELINE.json's full sizes -- through size-independent properties (window/seam
+exactness, batch == single, algorithm 1 == algorithm 2)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "terrain2d_golden.json")))
+ALGOS = [1, 2]
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def assert_bitwise(got, want, what=""):
+    g, w = bits(got), bits(want)
+    if not np.array_equal(g, w):
+        bad = np.argwhere(g != w)
+        i, j, c = bad[0]
+        raise AssertionError(f"{what}: {len(bad)} of {g.size} words differ; first at (i={i}, j={j}, comp={c}): "
+                             f"got {got[i, j, c]!r} want {want[i, j, c]!r}; "
+                             f"pos words bad={int((g[..., :3] != w[..., :3]).sum())} shade words bad={int((g[..., 3] != w[..., 3]).sum())}")
+
+
+def test_lcg_draws_bit_exact(ctx, oracle):
+    """The integer lattice hash: the device draw stream equals the MSVC LCG everywhere."""
+    for seed, first, n in [(1, 0, 64), (12345, 0, 100003), (777, 16785384 - 50, 50), (0xFFFFFFFF, 2**32 - 5, 37), (5, 3, 1)]:
+        got = ctx.lcg_draws_host(seed, first, n)
+        s = oracle.L.rno_lcg_state_after(seed, first)
+        want = np.empty(n, np.uint16)
+        for k in range(n):
+            s = oracle.L.rno_lcg_next_state(s)
+            want[k] = (s >> 16) & 0x7FFF
+        assert np.array_equal(got, want), (seed, first, n)
+    assert ctx.lcg_draws_host(1, 0, 8).tolist() == [41, 18467, 6334, 26500, 19169, 15724, 11478, 29358]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("depth,seed", [(3, 12345), (4, 1), (5, 5), (6, 12345), (7, 70), (8, 12345), (8, 777), (9, 9), (10, 12345), (11, 3)])
+@pytest.mark.parametrize("volcano", [0, 1])
+def test_field_equals_oracle_bitwise(ctx, rnlib, oracle, algo, depth, seed, volcano):
+    ctx.set_algorithm(algo)
+    p = rnlib.default_params(seed=seed, depth=depth, apply_volcano=volcano)
+    got, vpos = ctx.terrain2d_host(p, want_volcano_pos=True)
+    want, wpos = oracle.terrain2d(oracle_lib.params(seed=seed, depth=depth, apply_volcano=volcano), want_volcano_pos=True)
+    assert_bitwise(got, want, f"algo {algo} depth {depth} seed {seed} volcano {volcano}")
+    assert vpos == wpos
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("entry", GOLD["fields"], ids=lambda e: f"d{e['depth']}-s{e['seed']}")
+def test_field_matches_reference_digests(ctx, rnlib, oracle, algo, entry):
+    """Includes BASELINE config 1 (depth 8) and config 2 (depth 12, 4097^2)."""
+    ctx.set_algorithm(algo)
+    for volc, key in ((0, "fnv64_pre_volcano"), (1, "fnv64_post_volcano")):
+        p = rnlib.default_params(seed=entry["seed"], depth=entry["depth"], apply_volcano=volc)
+        got = ctx.terrain2d_host(p)
+        assert oracle.fnv64(got) == entry[key], (algo, entry["depth"], entry["seed"], volc)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_nondefault_params(ctx, rnlib, oracle, algo):
+    ctx.set_algorithm(algo)
+    kw = dict(persistence=0.6, sideways_scale=0.3, radiosity_strength=0.7, feature_scale=50.0, amplitude_variation=0.25,
+              amplitude=0.35, bulgy_rocks=0)
+    for depth in (5, 8):
+        got = ctx.terrain2d_host(rnlib.default_params(seed=99, depth=depth, apply_volcano=1, **kw))
+        want = oracle.terrain2d(oracle_lib.params(seed=99, depth=depth, apply_volcano=1, **kw))
+        assert_bitwise(got, want, f"non-default params depth {depth}")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_windows_are_seam_exact(ctx, rnlib, oracle, algo):
+    """'grid extent and origin': any sub-window equals the same indices of the full field."""
+    ctx.set_algorithm(algo)
+    depth = 9
+    p = rnlib.default_params(seed=4711, depth=depth, apply_volcano=1)
+    full = oracle.terrain2d(oracle_lib.params(seed=4711, depth=depth, apply_volcano=1))
+    S = (1 << depth) + 1
+    rng = np.random.default_rng(5)
+    wins = [(0, 0, 1, 1), (S - 1, S - 1, 1, 1), (0, 0, S, 1), (0, S - 1, S, 1), (100, 37, 64, 64), (255, 255, 3, 3), (0, 0, 129, S),
+            (384, 0, S - 384, S)]
+    for _ in range(6):
+        i0, j0 = (int(x) for x in rng.integers(0, S - 1, 2))
+        wins.append((i0, j0, int(rng.integers(1, S - i0 + 1)), int(rng.integers(1, S - j0 + 1))))
+    for (i0, j0, ni, nj) in wins:
+        got = ctx.terrain2d_host(p, window=rnlib.Window(i0, j0, ni, nj))
+        assert_bitwise(got, full[i0:i0 + ni, j0:j0 + nj], f"window {(i0, j0, ni, nj)}")
+
+
+def test_bad_arguments(ctx, rnlib):
+    L = rnlib.lib()
+    buf = np.empty((9 * 9, 4), np.float32)
+    p = rnlib.default_params(depth=3)
+    def call(pp, win=None, pitch=0):
+        return L.rn_terrain2d(ctx._h, C.byref(pp), C.byref(win) if win else None, buf.ctypes.data, pitch, 0, None, None)
+    assert call(p) == rnlib.RN_OK
+    assert call(rnlib.default_params(depth=2)) == rnlib.RN_ERR_BAD_PARAM
+    assert call(rnlib.default_params(depth=15)) == rnlib.RN_ERR_BAD_PARAM
+    assert call(rnlib.default_params(depth=3, lacunarity=3)) == rnlib.RN_ERR_UNSUPPORTED
+    assert call(rnlib.default_params(depth=3, persistence=-1.0)) == rnlib.RN_ERR_BAD_PARAM
+    assert call(p, rnlib.Window(0, 0, 10, 9)) == rnlib.RN_ERR_BAD_PARAM
+    assert call(p, rnlib.Window(-1, 0, 2, 2)) == rnlib.RN_ERR_BAD_PARAM
+    assert call(p, rnlib.Window(0, 0, 0, 2)) == rnlib.RN_ERR_BAD_PARAM
+    assert call(p, rnlib.Window(0, 0, 4, 4), pitch=3) == rnlib.RN_ERR_BAD_PARAM
+    assert L.rn_terrain2d(ctx._h, C.byref(p), None, None, 0, 0, None, None) == rnlib.RN_ERR_BAD_PARAM
+    assert L.rn_last_error_string() != b""
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_device_destination_and_pitch(ctx, rnlib, oracle, algo):
+    import torch
+    ctx.set_algorithm(algo)
+    depth = 7
+    S = (1 << depth) + 1
+    want = oracle.terrain2d(oracle_lib.params(seed=8, depth=depth, apply_volcano=1))
+    p = rnlib.default_params(seed=8, depth=depth, apply_volcano=1)
+    # dense, in place
+    d = torch.full((S, S, 4), float("nan"), device="cuda", dtype=torch.float32)
+    ctx.terrain2d_ptr(p, d.data_ptr(), dst_is_device=True)
+    assert_bitwise(d.cpu().numpy(), want, "device dense")
+    # padded pitch, on torch's current stream (asynchronous form)
+    pitch = S + 7
+    d2 = torch.full((S, pitch, 4), -1.0, device="cuda", dtype=torch.float32)
+    ctx.terrain2d_ptr(p, d2.data_ptr(), pitch_elems=pitch, dst_is_device=True, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    h = d2.cpu().numpy()
+    assert_bitwise(h[:, :S], want, "device pitched")
+    assert (h[:, S:] == -1.0).all()
+    # window into a device buffer
+    d3 = torch.zeros((20, 30, 4), device="cuda", dtype=torch.float32)
+    ctx.terrain2d_ptr(p, d3.data_ptr(), window=rnlib.Window(5, 9, 20, 30), dst_is_device=True)
+    assert_bitwise(d3.cpu().numpy(), want[5:25, 9:39], "device window")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_batch_equals_singles(ctx, rnlib, oracle, algo):
+    """BASELINE config 5 in miniature: tile k of a batch == a single run with seed k."""
+    ctx.set_algorithm(algo)
+    depth = 7
+    seeds = [12345 + k for k in range(9)] + [0, 0xFFFFFFFF]
+    p = rnlib.default_params(depth=depth, apply_volcano=1)
+    got = ctx.terrain2d_batch_host(p, seeds)
+    want = oracle.terrain2d_batch(oracle_lib.params(depth=depth, apply_volcano=1), seeds, threads=4)
+    for t in range(len(seeds)):
+        assert_bitwise(got[t], want[t], f"batch tile {t}")
+
+
+def test_algorithms_agree_at_full_size(ctx, rnlib, oracle):
+    """Depth 12 (4097^2) and depth 13: the fused tile path and the level-synchronous path are
+    independent implementations; bitwise equality at sizes the oracle is slow for."""
+    import torch
+    for depth, seed in ((12, 2), (13, 12345)):
+        S = (1 << depth) + 1
+        p = rnlib.default_params(seed=seed, depth=depth, apply_volcano=1)
+        a = torch.empty((S, S, 4), device="cuda", dtype=torch.float32)
+        b = torch.empty((S, S, 4), device="cuda", dtype=torch.float32)
+        ctx.set_algorithm(1)
+        ctx.terrain2d_ptr(p, a.data_ptr(), dst_is_device=True)
+        ctx.set_algorithm(2)
+        ctx.terrain2d_ptr(p, b.data_ptr(), dst_is_device=True)
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), depth
+        del a, b
+
+
+def test_depth12_against_oracle(ctx, rnlib, oracle):
+    """BASELINE config 2 against the oracle itself (about 1 s of CPU)."""
+    ctx.set_algorithm(0)
+    p = rnlib.default_params(seed=31337, depth=12, apply_volcano=1)
+    got = ctx.terrain2d_host(p)
+    want = oracle.terrain2d(oracle_lib.params(seed=31337, depth=12, apply_volcano=1))
+    assert_bitwise(got, want, "depth 12 seed 31337")

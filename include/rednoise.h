@@ -114,6 +114,14 @@ uint64_t rn_launch_count(const rn_context* ctx);
  * global-memory kernels (one launch set per level), 2 = fused tile kernels. */
 int rn_set_algorithm(rn_context* ctx, int algo);
 
+/* Stage profiling (algorithm 2): when enabled, every launch of the stage chain is bracketed by
+ * CUDA events on the launching stream; rn_last_stage_times() then synchronizes and returns the
+ * device time in ms of each launch of the most recent rn_terrain2d / rn_terrain2d_batch call
+ * (ms[0..n-1], coarse to fine; the last one is the kernel that writes the output).  Returns the
+ * number of launches, or a negative status.  Meant for roofline reporting, not for timed runs. */
+int rn_set_profiling(rn_context* ctx, int enable);
+int rn_last_stage_times(rn_context* ctx, float* ms, int cap);
+
 /* ---- the hot path --------------------------------------------------------- */
 /* Synthesize the field of Terrain(depth,size,amplitude) with srand(p->seed).
  *   win          NULL = whole (W+1)x(W+1) grid

@@ -21,7 +21,7 @@ RN_MIN_DEPTH, RN_MAX_DEPTH = 3, 14
 SYMBOLS = [
     "rn_version", "rn_last_error_string", "rn_status_string", "rn_params_default", "rn_terrain2d_side",
     "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
-    "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device",
+    "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device",
 ]
 
 
@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
     L.rn_launch_count.restype = u64
     L.rn_launch_count.argtypes = [vp]
     L.rn_set_algorithm.argtypes = [vp, i32]
+    L.rn_set_profiling.argtypes = [vp, i32]
+    L.rn_last_stage_times.argtypes = [vp, C.POINTER(C.c_float), i32]
     L.rn_terrain2d.argtypes = [vp, C.POINTER(Params), C.POINTER(Window), vp, sz, i32, vp, C.POINTER(C.c_float)]
     L.rn_terrain2d_batch.argtypes = [vp, C.POINTER(Params), C.POINTER(u32), i32, vp, sz, i32, vp]
     L.rn_lcg_draws_device.argtypes = [vp, u32, u64, u64, vp, i32, vp]
@@ -134,6 +136,17 @@ class Context:
 
     def set_algorithm(self, algo: int):
         _check(lib().rn_set_algorithm(self._h, algo))
+
+    def set_profiling(self, on: bool):
+        _check(lib().rn_set_profiling(self._h, 1 if on else 0))
+
+    def last_stage_times(self):
+        """Device ms of each launch of the last call (coarse to fine); needs set_profiling(True)."""
+        buf = (C.c_float * 8)()
+        n = lib().rn_last_stage_times(self._h, buf, 8)
+        if n < 0:
+            _check(-n)
+        return [float(buf[k]) for k in range(n)]
 
     # -- raw pointer form (what the C ABI takes) ---------------------------------------
     def terrain2d_ptr(self, p: Params, ptr: int, *, window: Window | None = None, pitch_elems: int = 0,

@@ -22,7 +22,11 @@ struct rn_context {
   // grow-only scratch
   void* field = nullptr;   size_t field_bytes = 0;    // full-field staging when dst is a window / host memory
   void* plane = nullptr;   size_t plane_bytes = 0;    // algorithm 1: offset plane; algorithm 2: coarse grids
-  void* small = nullptr;   size_t small_bytes = 0;    // staging for rn_lcg_draws_device with a host dst
+  void* small = nullptr;   size_t small_bytes = 0;    // staging for rn_lcg_draws_device with a host dst; batch seeds
+  // stage profiling
+  int profiling = 0;
+  cudaEvent_t ev[9] = {};
+  int ev_stages = 0;
 };
 
 namespace {
@@ -98,14 +102,31 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// Synthesize the full (W+1)^2 field of `p` into device memory g (row pitch = pitch elements).
-int synth_full(rn_context* ctx, const rn_params* p, Elem* g, size_t pitch, cudaStream_t stream)
+// Algorithm 1: the full (W+1)^2 field of `p` into device memory g (row pitch = pitch elements).
+int synth_full_levelsync(rn_context* ctx, const rn_params* p, Elem* g, size_t pitch, cudaStream_t stream)
 {
   const int W = 1 << p->depth;
   const Law law = law_of(p);
   int st = ensure(&ctx->plane, &ctx->plane_bytes, sizeof(float) * pitch * (size_t)(W + 1));
   if (st != RN_OK) return st;
   RN_CUDA(levelsync_generate(g, (float*)ctx->plane, pitch, p->depth, p->depth - 2, law, p->persistence, p->seed, stream, &ctx->launches));
+  return RN_OK;
+}
+
+// Algorithm 2: the window `w` of `nfields` fields (seeds on the device, or p->seed) straight into device memory.
+int synth_window_fused(rn_context* ctx, const rn_params* p, const rn_window& w, Elem* g, size_t pitch, size_t field_stride,
+                       const uint32_t* dev_seeds, int nfields, cudaStream_t stream)
+{
+  const Law law = law_of(p);
+  const size_t need = fused_scratch_bytes(p->depth, nfields);
+  int st = ensure(&ctx->plane, &ctx->plane_bytes, need ? need : 256);
+  if (st != RN_OK) return st;
+  if (ctx->profiling && !ctx->ev[0])
+    for (int k = 0; k < 9; k++) RN_CUDA(cudaEventCreate(&ctx->ev[k]));
+  ctx->ev_stages = 0;
+  RN_CUDA(fused_generate(g, pitch, field_stride, p->depth, w.i0, w.j0, w.ni, w.nj, law, p->persistence, p->seed, dev_seeds, nfields,
+                         p->apply_volcano != 0, p->amplitude, ctx->plane, stream, &ctx->launches, ctx->profiling ? ctx->ev : nullptr,
+                         ctx->profiling ? &ctx->ev_stages : nullptr));
   return RN_OK;
 }
 
@@ -230,6 +251,8 @@ int rn_destroy(rn_context* ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
   }
+  for (int k = 0; k < 9; k++)
+    if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
   cudaFree(ctx->field);
   cudaFree(ctx->plane);
   cudaFree(ctx->small);
@@ -245,6 +268,26 @@ int rn_set_algorithm(rn_context* ctx, int algo)
   if (algo < 0 || algo > 2) return fail(RN_ERR_BAD_PARAM, "algorithm must be 0 (auto), 1 (level-synchronous) or 2 (fused tiles)");
   ctx->algo = algo;
   return RN_OK;
+}
+
+int rn_set_profiling(rn_context* ctx, int enable)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  ctx->profiling = enable != 0;
+  ctx->ev_stages = 0;
+  return RN_OK;
+}
+
+int rn_last_stage_times(rn_context* ctx, float* ms, int cap)
+{
+  if (!ctx || !ms || cap <= 0) return -fail(RN_ERR_BAD_PARAM, "ctx/ms is NULL");
+  if (!ctx->profiling || ctx->ev_stages == 0) return 0;
+  DeviceGuard guard(ctx->device);
+  if (cudaEventSynchronize(ctx->ev[ctx->ev_stages]) != cudaSuccess) return -fail(RN_ERR_CUDA, "cudaEventSynchronize failed");
+  int n = ctx->ev_stages < cap ? ctx->ev_stages : cap;
+  for (int k = 0; k < n; k++)
+    if (cudaEventElapsedTime(&ms[k], ctx->ev[k], ctx->ev[k + 1]) != cudaSuccess) return -fail(RN_ERR_CUDA, "cudaEventElapsedTime failed");
+  return n;
 }
 
 int rn_terrain2d(rn_context* ctx, const rn_params* p, const rn_window* win, rn_element* dst, size_t pitch_elems,
@@ -268,45 +311,76 @@ int rn_terrain2d(rn_context* ctx, const rn_params* p, const rn_window* win, rn_e
   cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
   const bool blocking = !(stream_v && dst_is_device);
 
-  const bool whole = (w.i0 == 0 && w.j0 == 0 && w.ni == side && w.nj == side);
-  const bool in_place = whole && dst_is_device && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
-  Elem* g;
-  size_t gpitch;
-  if (in_place) {
-    g = reinterpret_cast<Elem*>(dst);
-    gpitch = pitch_elems;
-  } else {
-    st = ensure(&ctx->field, &ctx->field_bytes, sizeof(Elem) * (size_t)side * (size_t)side);
+  const bool aligned = dst_is_device && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
+  const int c = W / 2;
+  const bool centre_inside = (c >= w.i0 && c < w.i0 + w.ni && c >= w.j0 && c < w.j0 + w.nj);
+  Elem centre{};
+  if (ctx->algo == 1) {
+    // ---- algorithm 1: level-synchronous, whole field in global memory, then window extraction ----
+    const bool whole = (w.i0 == 0 && w.j0 == 0 && w.ni == side && w.nj == side);
+    const bool in_place = whole && aligned;
+    Elem* g;
+    size_t gpitch;
+    if (in_place) {
+      g = reinterpret_cast<Elem*>(dst);
+      gpitch = pitch_elems;
+    } else {
+      st = ensure(&ctx->field, &ctx->field_bytes, sizeof(Elem) * (size_t)side * (size_t)side);
+      if (st != RN_OK) return st;
+      g = reinterpret_cast<Elem*>(ctx->field);
+      gpitch = (size_t)side;
+    }
+    st = synth_full_levelsync(ctx, p, g, gpitch, stream);
     if (st != RN_OK) return st;
-    g = reinterpret_cast<Elem*>(ctx->field);
-    gpitch = (size_t)side;
-  }
-  st = synth_full(ctx, p, g, gpitch, stream);
-  if (st != RN_OK) return st;
-  if (p->apply_volcano) {
-    // only the requested window needs the epilogue (plus the centre sample for volcano_pos)
-    Elem* wg = g + (size_t)w.i0 * gpitch + (size_t)w.j0;
-    RN_CUDA(volcano_apply(wg, gpitch, p->depth, w.i0, w.j0, w.ni, w.nj, p->amplitude, stream, &ctx->launches));
-  }
-  if (!in_place) {
-    const Elem* src = g + (size_t)w.i0 * gpitch + (size_t)w.j0;
-    RN_CUDA(cudaMemcpy2DAsync(dst, pitch_elems * sizeof(Elem), src, gpitch * sizeof(Elem), (size_t)w.nj * sizeof(Elem), (size_t)w.ni,
-                              dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+    if (p->apply_volcano) {
+      Elem* wg = g + (size_t)w.i0 * gpitch + (size_t)w.j0;
+      RN_CUDA(volcano_apply(wg, gpitch, p->depth, w.i0, w.j0, w.ni, w.nj, p->amplitude, stream, &ctx->launches));
+    }
+    if (!in_place) {
+      const Elem* src = g + (size_t)w.i0 * gpitch + (size_t)w.j0;
+      RN_CUDA(cudaMemcpy2DAsync(dst, pitch_elems * sizeof(Elem), src, gpitch * sizeof(Elem), (size_t)w.nj * sizeof(Elem), (size_t)w.ni,
+                                dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+    }
+    if (volcano_pos) {
+      RN_CUDA(cudaMemcpyAsync(&centre, g + (size_t)c * gpitch + (size_t)c, sizeof(Elem), cudaMemcpyDeviceToHost, stream));
+      RN_CUDA(cudaStreamSynchronize(stream));
+      if (p->apply_volcano && !centre_inside) centre.y += volcano_height(c, c, W, p->amplitude);
+    }
+  } else {
+    // ---- algorithm 2 (default): fused tiles write the window directly ----
+    Elem* g;
+    size_t gpitch;
+    if (aligned) {
+      g = reinterpret_cast<Elem*>(dst);
+      gpitch = pitch_elems;
+    } else {
+      st = ensure(&ctx->field, &ctx->field_bytes, sizeof(Elem) * (size_t)w.ni * (size_t)w.nj);
+      if (st != RN_OK) return st;
+      g = reinterpret_cast<Elem*>(ctx->field);
+      gpitch = (size_t)w.nj;
+    }
+    st = synth_window_fused(ctx, p, w, g, gpitch, 0, nullptr, 1, stream);
+    if (st != RN_OK) return st;
+    if (!aligned)
+      RN_CUDA(cudaMemcpy2DAsync(dst, pitch_elems * sizeof(Elem), g, gpitch * sizeof(Elem), (size_t)w.nj * sizeof(Elem), (size_t)w.ni,
+                                dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+    if (volcano_pos) {
+      if (centre_inside) {
+        RN_CUDA(cudaMemcpyAsync(&centre, g + (size_t)(c - w.i0) * gpitch + (size_t)(c - w.j0), sizeof(Elem), cudaMemcpyDeviceToHost, stream));
+      } else {
+        // the centre sample lies outside the window: synthesize it alone (a handful of tiles)
+        st = ensure(&ctx->small, &ctx->small_bytes, 256);
+        if (st != RN_OK) return st;
+        const rn_window cw{c, c, 1, 1};
+        st = synth_window_fused(ctx, p, cw, reinterpret_cast<Elem*>(ctx->small), 1, 0, nullptr, 1, stream);
+        if (st != RN_OK) return st;
+        RN_CUDA(cudaMemcpyAsync(&centre, ctx->small, sizeof(Elem), cudaMemcpyDeviceToHost, stream));
+      }
+      RN_CUDA(cudaStreamSynchronize(stream));
+    }
   }
   if (volcano_pos) {
     // Terrain.cpp:140 + :89: volcanoPos = baseArray[W/2][W/2].pos * size
-    const int c = W / 2;
-    Elem centre;
-    const bool inside = (c >= w.i0 && c < w.i0 + w.ni && c >= w.j0 && c < w.j0 + w.nj);
-    if (p->apply_volcano && !inside) {
-      // the centre sample was not covered by the window epilogue: apply it to a private copy
-      RN_CUDA(cudaMemcpyAsync(&centre, g + (size_t)c * gpitch + (size_t)c, sizeof(Elem), cudaMemcpyDeviceToHost, stream));
-      RN_CUDA(cudaStreamSynchronize(stream));
-      centre.y += volcano_height(c, c, W, p->amplitude);
-    } else {
-      RN_CUDA(cudaMemcpyAsync(&centre, g + (size_t)c * gpitch + (size_t)c, sizeof(Elem), cudaMemcpyDeviceToHost, stream));
-      RN_CUDA(cudaStreamSynchronize(stream));
-    }
     volcano_pos[0] = centre.x * p->size;
     volcano_pos[1] = centre.y * p->size;
     volcano_pos[2] = centre.z * p->size;
@@ -326,12 +400,46 @@ int rn_terrain2d_batch(rn_context* ctx, const rn_params* p, const uint32_t* seed
   const size_t side = (size_t)(1 << p->depth) + 1;
   if (tile_stride_elems == 0) tile_stride_elems = side * side;
   if (tile_stride_elems < side * side) return fail(RN_ERR_BAD_PARAM, "tile_stride_elems < side*side");
-  for (int t = 0; t < ntiles; t++) {
-    rn_params q = *p;
-    q.seed = seeds[t];
-    st = rn_terrain2d(ctx, &q, nullptr, dst + (size_t)t * tile_stride_elems, side, dst_is_device, stream_v, nullptr);
-    if (st != RN_OK) return st;
+  if (ntiles == 0) return RN_OK;
+  if (ctx->algo == 1) {
+    for (int t = 0; t < ntiles; t++) {
+      rn_params q = *p;
+      q.seed = seeds[t];
+      st = rn_terrain2d(ctx, &q, nullptr, dst + (size_t)t * tile_stride_elems, side, dst_is_device, stream_v, nullptr);
+      if (st != RN_OK) return st;
+    }
+    return RN_OK;
   }
+  // algorithm 2: one launch chain per chunk of fields, blockIdx.z = field
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+  const bool direct = dst_is_device && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
+  const size_t field_bytes = side * side * sizeof(Elem);
+  // chunk so that staging (host destination) and the intermediate grids stay bounded
+  size_t chunk = direct ? 4096 : ((size_t)1 << 30) / field_bytes;
+  if (chunk < 1) chunk = 1;
+  if (chunk > 32768) chunk = 32768;
+  st = ensure(&ctx->small, &ctx->small_bytes, sizeof(uint32_t) * (size_t)ntiles);
+  if (st != RN_OK) return st;
+  RN_CUDA(cudaMemcpyAsync(ctx->small, seeds, sizeof(uint32_t) * (size_t)ntiles, cudaMemcpyHostToDevice, stream));
+  const rn_window w{0, 0, (int)side, (int)side};
+  for (size_t t0 = 0; t0 < (size_t)ntiles; t0 += chunk) {
+    const int nf = (int)(((size_t)ntiles - t0 < chunk) ? (size_t)ntiles - t0 : chunk);
+    const uint32_t* dseeds = reinterpret_cast<const uint32_t*>(ctx->small) + t0;
+    if (direct) {
+      st = synth_window_fused(ctx, p, w, reinterpret_cast<Elem*>(dst + t0 * tile_stride_elems), side, tile_stride_elems, dseeds, nf, stream);
+      if (st != RN_OK) return st;
+    } else {
+      st = ensure(&ctx->field, &ctx->field_bytes, field_bytes * (size_t)nf);
+      if (st != RN_OK) return st;
+      st = synth_window_fused(ctx, p, w, reinterpret_cast<Elem*>(ctx->field), side, side * side, dseeds, nf, stream);
+      if (st != RN_OK) return st;
+      RN_CUDA(cudaMemcpy2DAsync(dst + t0 * tile_stride_elems, tile_stride_elems * sizeof(Elem), ctx->field, field_bytes, field_bytes, (size_t)nf,
+                                dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+    }
+  }
+  if (!(stream_v && dst_is_device)) RN_CUDA(cudaStreamSynchronize(stream));
   return RN_OK;
 }
 

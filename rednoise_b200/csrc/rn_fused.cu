@@ -1,0 +1,96 @@
+// rn_fused.cu -- algorithm 2: the fused tile kernels (rn_tile.cuh) and their stage chain.
+//
+// Replaces the level loop of Terrain::Terrain (Terrain.cpp:60-82) + addVolcano (:88) with
+// 2-4 launches per field: each stage refines a complete coarse grid by 2-4 levels per CTA in
+// shared memory and stores finished 64x64 tiles with 128-bit coalesced writes.  Intermediate
+// grids (<= 1/64 of the output) stay L2-resident between stages.
+#include "rn_kernels.h"
+#include "rn_plan.h"
+
+namespace rn {
+
+namespace {
+
+constexpr int kStageThreads = 512;
+
+template <int L, int T, int NT, int P>
+__device__ __forceinline__ void run_phases(const StageParams& sp, const TileCtx& cx, float* sm)
+{
+  Tile<L, T, NT>::template phase<P>(sp, cx, sm, (int)threadIdx.x);
+  if constexpr (P + 1 < Tile<L, T, NT>::NPHASES) {
+    __syncthreads();
+    run_phases<L, T, NT, P + 1>(sp, cx, sm);
+  }
+}
+
+template <int L, int T, int NT>
+__global__ void __launch_bounds__(NT, (TileGeo<L, T>::BYTES <= 113 * 1024) ? 2 : 1) k_stage(const __grid_constant__ StageParams sp)
+{
+  extern __shared__ __align__(16) float sm[];
+  TileCtx cx;
+  cx.I0 = (sp.tile_i0 + (int)blockIdx.y) * T;
+  cx.J0 = (sp.tile_j0 + (int)blockIdx.x) * T;
+  const unsigned f = blockIdx.z;
+  cx.seed = sp.seeds ? sp.seeds[f] : sp.seed;
+  cx.gin = sp.gin ? sp.gin + (size_t)f * sp.gin_field_stride : nullptr;
+  cx.gout = sp.gout + (size_t)f * sp.gout_field_stride;
+  run_phases<L, T, NT, 0>(sp, cx, sm);
+}
+
+template <int L>
+cudaError_t launch_stage(const StageParams& sp, dim3 grid, cudaStream_t stream)
+{
+  using G = TileGeo<L, kTile>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64 && !configured[dev]) {
+    e = cudaFuncSetAttribute(k_stage<L, kTile, kStageThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  k_stage<L, kTile, kStageThreads><<<grid, kStageThreads, G::BYTES, stream>>>(sp);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t fused_scratch_bytes(int depth, int nfields) { return chain_scratch_bytes(depth, nfields); }
+
+// Synthesizes the window [i0,i0+ni) x [j0,j0+nj) of `nfields` depth-`depth` fields.
+//   dst     element (i0, j0) of field 0; row pitch `pitch`, field stride `field_stride` (elements)
+//   seeds   device pointer to nfields seeds, or nullptr (then every field uses `seed`)
+//   scratch fused_scratch_bytes(depth, nfields) bytes of device memory
+cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int depth, int i0, int j0, int ni, int nj, const Law& law,
+                           float persistence, uint32_t seed, const uint32_t* seeds, int nfields, int volcano, float amplitude,
+                           void* scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events, int* nstages)
+{
+  StageLaunch chain[kMaxStages];
+  const int ns = build_chain(chain, depth, i0, j0, ni, nj, reinterpret_cast<E4*>(dst), pitch, field_stride, scratch, nfields, law,
+                             persistence, seed, seeds, volcano, amplitude);
+  if (nstages) *nstages = ns;
+  if (events) {
+    cudaError_t e0 = cudaEventRecord(events[0], stream);
+    if (e0 != cudaSuccess) return e0;
+  }
+  for (int k = 0; k < ns; k++) {
+    const dim3 grid(chain[k].gx, chain[k].gy, (unsigned)nfields);
+    cudaError_t e;
+    switch (chain[k].L) {
+      case 1: e = launch_stage<1>(chain[k].sp, grid, stream); break;
+      case 2: e = launch_stage<2>(chain[k].sp, grid, stream); break;
+      case 3: e = launch_stage<3>(chain[k].sp, grid, stream); break;
+      default: e = launch_stage<4>(chain[k].sp, grid, stream); break;
+    }
+    if (e != cudaSuccess) return e;
+    if (events) {
+      e = cudaEventRecord(events[k + 1], stream);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  if (launches) *launches += (uint64_t)ns;
+  return cudaSuccess;
+}
+
+}  // namespace rn

@@ -1,0 +1,131 @@
+// tests/host_replay/rn_replay.cpp -- TEST SCAFFOLDING ONLY (never linked into the product).
+//
+// Replays the fused tile algorithm (rednoise_b200/csrc/rn_tile.cuh + rn_plan.h, the very code
+// the CUDA kernels are compiled from) on the CPU: every phase is executed for every thread
+// index of every tile, with the barrier between phases modelled by finishing a phase for all
+// threads before the next one starts.  This validates tiling, halos, windows, boundary rules,
+// RNG indexing and shade ordering against the oracle in a container without a GPU.  With
+// `poison` the tile's "shared memory" is filled with signalling garbage (NaN) first, proving
+// that no out-of-cone value ever reaches an output sample, and every shared-memory index is
+// range-checked by construction (the buffer is exactly TileGeo::WORDS long inside guard pages
+// of NaN that are verified untouched).
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../include/rednoise.h"
+#include "../../rednoise_b200/csrc/rn_plan.h"
+
+using namespace rn;
+
+namespace {
+
+constexpr int NT = 512;
+constexpr int GUARD = 4096;  // words on each side
+
+template <int L, int P>
+void run_phase(const StageParams& sp, const TileCtx& cx, float* sm)
+{
+  for (int tid = 0; tid < NT; tid++) Tile<L, kTile, NT>::template phase<P>(sp, cx, sm, tid);
+  if constexpr (P + 1 < Tile<L, kTile, NT>::NPHASES) run_phase<L, P + 1>(sp, cx, sm);
+}
+
+template <int L>
+int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison)
+{
+  using G = TileGeo<L, kTile>;
+  std::vector<float> buf((size_t)G::WORDS + 2 * GUARD + 4);
+  // 16-byte align the tile's shared memory
+  float* base = buf.data();
+  while ((reinterpret_cast<uintptr_t>(base + GUARD) & 15u) != 0) base++;
+  float* sm = base + GUARD;
+  uint32_t nanbits = 0x7fc0dead;
+  float nanv;
+  memcpy(&nanv, &nanbits, 4);
+  int bad = 0;
+  for (int f = 0; f < nfields; f++)
+    for (unsigned by = 0; by < sl.gy; by++)
+      for (unsigned bx = 0; bx < sl.gx; bx++) {
+        for (size_t i = 0; i < (size_t)G::WORDS + 2 * GUARD; i++) base[i] = poison ? nanv : 0.0f;
+        TileCtx cx;
+        cx.I0 = (sl.sp.tile_i0 + (int)by) * kTile;
+        cx.J0 = (sl.sp.tile_j0 + (int)bx) * kTile;
+        cx.seed = seeds ? seeds[f] : sl.sp.seed;
+        cx.gin = sl.sp.gin ? sl.sp.gin + (size_t)f * sl.sp.gin_field_stride : nullptr;
+        cx.gout = sl.sp.gout + (size_t)f * sl.sp.gout_field_stride;
+        run_phase<L, 0>(sl.sp, cx, sm);
+        if (poison) {
+          for (int i = 0; i < GUARD; i++) {
+            uint32_t a, b;
+            memcpy(&a, &base[i], 4);
+            memcpy(&b, &sm[G::WORDS + i], 4);
+            if (a != nanbits || b != nanbits) bad = 1;  // a write outside the tile's shared memory
+          }
+        }
+      }
+  return bad;
+}
+
+}  // namespace
+
+extern "C" {
+
+int replay_smem_bytes(int L)
+{
+  switch (L) {
+    case 1: return (int)TileGeo<1, kTile>::BYTES;
+    case 2: return (int)TileGeo<2, kTile>::BYTES;
+    case 3: return (int)TileGeo<3, kTile>::BYTES;
+    default: return (int)TileGeo<4, kTile>::BYTES;
+  }
+}
+
+int replay_plan(int depth, int* din, int* L)
+{
+  StagePlan plan[kMaxStages];
+  const int ns = plan_stages(depth, plan);
+  for (int k = 0; k < ns; k++) {
+    din[k] = plan[k].din;
+    L[k] = plan[k].L;
+  }
+  return ns;
+}
+
+// Same contract as rn_terrain2d with a host destination (window may be NULL).  Returns 0 on
+// success, 100 if a tile wrote outside its shared memory.
+int replay_terrain2d(const rn_params* p, const rn_window* win, rn_element* dst, size_t pitch_elems, int poison)
+{
+  if (!p || !dst || p->depth < RN_MIN_DEPTH || p->depth > RN_MAX_DEPTH) return RN_ERR_BAD_PARAM;
+  const int side = (1 << p->depth) + 1;
+  rn_window w{0, 0, side, side};
+  if (win) w = *win;
+  if (pitch_elems == 0) pitch_elems = (size_t)w.nj;
+  Law law;
+  law.amplitude = p->amplitude;
+  law.sideways_scale = p->sideways_scale;
+  law.radiosity_strength = p->radiosity_strength;
+  law.amplitude_variation = p->amplitude_variation;
+  law.band_hi = 3.0f / p->feature_scale;
+  law.band_lo = 0.5f / p->feature_scale;
+  law.bulgy = p->bulgy_rocks != 0;
+  const size_t sbytes = chain_scratch_bytes(p->depth, 1);
+  void* scratch = nullptr;
+  if (sbytes && posix_memalign(&scratch, 256, sbytes) != 0) return RN_ERR_OOM;
+  if (sbytes && poison) memset(scratch, 0xff, sbytes);  // NaN: untouched intermediate samples must never be consumed
+  StageLaunch chain[kMaxStages];
+  const int ns = build_chain(chain, p->depth, w.i0, w.j0, w.ni, w.nj, reinterpret_cast<E4*>(dst), pitch_elems, 0, scratch, 1, law,
+                             p->persistence, p->seed, nullptr, p->apply_volcano, p->amplitude);
+  int bad = 0;
+  for (int k = 0; k < ns; k++) {
+    switch (chain[k].L) {
+      case 1: bad |= run_stage<1>(chain[k], 1, nullptr, poison); break;
+      case 2: bad |= run_stage<2>(chain[k], 1, nullptr, poison); break;
+      case 3: bad |= run_stage<3>(chain[k], 1, nullptr, poison); break;
+      default: bad |= run_stage<4>(chain[k], 1, nullptr, poison); break;
+    }
+  }
+  free(scratch);
+  return bad ? 100 : 0;
+}
+
+}  // extern "C"

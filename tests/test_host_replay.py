@@ -1,0 +1,96 @@
+"""CPU: the fused tile algorithm (rednoise_b200/csrc/rn_tile.cuh + rn_plan.h -- the very code the
+CUDA stage kernels are compiled from) replayed thread by thread on the host
+(tests/host_replay/rn_replay.cpp) against the oracle: tiling, halos, windows, boundary rules, RNG
+indexing and shade ordering are validated bit for bit without a GPU.  The replay poisons the
+tile's shared memory and the intermediate grids with NaN first, so a sample computed from
+anything outside its dependency cone would show up as a NaN / bit mismatch."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_replay", "rn_replay.cpp")
+SO = os.path.join(HERE, "host_replay", "librn_replay.so")
+CSRC = os.path.join(os.path.dirname(HERE), "rednoise_b200", "csrc")
+
+
+class Win(C.Structure):
+    _fields_ = [("i0", C.c_int32), ("j0", C.c_int32), ("ni", C.c_int32), ("nj", C.c_int32)]
+
+
+@pytest.fixture(scope="module")
+def replay():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rn_tile.cuh", "rn_plan.h", "rn_math.cuh")]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", SO, SRC], check=True)
+    L = C.CDLL(SO)
+    L.replay_terrain2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    return L
+
+
+def run(L, p, win=None, pitch=0, poison=1):
+    s = (1 << p.depth) + 1
+    ni, nj = (win.ni, win.nj) if win is not None else (s, s)
+    out = np.full((ni, max(pitch, nj), 4), -7.0, np.float32)
+    st = L.replay_terrain2d(C.byref(p), C.byref(win) if win is not None else None, out.ctypes.data, max(pitch, nj), poison)
+    assert st == 0
+    return out
+
+
+@pytest.mark.parametrize("depth,seed", [(3, 12345), (4, 1), (5, 5), (6, 12345), (7, 70), (8, 12345), (8, 777), (9, 9), (10, 12345), (11, 3)])
+@pytest.mark.parametrize("volcano", [0, 1])
+def test_replay_equals_oracle_bitwise(replay, oracle, depth, seed, volcano):
+    p = oracle_lib.params(seed=seed, depth=depth, apply_volcano=volcano)
+    got = run(replay, p)
+    want = oracle.terrain2d(p)
+    assert not np.isnan(got).any()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_replay_depth12_digest(replay, oracle):
+    """BASELINE config 2 against the reference digest (tests/golden)."""
+    import json
+    gold = json.load(open(os.path.join(HERE, "golden", "terrain2d_golden.json")))
+    e = [f for f in gold["fields"] if f["depth"] == 12][0]
+    got = run(replay, oracle_lib.params(seed=e["seed"], depth=12, apply_volcano=1))
+    assert oracle.fnv64(got) == e["fnv64_post_volcano"]
+
+
+def test_replay_nondefault_params(replay, oracle):
+    kw = dict(persistence=0.6, sideways_scale=0.3, radiosity_strength=0.7, feature_scale=50.0, amplitude_variation=0.25,
+              amplitude=0.35, bulgy_rocks=0)
+    for depth in (5, 8):
+        p = oracle_lib.params(seed=99, depth=depth, apply_volcano=1, **kw)
+        assert np.array_equal(run(replay, p).view(np.uint32), oracle.terrain2d(p).view(np.uint32))
+
+
+def test_replay_windows_are_seam_exact(replay, oracle):
+    depth = 9
+    S = (1 << depth) + 1
+    p = oracle_lib.params(seed=4711, depth=depth, apply_volcano=1)
+    full = oracle.terrain2d(p)
+    rng = np.random.default_rng(5)
+    wins = [(0, 0, 1, 1), (S - 1, S - 1, 1, 1), (0, 0, S, 1), (0, S - 1, S, 1), (100, 37, 64, 64), (255, 255, 3, 3), (0, 0, 129, S),
+            (384, 0, S - 384, S), (64, 64, 64, 64), (63, 63, 2, 2), (512, 0, 1, S)]
+    for _ in range(10):
+        i0, j0 = (int(x) for x in rng.integers(0, S - 1, 2))
+        wins.append((i0, j0, int(rng.integers(1, S - i0 + 1)), int(rng.integers(1, S - j0 + 1))))
+    for (i0, j0, ni, nj) in wins:
+        got = run(replay, p, Win(i0, j0, ni, nj), pitch=nj + 3)
+        assert np.array_equal(got[:, :nj].view(np.uint32), full[i0:i0 + ni, j0:j0 + nj].view(np.uint32)), (i0, j0, ni, nj)
+        assert (got[:, nj:] == -7.0).all()
+
+
+def test_stage_plans(replay):
+    d, l = (C.c_int * 8)(), (C.c_int * 8)()
+    for depth in range(3, 15):
+        n = replay.replay_plan(depth, d, l)
+        assert d[0] == 2 and sum(l[k] for k in range(n)) == depth - 2
+        assert all(1 <= l[k] <= 4 for k in range(n)) and all(d[k + 1] == d[k] + l[k] for k in range(n - 1))
+    for L in (1, 2, 3, 4):
+        assert replay.replay_smem_bytes(L) <= 227 * 1024

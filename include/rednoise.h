@@ -143,6 +143,11 @@ int rn_terrain2d_batch(rn_context* ctx, const rn_params* p, const uint32_t* seed
 int rn_lcg_draws_device(rn_context* ctx, uint32_t seed, uint64_t first, uint64_t n, uint16_t* dst,
                         int dst_is_device, void* stream);
 
+/* Device self-test of the arithmetic shortcuts: the normal-range sqrt / reciprocal sequences
+ * used by the fused kernels are compared with the IEEE-rounded intrinsics over every binary32
+ * value in 2^-100 .. 2^100.  mismatches[0..2] = sqrt, reciprocal, 1/sqrt (all must be 0). */
+int rn_selftest_math(rn_context* ctx, uint64_t* mismatches3);
+
 #ifdef __cplusplus
 }
 #endif

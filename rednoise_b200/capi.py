@@ -21,7 +21,7 @@ RN_MIN_DEPTH, RN_MAX_DEPTH = 3, 14
 SYMBOLS = [
     "rn_version", "rn_last_error_string", "rn_status_string", "rn_params_default", "rn_terrain2d_side",
     "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
-    "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device",
+    "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device", "rn_selftest_math",
 ]
 
 
@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
     L.rn_terrain2d.argtypes = [vp, C.POINTER(Params), C.POINTER(Window), vp, sz, i32, vp, C.POINTER(C.c_float)]
     L.rn_terrain2d_batch.argtypes = [vp, C.POINTER(Params), C.POINTER(u32), i32, vp, sz, i32, vp]
     L.rn_lcg_draws_device.argtypes = [vp, u32, u64, u64, vp, i32, vp]
+    L.rn_selftest_math.argtypes = [vp, C.POINTER(u64)]
     _lib = L
     return L
 
@@ -177,6 +178,11 @@ class Context:
         out = np.empty((len(seeds), s, s, 4), np.float32)
         self.terrain2d_batch_ptr(p, seeds, out.ctypes.data, dst_is_device=False)
         return out
+
+    def selftest_math(self):
+        buf = (C.c_uint64 * 3)()
+        _check(lib().rn_selftest_math(self._h, buf))
+        return [int(x) for x in buf]
 
     def lcg_draws_host(self, seed: int, first: int, n: int) -> np.ndarray:
         out = np.empty(n, np.uint16)

@@ -443,6 +443,21 @@ int rn_terrain2d_batch(rn_context* ctx, const rn_params* p, const uint32_t* seed
   return RN_OK;
 }
 
+int rn_selftest_math(rn_context* ctx, uint64_t* mismatches3)
+{
+  if (!ctx || !mismatches3) return fail(RN_ERR_BAD_PARAM, "ctx/mismatches3 is NULL");
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  int st = ensure(&ctx->small, &ctx->small_bytes, 256);
+  if (st != RN_OK) return st;
+  RN_CUDA(selftest_math((unsigned long long*)ctx->small, ctx->stream, &ctx->launches));
+  unsigned long long h[3];
+  RN_CUDA(cudaMemcpyAsync(h, ctx->small, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  RN_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 3; k++) mismatches3[k] = h[k];
+  return RN_OK;
+}
+
 int rn_lcg_draws_device(rn_context* ctx, uint32_t seed, uint64_t first, uint64_t n, uint16_t* dst, int dst_is_device, void* stream_v)
 {
   if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");

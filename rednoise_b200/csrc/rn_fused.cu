@@ -13,13 +13,13 @@ namespace {
 
 constexpr int kStageThreads = 512;
 
-template <int L, int T, int NT, int P>
+template <int L, int T, int NT, bool EDGE, int P>
 __device__ __forceinline__ void run_phases(const StageParams& sp, const TileCtx& cx, float* sm)
 {
-  Tile<L, T, NT>::template phase<P>(sp, cx, sm, (int)threadIdx.x);
-  if constexpr (P + 1 < Tile<L, T, NT>::NPHASES) {
+  Tile<L, T, NT, EDGE>::template phase<P>(sp, cx, sm, (int)threadIdx.x);
+  if constexpr (P + 1 < Tile<L, T, NT, EDGE>::NPHASES) {
     __syncthreads();
-    run_phases<L, T, NT, P + 1>(sp, cx, sm);
+    run_phases<L, T, NT, EDGE, P + 1>(sp, cx, sm);
   }
 }
 
@@ -34,7 +34,9 @@ __global__ void __launch_bounds__(NT, (TileGeo<L, T>::BYTES <= 113 * 1024) ? 2 :
   cx.seed = sp.seeds ? sp.seeds[f] : sp.seed;
   cx.gin = sp.gin ? sp.gin + (size_t)f * sp.gin_field_stride : nullptr;
   cx.gout = sp.gout + (size_t)f * sp.gout_field_stride;
-  run_phases<L, T, NT, 0>(sp, cx, sm);
+  // interior tiles (no part of the dependency cone outside the lattice) take the lean instantiation
+  if (Tile<L, T, NT, true>::is_edge(cx, 1 << sp.dout)) run_phases<L, T, NT, true, 0>(sp, cx, sm);
+  else run_phases<L, T, NT, false, 0>(sp, cx, sm);
 }
 
 template <int L>

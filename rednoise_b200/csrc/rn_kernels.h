@@ -22,6 +22,8 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
 // stored at g with row pitch `pitch` (g points at window element (i0,j0)).
 cudaError_t volcano_apply(Elem* g, size_t pitch, int depth, int i0, int j0, int ni, int nj, float amplitude, cudaStream_t stream,
                           uint64_t* launches);
+// Exhaustive device check of sqrt_rn_normal / rcp_rn_normal against the IEEE intrinsics (3 mismatch counters).
+cudaError_t selftest_math(unsigned long long* dev_counts3, cudaStream_t stream, uint64_t* launches);
 // 15-bit draws first..first+n-1 of srand(seed) as uint16.
 cudaError_t lcg_draws(uint16_t* dst, uint32_t seed, uint64_t first, uint64_t n, cudaStream_t stream, uint64_t* launches);
 

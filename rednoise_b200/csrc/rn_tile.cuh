@@ -44,9 +44,13 @@ namespace rn {
 
 #if defined(__CUDACC__)
 typedef float4 E4;
+typedef uint2 uint2_t;
 #else
 struct alignas(16) E4 {
   float x, y, z, w;
+};
+struct alignas(8) uint2_t {
+  uint32_t x, y;
 };
 #endif
 
@@ -64,6 +68,7 @@ constexpr int kMaxStageLevels = 4;
 struct StageLevel {
   int n;                       // squares per side
   uint32_t kS, kD1, kD2;       // 1 + call index of the level's first generateSquare / loop-1 / loop-2 draw, mod 2^32
+  Jump jn, jn1;                // LCG jumps over n and n+1 draws: one row of generateSquare / loop-1 calls, one row of loop-2 calls
   float blahS, blahD, blahDh;  // Terrain.cpp:231 ; :186 unclamped ; :186 with the X extent clamped
 };
 
@@ -93,6 +98,7 @@ RN_CX int cdiv_(int a, int b) { return a >= 0 ? (a + b - 1) / b : -((-a) / b); }
 RN_CX int fdiv_(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 RN_CX int imin_(int a, int b) { return a < b ? a : b; }
 RN_CX int imax_(int a, int b) { return a > b ? a : b; }
+RN_CX int mod8_(int a) { return ((a % 8) + 8) % 8; }
 
 // Cell ranges of the three phases of a level with half-step h (fine units) for a tile [0,T].
 template <int h, int T>
@@ -109,6 +115,11 @@ struct LevelRange {
 };
 
 // Shared-memory geometry of a stage (offsets in 4-byte words).
+//
+// The copy-out reads, per quarter warp, 4 consecutive corners K + 4 consecutive mids M1 (even
+// rows) or 4 M2 + 4 centres C (odd rows) with one LDS.128 each.  That is conflict-free iff the
+// 16-byte slots of the two runs differ by 4 (mod 8): the row pitches of LAT and of the class
+// arrays are congruent mod 8 and the array bases are padded accordingly (PAD_M1, PAD_M2).
 template <int L, int T>
 struct TileGeo {
   static_assert(L >= 1 && L <= kMaxStageLevels, "1..4 fused levels");
@@ -116,24 +127,35 @@ struct TileGeo {
   static constexpr int H = stage_halo(L);        // halo, fine units
   static constexpr int HL = H / 2;               // halo, LAT units
   static constexpr int NLAT = (T + 2 * H) / 2 + 1;
-  static constexpr int PLAT = NLAT;              // LAT row pitch (E4)
   static constexpr int NC = T / 2 + 2;           // last-level class arrays: cells -1 .. T/2
   static constexpr int PC = NC;                  // row pitch (E4 / float)
+  static constexpr int PLAT = NLAT + mod8_(PC - NLAT);  // LAT row pitch (E4), congruent to PC mod 8
   static constexpr int NTS = NC + 2;             // TS keeps a second ring (cells -2 .. T/2+1)
   static constexpr int PTS = NTS;
   static constexpr int NR = NC + 1;              // rows of an RNG row table, columns of the jump table
-  static constexpr int LAT = 0;
-  static constexpr int CARR = LAT + 4 * NLAT * PLAT;
-  static constexpr int M1ARR = CARR + 4 * NC * PC;
-  static constexpr int M2ARR = M1ARR + 4 * NC * PC;
+  // E4-slot offsets
+  static constexpr int LAT4 = 0;
+  static constexpr int CARR4 = LAT4 + NLAT * PLAT;
+  static constexpr int M1RAW4 = CARR4 + NC * PC;
+  // want (LAT4 + HL*PLAT + HL) - (M1ARR4 + PC + 1) == 4 (mod 8)
+  static constexpr int PAD_M1 = mod8_((LAT4 + HL * PLAT + HL) - (M1RAW4 + PC + 1) - 4);
+  static constexpr int M1ARR4 = M1RAW4 + PAD_M1;
+  static constexpr int M2RAW4 = M1ARR4 + NC * PC;
+  // want M2ARR4 - CARR4 == 4 (mod 8)
+  static constexpr int PAD_M2 = mod8_(CARR4 + 4 - M2RAW4);
+  static constexpr int M2ARR4 = M2RAW4 + PAD_M2;
+  static_assert(mod8_((LAT4 + HL * PLAT + HL) - (M1ARR4 + PC + 1)) == 4 && mod8_(M2ARR4 - CARR4) == 4, "copy-out bank alignment");
+  // word offsets
+  static constexpr int LAT = 4 * LAT4, CARR = 4 * CARR4, M1ARR = 4 * M1ARR4, M2ARR = 4 * M2ARR4;
   static constexpr int TL = M1ARR;  // loss plane of the in-place levels: dead before M1/M2 are written
-  static_assert(NLAT * PLAT <= 8 * NC * PC, "in-place loss plane must fit in the M1/M2 arrays");
+  static_assert(NLAT * PLAT <= 4 * (M2ARR4 + NC * PC - M1ARR4), "in-place loss plane must fit in the M1/M2 arrays");
   static constexpr int TS = M2ARR + 4 * NC * PC;
   static constexpr int TD1 = TS + NTS * PTS;
   static constexpr int TD2 = TD1 + NC * PC;
-  static constexpr int JUMP = TD2 + NC * PC;     // NR x (a, c)
-  static constexpr int ROWS = JUMP + 2 * NR;     // L x 3 x NR start states
-  static constexpr int WORDS = ((ROWS + L * 3 * NR + 3) / 4) * 4;
+  static constexpr int JUMP = ((TD2 + NC * PC + 1) / 2) * 2;  // NR x (a, c), 8-byte aligned
+  static constexpr int ROWS = JUMP + 2 * NR;                  // L x 3 x NR row start states
+  static constexpr int STARTS = ROWS + L * 3 * NR;            // L x 3 tile start states
+  static constexpr int WORDS = ((STARTS + L * 3 + 3) / 4) * 4;
   static constexpr size_t BYTES = (size_t)WORDS * 4;
 };
 
@@ -191,22 +213,29 @@ RN_HD uint32_t lcg_state_after32(uint32_t seed, uint32_t k)
   return s;
 }
 
-// Terrain.cpp:129-137 with d /= maxWidth written as a multiplication by the exact power of two.
-RN_HD float volcano_height_pow2(int i, int j, int W, float inv_w, float gain)
+// state after r repetitions of the jump j (r small: a row index inside a tile)
+RN_HD uint32_t jump_apply_pow(Jump j, uint32_t r, uint32_t s)
 {
-  const float fx = (float)(i - W / 2), fy = (float)(j - W / 2);
-  const float r2 = fx * fx + fy * fy;
-#if defined(__CUDA_ARCH__)
-  float d = __fsqrt_rn(r2);
-  d = d * inv_w;
-  float height = __frcp_rn(d);
-#else
-  float d = sqrtf(r2);
-  d = d * inv_w;
-  float height = 1.0f / d;
-#endif
+  while (r) {
+    if (r & 1u) s = jump_apply(j, s);
+    j = jump_compose(j, j);
+    r >>= 1;
+  }
+  return s;
+}
+
+// addVolcano, Terrain.cpp:129-137, for one sample whose squared index distance from the volcano is
+// r2 = fx*fx + fy*fy.  d /= maxWidth is a multiplication by the exact power of two inv_w.
+// r2 is either 0 (the centre sample) or >= 1, so sqrt / reciprocal see normal numbers.
+RN_HD float volcano_height_r2(float r2, float inv_w, float gain)
+{
+  float d = sqrt_rn_normal(r2) * inv_w;
+  float height = rcp_rn_normal(d);
   const float minRad = 0.02f;
-  if (d < minRad) height = 60000.f * (d * d - minRad * minRad) + (1.0f / minRad);
+  if (!(d >= minRad)) {  // also taken by the centre sample, where the approximations above see 0
+    if (r2 == 0.0f) d = 0.0f;
+    height = 60000.f * (d * d - minRad * minRad) + (1.0f / minRad);
+  }
   return height * gain;
 }
 
@@ -217,56 +246,74 @@ struct TileCtx {
   E4* gout;
 };
 
-template <int L, int T, int NT>
+// Visits the cells c = tid, tid+NT, ... of an N x N range as (row, column), updating the pair
+// incrementally instead of dividing every time.
+template <int N, int NT, class F>
+RN_HD void for_cells(int tid, F&& f)
+{
+  constexpr int DA = NT / N, DB = NT % N;
+  int ra = tid / N, rb = tid - ra * N;
+  for (int c = tid; c < N * N; c += NT) {
+    f(ra, rb);
+    ra += DA;
+    rb += DB;
+    if (rb >= N) {
+      rb -= N;
+      ra++;
+    }
+  }
+}
+
+// EDGE = the tile's dependency cone may reach outside the global lattice: existence tests and the
+// border forms of averageDiamond / generateDiamond are compiled in.  Interior tiles (the vast
+// majority) use EDGE = false, where every cell of every range exists.
+template <int L, int T, int NT, bool EDGE>
 struct Tile {
   using G = TileGeo<L, T>;
-  static constexpr int NPHASES = 2 + 3 * L;
+  static constexpr int NPHASES = 3 + 3 * L;
+
+  static RN_HD bool is_edge(const TileCtx& cx, int Wout)
+  {
+    return cx.I0 - G::H < 0 || cx.J0 - G::H < 0 || cx.I0 + T + G::H > Wout || cx.J0 + T + G::H > Wout;
+  }
 
   // ------------------------------------------------------------------ phase 0 ----
-  // RNG tables (column jumps A^c, C_c; per level the start state of every cell row for the
-  // S, D-loop-1 and D-loop-2 draws) and the input lattice.
+  // Input lattice, LCG column jumps (A^c, C_c) and, per level and draw table (generateSquare,
+  // loop 1, loop 2), the LCG state in front of the tile's first cell (one 32-step skip-ahead each).
   template <int M>
-  static RN_HD void fill_rows(const StageParams& sp, const TileCtx& cx, float* sm, int e)
+  static RN_HD void fill_start(const StageParams& sp, const TileCtx& cx, float* sm, int which)
   {
     constexpr int h = 1 << (L - 1 - M);
     using R = LevelRange<h, T>;
-    uint32_t* rows = reinterpret_cast<uint32_t*>(sm + G::ROWS) + M * 3 * G::NR;
     const StageLevel& lv = sp.lev[M];
-    const int which = e / G::NR, r = e - which * G::NR;
     const int A0 = cx.I0 >> (L - M), B0 = cx.J0 >> (L - M);
     const uint32_t n = (uint32_t)lv.n;
     uint32_t k;
-    if (which == 0) {
-      if (r >= R::NS) return;
-      k = lv.kS + (uint32_t)(A0 + R::S_lo + r) * n + (uint32_t)(B0 + R::S_lo);
-    } else if (which == 1) {
-      if (r >= R::ND) return;
-      k = lv.kD1 + (uint32_t)(A0 + R::D_lo + r) * n + (uint32_t)(B0 + R::D_lo);
-    } else {
-      if (r >= R::ND) return;
-      k = lv.kD2 + (uint32_t)(A0 + R::D_lo + r) * (n + 1u) + (uint32_t)(B0 + R::D_lo);
-    }
-    rows[e] = lcg_state_after32(cx.seed, k);
+    if (which == 0) k = lv.kS + (uint32_t)(A0 + R::S_lo) * n + (uint32_t)(B0 + R::S_lo);
+    else if (which == 1) k = lv.kD1 + (uint32_t)(A0 + R::D_lo) * n + (uint32_t)(B0 + R::D_lo);
+    else k = lv.kD2 + (uint32_t)(A0 + R::D_lo) * (n + 1u) + (uint32_t)(B0 + R::D_lo);
+    reinterpret_cast<uint32_t*>(sm + G::STARTS)[M * 3 + which] = lcg_state_after32(cx.seed, k);
   }
-
   template <int M>
-  static RN_HD void fill_rows_dispatch(const StageParams& sp, const TileCtx& cx, float* sm, int m, int e)
+  static RN_HD void fill_start_dispatch(const StageParams& sp, const TileCtx& cx, float* sm, int m, int which)
   {
-    if (m == M) fill_rows<M>(sp, cx, sm, e);
-    else if constexpr (M + 1 < L) fill_rows_dispatch<M + 1>(sp, cx, sm, m, e);
+    if (m == M) fill_start<M>(sp, cx, sm, which);
+    else if constexpr (M + 1 < L) fill_start_dispatch<M + 1>(sp, cx, sm, m, which);
   }
 
   static RN_HD void phase_init(const StageParams& sp, const TileCtx& cx, float* sm, int tid)
   {
+    static_assert(NT >= 64 + 3 * kMaxStageLevels, "thread roles of phase_init");
+    // the last 3L threads (a different warp from the lattice loaders of small tiles) do the skip-aheads
+    if (tid >= NT - 3 * L) {
+      const int e = tid - (NT - 3 * L);
+      fill_start_dispatch<0>(sp, cx, sm, e / 3, e % 3);
+    }
     uint32_t* jump = reinterpret_cast<uint32_t*>(sm + G::JUMP);
     for (int c = tid; c < G::NR; c += NT) {
       const Jump j = jump_of((uint64_t)c);
       jump[2 * c] = j.a;
       jump[2 * c + 1] = j.c;
-    }
-    for (int idx = tid; idx < L * 3 * G::NR; idx += NT) {
-      const int m = idx / (3 * G::NR);
-      fill_rows_dispatch<0>(sp, cx, sm, m, idx - m * 3 * G::NR);
     }
     // input lattice: LAT indices that are multiples of 2^(L-1) <-> input grid points
     constexpr int NIN = (T + 2 * G::H) / (1 << L) + 1;
@@ -277,7 +324,7 @@ struct Tile {
     for (int idx = tid; idx < NIN * NIN; idx += NT) {
       const int li = idx / NIN, lj = idx - li * NIN;
       const int gi = gi0 + li, gj = gj0 + lj;
-      if (gi < 0 || gj < 0 || gi > Win || gj > Win) continue;
+      if (EDGE && (gi < 0 || gj < 0 || gi > Win || gj > Win)) continue;
       E4 v;
       if (cx.gin) {
         v = cx.gin[(size_t)gi * sp.gin_pitch + (size_t)gj];
@@ -289,13 +336,39 @@ struct Tile {
     }
   }
 
+  // ------------------------------------------------------------------ phase 1 ----
+  // Row start states: row r of a table = the tile start state advanced by r rows of draws.
+  template <int M>
+  static RN_HD void fill_rows(const StageParams& sp, float* sm, int e)
+  {
+    constexpr int h = 1 << (L - 1 - M);
+    using R = LevelRange<h, T>;
+    const int which = e / G::NR, r = e - which * G::NR;
+    if (r >= (which == 0 ? R::NS : R::ND)) return;
+    const StageLevel& lv = sp.lev[M];
+    const uint32_t start = reinterpret_cast<const uint32_t*>(sm + G::STARTS)[M * 3 + which];
+    reinterpret_cast<uint32_t*>(sm + G::ROWS)[M * 3 * G::NR + e] = jump_apply_pow(which == 2 ? lv.jn1 : lv.jn, (uint32_t)r, start);
+  }
+  template <int M>
+  static RN_HD void fill_rows_dispatch(const StageParams& sp, float* sm, int m, int e)
+  {
+    if (m == M) fill_rows<M>(sp, sm, e);
+    else if constexpr (M + 1 < L) fill_rows_dispatch<M + 1>(sp, sm, m, e);
+  }
+  static RN_HD void phase_rows(const StageParams& sp, float* sm, int tid)
+  {
+    for (int idx = tid; idx < L * 3 * G::NR; idx += NT) {
+      const int m = idx / (3 * G::NR);
+      fill_rows_dispatch<0>(sp, sm, m, idx - m * 3 * G::NR);
+    }
+  }
+
   template <int M, int WHICH>
   static RN_HD uint32_t draw_of(const float* sm, int row, int col)
   {
-    const uint32_t* jump = reinterpret_cast<const uint32_t*>(sm + G::JUMP);
+    const uint2_t j = reinterpret_cast<const uint2_t*>(sm + G::JUMP)[col];
     const uint32_t* rows = reinterpret_cast<const uint32_t*>(sm + G::ROWS) + (M * 3 + WHICH) * G::NR;
-    const uint32_t st = jump[2 * col] * rows[row] + jump[2 * col + 1];
-    return lcg_draw_from_state(st);
+    return lcg_draw_from_state(j.x * rows[row] + j.y);
   }
 
   // ------------------------------------------------------------------ phase S ----
@@ -308,10 +381,9 @@ struct Tile {
     const StageLevel& lv = sp.lev[M];
     const int A0 = cx.I0 >> (L - M), B0 = cx.J0 >> (L - M);
     const unsigned n = (unsigned)lv.n;
-    for (int c = tid; c < R::NS * R::NS; c += NT) {
-      const int ra = c / R::NS, rb = c - ra * R::NS;
+    for_cells<R::NS, NT>(tid, [&](int ra, int rb) {
       const int a = R::S_lo + ra, b = R::S_lo + rb;
-      const bool ex = (unsigned)(A0 + a) < n && (unsigned)(B0 + b) < n;
+      const bool ex = !EDGE || ((unsigned)(A0 + a) < n && (unsigned)(B0 + b) < n);
       float loss = 0.0f;
       if (ex) {
         // averageSquare (Terrain.cpp:216-222) + generateSquare (:224-258)
@@ -319,12 +391,12 @@ struct Tile {
         const V3 avg = vmul(vadd(vadd(vadd(pos4(k00), pos4(k10)), pos4(k01)), pos4(k11)), 0.25f);
         const float sh = (k00.w + k10.w + k01.w + k11.w) * 0.25f;
         const uint32_t draw = draw_of<M, 0>(sm, ra, rb);
-        const Displaced dp = displace(sp.law, avg, vsub(pos4(k11), pos4(k00)), vsub(pos4(k10), pos4(k01)), lv.blahS, draw);
+        const Displaced dp = displace<true>(sp.law, avg, vsub(pos4(k11), pos4(k00)), vsub(pos4(k10), pos4(k01)), lv.blahS, draw);
         v.C(a, b) = e4_of(dp.pos, sh + shade_gain(sp.law, dp.offset));
         loss = shade_loss(sp.law, dp.offset);
       }
       v.TS(a, b) = loss;
-    }
+    });
   }
 
   // ------------------------------------------------------------------ phase D ----
@@ -344,7 +416,7 @@ struct Tile {
     float sh = (ex0.w + ex1.w + ey0.w + ey1.w) * 0.25f;
     const V3 px0 = sx0 ? avg : pos4(ex0), px1 = sx1 ? avg : pos4(ex1);
     const V3 py0 = sy0 ? avg : pos4(ey0), py1 = sy1 ? avg : pos4(ey1);
-    const Displaced dp = displace(law, avg, vsub(px0, px1), vsub(py1, py0), blah, draw);
+    const Displaced dp = displace<true>(law, avg, vsub(px0, px1), vsub(py1, py0), blah, draw);
     const float loss = shade_loss(law, dp.offset);
     sh += shade_gain(law, dp.offset);
     sh -= loss;  // the scatter onto the clamped index lands on the midpoint itself
@@ -357,7 +429,7 @@ struct Tile {
   {
     const V3 avg = vmul(vadd(vadd(vadd(pos4(ex0), pos4(ex1)), pos4(ey0)), pos4(ey1)), 0.25f);
     const float sh = (ex0.w + ex1.w + ey0.w + ey1.w) * 0.25f;
-    const Displaced dp = displace(law, avg, vsub(pos4(ex0), pos4(ex1)), vsub(pos4(ey1), pos4(ey0)), blah, draw);
+    const Displaced dp = displace<true>(law, avg, vsub(pos4(ex0), pos4(ex1)), vsub(pos4(ey1), pos4(ey0)), blah, draw);
     *loss_out = shade_loss(law, dp.offset);
     return e4_of(dp.pos, sh + shade_gain(law, dp.offset));
   }
@@ -371,12 +443,15 @@ struct Tile {
     const StageLevel& lv = sp.lev[M];
     const int A0 = cx.I0 >> (L - M), B0 = cx.J0 >> (L - M);
     const int n = lv.n;
-    for (int c = tid; c < R::ND * R::ND; c += NT) {
-      const int ra = c / R::ND, rb = c - ra * R::ND;
+    for_cells<R::ND, NT>(tid, [&](int ra, int rb) {
       const int a = R::D_lo + ra, b = R::D_lo + rb;
       const int Ag = A0 + a, Bg = B0 + b;
-      const bool v1 = a >= R::MA_lo && a <= R::MA_hi && b >= R::MB_lo && b <= R::MB_hi && Ag >= 0 && Ag <= n && Bg >= 0 && Bg < n;
-      const bool v2 = a >= R::MB_lo && a <= R::MB_hi && b >= R::MA_lo && b <= R::MA_hi && Ag >= 0 && Ag < n && Bg >= 0 && Bg <= n;
+      bool v1 = a >= R::MA_lo && a <= R::MA_hi && b >= R::MB_lo && b <= R::MB_hi;
+      bool v2 = a >= R::MB_lo && a <= R::MB_hi && b >= R::MA_lo && b <= R::MA_hi;
+      if (EDGE) {
+        v1 = v1 && Ag >= 0 && Ag <= n && Bg >= 0 && Bg < n;
+        v2 = v2 && Ag >= 0 && Ag < n && Bg >= 0 && Bg <= n;
+      }
       float t1 = 0.0f, t2 = 0.0f;
       if (v1 || v2) {
         // corner shades as generateSquare left them: minus the scatter of the surrounding centres,
@@ -389,7 +464,7 @@ struct Tile {
           k01.w = (((k01.w - ts_m0) - v.TS(a - 1, b + 1)) - ts_00) - v.TS(a, b + 1);
           const uint32_t draw = draw_of<M, 1>(sm, ra, rb);
           E4 m;
-          if (Ag == 0 || Ag == n) {
+          if (EDGE && (Ag == 0 || Ag == n)) {
             const E4 dummy = k00;
             m = mid_border(sp.law, Ag == 0 ? dummy : v.C(a - 1, b), Ag == n ? dummy : v.C(a, b), k00, k01, Ag == 0, Ag == n, false, false,
                            lv.blahDh, draw, &t1);
@@ -403,7 +478,7 @@ struct Tile {
           k10.w = (((k10.w - ts_0m) - ts_00) - v.TS(a + 1, b - 1)) - v.TS(a + 1, b);
           const uint32_t draw = draw_of<M, 2>(sm, ra, rb);
           E4 m;
-          if (Bg == 0 || Bg == n) {
+          if (EDGE && (Bg == 0 || Bg == n)) {
             const E4 dummy = k00;
             m = mid_border(sp.law, k00, k10, Bg == 0 ? dummy : v.C(a, b - 1), Bg == n ? dummy : v.C(a, b), false, false, Bg == 0, Bg == n,
                            lv.blahD, draw, &t2);
@@ -415,7 +490,7 @@ struct Tile {
       }
       v.TD1(a, b) = t1;
       v.TD2(a, b) = t2;
-    }
+    });
   }
 
   // ------------------------------------------------------------------ phase G ----
@@ -428,11 +503,16 @@ struct Tile {
     const StageLevel& lv = sp.lev[M];
     const int A0 = cx.I0 >> (L - M), B0 = cx.J0 >> (L - M);
     const int n = lv.n;
-    for (int c = tid; c < R::NG * R::NG; c += NT) {
-      const int ra = c / R::NG, rb = c - ra * R::NG;
+    for_cells<R::NG, NT>(tid, [&](int ra, int rb) {
       const int a = R::G_lo + ra, b = R::G_lo + rb;
       const int Ag = A0 + a, Bg = B0 + b;
-      if (a >= R::GK_lo && a <= R::GK_hi && b >= R::GK_lo && b <= R::GK_hi && Ag >= 0 && Ag <= n && Bg >= 0 && Bg <= n) {
+      bool gk = a >= R::GK_lo && a <= R::GK_hi && b >= R::GK_lo && b <= R::GK_hi;
+      bool gc = a >= R::GC_lo && a <= R::GC_hi && b >= R::GC_lo && b <= R::GC_hi;
+      if (EDGE) {
+        gk = gk && Ag >= 0 && Ag <= n && Bg >= 0 && Bg <= n;
+        gc = gc && Ag >= 0 && Ag < n && Bg >= 0 && Bg < n;
+      }
+      if (gk) {
         // corner: generateSquare scatter of 4 squares, then generateDiamond loop 1 (same row), loop 2 (same column)
         float sh = v.K(a, b).w;
         sh -= v.TS(a - 1, b - 1);
@@ -445,7 +525,7 @@ struct Tile {
         sh -= v.TD2(a, b);
         v.K(a, b).w = sh;
       }
-      if (a >= R::GC_lo && a <= R::GC_hi && b >= R::GC_lo && b <= R::GC_hi && Ag >= 0 && Ag < n && Bg >= 0 && Bg < n) {
+      if (gc) {
         // square centre: loop-1 midpoints are its x neighbours, loop-2 midpoints its y neighbours
         float sh = v.C(a, b).w;
         sh -= v.TD1(a, b);
@@ -454,32 +534,69 @@ struct Tile {
         sh -= v.TD2(a, b + 1);
         v.C(a, b).w = sh;
       }
-    }
+    });
   }
 
   // ---------------------------------------------------------------- copy-out ----
+  // E4 slot of output sample (r, c) of the tile: the four classes of the last level.
+  static RN_HD int out_slot(int r, int c)
+  {
+    const int A = r >> 1, B = c >> 1;
+    const int ci = (A + 1) * G::PC + (B + 1);
+    if (r & 1) return (c & 1) ? G::CARR4 + ci : G::M2ARR4 + ci;
+    return (c & 1) ? G::M1ARR4 + ci : G::LAT4 + (A + G::HL) * G::PLAT + (B + G::HL);
+  }
+
   static RN_HD void store_point(const StageParams& sp, const TileCtx& cx, const float* sm, int r, int c, int Wout, float inv_w)
   {
     const int gi = cx.I0 + r, gj = cx.J0 + c;
     const int wi = gi - sp.win_i0, wj = gj - sp.win_j0;
     if ((unsigned)wi >= (unsigned)sp.win_ni || (unsigned)wj >= (unsigned)sp.win_nj) return;
-    const int A = r >> 1, B = c >> 1;
-    const int ci = (A + 1) * G::PC + (B + 1);
-    const int ki = (A + G::HL) * G::PLAT + (B + G::HL);
-    int off;  // E4 index into shared memory
-    if (r & 1) off = (c & 1) ? G::CARR / 4 + ci : G::M2ARR / 4 + ci;
-    else off = (c & 1) ? G::M1ARR / 4 + ci : G::LAT / 4 + ki;
-    E4 e = reinterpret_cast<const E4*>(sm)[off];
-    if (sp.volcano) e.y = e.y + volcano_height_pow2(gi, gj, Wout, inv_w, sp.volcano_gain);
+    E4 e = reinterpret_cast<const E4*>(sm)[out_slot(r, c)];
+    if (sp.volcano) {
+      const float fx = (float)(gi - Wout / 2), fy = (float)(gj - Wout / 2);
+      e.y = e.y + volcano_height_r2(fx * fx + fy * fy, inv_w, sp.volcano_gain);
+    }
     cx.gout[(size_t)wi * sp.gout_pitch + (size_t)wj] = e;
   }
 
   static RN_HD void phase_out(const StageParams& sp, const TileCtx& cx, float* sm, int tid)
   {
+    static_assert(NT % T == 0, "a thread keeps its column in the copy-out");
     const int Wout = 1 << sp.dout;
     const float inv_w = 1.0f / (float)Wout;
     const bool close_i = cx.I0 + T >= Wout, close_j = cx.J0 + T >= Wout;  // the last tile also owns row / column W
-    const int nr = imin_(T, Wout - cx.I0) + (close_i ? 1 : 0);            // rows owned (Wout < T: a single short tile)
+    const int wi0 = cx.I0 - sp.win_i0, wj0 = cx.J0 - sp.win_j0;
+    const bool inside = wi0 >= 0 && wj0 >= 0 && wi0 + T <= sp.win_ni && wj0 + T <= sp.win_nj;
+    if (!EDGE && inside) {
+      // Fast path: the whole T x T tile is stored.  A thread owns one column c and the rows
+      // r0, r0+RS, ...; RS is even, so its samples all come from the same class array and both
+      // the shared-memory slot and the global pointer advance by constants.
+      constexpr int RS = NT / T;
+      static_assert(RS % 2 == 0, "row parity must stay fixed per thread");
+      const int c = tid % T, r0 = tid / T;
+      const E4* src = reinterpret_cast<const E4*>(sm) + out_slot(r0, c);
+      const int sstep = (RS / 2) * ((r0 & 1) || (c & 1) ? G::PC : G::PLAT);
+      E4* dst = cx.gout + (size_t)(wi0 + r0) * sp.gout_pitch + (size_t)(wj0 + c);
+      const size_t dstep = (size_t)RS * sp.gout_pitch;
+      const float fy = (float)(cx.J0 + c - Wout / 2);
+      const float fy2 = fy * fy;
+      int xi = cx.I0 + r0 - Wout / 2;
+#pragma unroll 4
+      for (int k = 0; k < T / RS; k++) {
+        E4 e = *src;
+        if (sp.volcano) {
+          const float fx = (float)xi;
+          e.y = e.y + volcano_height_r2(fx * fx + fy2, inv_w, sp.volcano_gain);
+        }
+        *dst = e;
+        src += sstep;
+        dst += dstep;
+        xi += RS;
+      }
+      return;
+    }
+    const int nr = imin_(T, Wout - cx.I0) + (close_i ? 1 : 0);  // rows owned (Wout < T: a single short tile)
     const int nc = imin_(T, Wout - cx.J0) + (close_j ? 1 : 0);
     for (int idx = tid; idx < T * T; idx += NT) {
       const int r = idx / T, c = idx - r * T;
@@ -492,15 +609,16 @@ struct Tile {
   }
 
   // ---------------------------------------------------------------- dispatch ----
-  // phase 0 = init, then per level m: 1+3m = S, 2+3m = D, 3+3m = G, last = copy-out.
+  // phase 0 = init, 1 = RNG rows, then per level m: 2+3m = S, 3+3m = D, 4+3m = G, last = copy-out.
   template <int P>
   static RN_HD void phase(const StageParams& sp, const TileCtx& cx, float* sm, int tid)
   {
     if constexpr (P == 0) phase_init(sp, cx, sm, tid);
+    else if constexpr (P == 1) phase_rows(sp, sm, tid);
     else if constexpr (P == NPHASES - 1) phase_out(sp, cx, sm, tid);
-    else if constexpr ((P - 1) % 3 == 0) phase_S<(P - 1) / 3>(sp, cx, sm, tid);
-    else if constexpr ((P - 1) % 3 == 1) phase_D<(P - 1) / 3>(sp, cx, sm, tid);
-    else phase_G<(P - 1) / 3>(sp, cx, sm, tid);
+    else if constexpr ((P - 2) % 3 == 0) phase_S<(P - 2) / 3>(sp, cx, sm, tid);
+    else if constexpr ((P - 2) % 3 == 1) phase_D<(P - 2) / 3>(sp, cx, sm, tid);
+    else phase_G<(P - 2) / 3>(sp, cx, sm, tid);
   }
 };
 

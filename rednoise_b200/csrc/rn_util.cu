@@ -43,7 +43,38 @@ __global__ void k_lcg_draws(uint16_t* dst, uint32_t seed, uint64_t first, uint64
   }
 }
 
+// Exhaustive check of the normal-range sqrt / reciprocal sequences (rn_math.cuh) against the
+// IEEE intrinsics, over every binary32 bit pattern with biased exponent in [27, 227]
+// (2^-100 .. 2^100), both signs skipped for sqrt.  counts[0] = sqrt mismatches, counts[1] = rcp
+// mismatches, counts[2] = mismatches of the composed 1/sqrt used by normalise().
+__global__ void k_selftest_math(unsigned long long* counts)
+{
+  const uint64_t first = (uint64_t)27 << 23, last = (uint64_t)228 << 23;
+  unsigned long long bad_s = 0, bad_r = 0, bad_c = 0;
+  for (uint64_t b = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < last; b += (uint64_t)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float((uint32_t)b);
+    const float s_ref = __fsqrt_rn(x), s_fast = sqrt_rn_normal(x);
+    if (__float_as_uint(s_ref) != __float_as_uint(s_fast)) bad_s++;
+    const float r_ref = __frcp_rn(x), r_fast = rcp_rn_normal(x);
+    if (__float_as_uint(r_ref) != __float_as_uint(r_fast)) bad_r++;
+    const float c_ref = __frcp_rn(s_ref), c_fast = rcp_rn_normal(s_fast);
+    if (__float_as_uint(c_ref) != __float_as_uint(c_fast)) bad_c++;
+  }
+  if (bad_s) atomicAdd(&counts[0], bad_s);
+  if (bad_r) atomicAdd(&counts[1], bad_r);
+  if (bad_c) atomicAdd(&counts[2], bad_c);
+}
+
 }  // namespace
+
+cudaError_t selftest_math(unsigned long long* dev_counts3, cudaStream_t stream, uint64_t* launches)
+{
+  cudaError_t e = cudaMemsetAsync(dev_counts3, 0, 3 * sizeof(unsigned long long), stream);
+  if (e != cudaSuccess) return e;
+  k_selftest_math<<<148 * 8, 256, 0, stream>>>(dev_counts3);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
 
 cudaError_t volcano_apply(Elem* g, size_t pitch, int depth, int i0, int j0, int ni, int nj, float amplitude, cudaStream_t stream,
                           uint64_t* launches)

@@ -23,15 +23,15 @@ namespace {
 constexpr int NT = 512;
 constexpr int GUARD = 4096;  // words on each side
 
-template <int L, int P>
+template <int L, bool EDGE, int P>
 void run_phase(const StageParams& sp, const TileCtx& cx, float* sm)
 {
-  for (int tid = 0; tid < NT; tid++) Tile<L, kTile, NT>::template phase<P>(sp, cx, sm, tid);
-  if constexpr (P + 1 < Tile<L, kTile, NT>::NPHASES) run_phase<L, P + 1>(sp, cx, sm);
+  for (int tid = 0; tid < NT; tid++) Tile<L, kTile, NT, EDGE>::template phase<P>(sp, cx, sm, tid);
+  if constexpr (P + 1 < Tile<L, kTile, NT, EDGE>::NPHASES) run_phase<L, EDGE, P + 1>(sp, cx, sm);
 }
 
 template <int L>
-int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison)
+int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
 {
   using G = TileGeo<L, kTile>;
   std::vector<float> buf((size_t)G::WORDS + 2 * GUARD + 4);
@@ -53,7 +53,8 @@ int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
         cx.seed = seeds ? seeds[f] : sl.sp.seed;
         cx.gin = sl.sp.gin ? sl.sp.gin + (size_t)f * sl.sp.gin_field_stride : nullptr;
         cx.gout = sl.sp.gout + (size_t)f * sl.sp.gout_field_stride;
-        run_phase<L, 0>(sl.sp, cx, sm);
+        if (force_edge || Tile<L, kTile, NT, true>::is_edge(cx, 1 << sl.sp.dout)) run_phase<L, true, 0>(sl.sp, cx, sm);
+        else run_phase<L, false, 0>(sl.sp, cx, sm);
         if (poison) {
           for (int i = 0; i < GUARD; i++) {
             uint32_t a, b;
@@ -91,7 +92,8 @@ int replay_plan(int depth, int* din, int* L)
   return ns;
 }
 
-// Same contract as rn_terrain2d with a host destination (window may be NULL).  Returns 0 on
+// Same contract as rn_terrain2d with a host destination (window may be NULL).  poison bit 0: NaN-fill
+// shared memory and scratch; bit 1: run every tile through the EDGE instantiation.  Returns 0 on
 // success, 100 if a tile wrote outside its shared memory.
 int replay_terrain2d(const rn_params* p, const rn_window* win, rn_element* dst, size_t pitch_elems, int poison)
 {
@@ -118,10 +120,10 @@ int replay_terrain2d(const rn_params* p, const rn_window* win, rn_element* dst, 
   int bad = 0;
   for (int k = 0; k < ns; k++) {
     switch (chain[k].L) {
-      case 1: bad |= run_stage<1>(chain[k], 1, nullptr, poison); break;
-      case 2: bad |= run_stage<2>(chain[k], 1, nullptr, poison); break;
-      case 3: bad |= run_stage<3>(chain[k], 1, nullptr, poison); break;
-      default: bad |= run_stage<4>(chain[k], 1, nullptr, poison); break;
+      case 1: bad |= run_stage<1>(chain[k], 1, nullptr, poison & 1, (poison >> 1) & 1); break;
+      case 2: bad |= run_stage<2>(chain[k], 1, nullptr, poison & 1, (poison >> 1) & 1); break;
+      case 3: bad |= run_stage<3>(chain[k], 1, nullptr, poison & 1, (poison >> 1) & 1); break;
+      default: bad |= run_stage<4>(chain[k], 1, nullptr, poison & 1, (poison >> 1) & 1); break;
     }
   }
   free(scratch);

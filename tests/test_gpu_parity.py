@@ -44,6 +44,11 @@ def test_lcg_draws_bit_exact(ctx, oracle):
     assert ctx.lcg_draws_host(1, 0, 8).tolist() == [41, 18467, 6334, 26500, 19169, 15724, 11478, 29358]
 
 
+def test_normal_range_math_is_ieee_exact(ctx):
+    """sqrt_rn_normal / rcp_rn_normal (fused kernels) == __fsqrt_rn / __frcp_rn on every binary32 in 2^-100..2^100."""
+    assert ctx.selftest_math() == [0, 0, 0]
+
+
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("depth,seed", [(3, 12345), (4, 1), (5, 5), (6, 12345), (7, 70), (8, 12345), (8, 777), (9, 9), (10, 12345), (11, 3)])
 @pytest.mark.parametrize("volcano", [0, 1])

@@ -52,6 +52,14 @@ def test_replay_equals_oracle_bitwise(replay, oracle, depth, seed, volcano):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("depth,seed", [(8, 5), (9, 12345), (10, 77)])
+def test_replay_edge_instantiation_equals_interior(replay, oracle, depth, seed):
+    """Every tile through the EDGE (existence-tested) instantiation == the mixed interior/edge run == the oracle."""
+    p = oracle_lib.params(seed=seed, depth=depth, apply_volcano=1)
+    a = run(replay, p, poison=3)
+    assert np.array_equal(a.view(np.uint32), oracle.terrain2d(p).view(np.uint32))
+
+
 def test_replay_depth12_digest(replay, oracle):
     """BASELINE config 2 against the reference digest (tests/golden)."""
     import json

@@ -62,8 +62,6 @@ inline void fill_stage_levels(StageParams& sp, float persistence)
     lv.kS = (uint32_t)(base + 1);
     lv.kD1 = (uint32_t)(base + n * n + 1);
     lv.kD2 = (uint32_t)(base + n * n + n * (n + 1) + 1);
-    lv.jn = jump_of(n);
-    lv.jn1 = jump_of(n + 1);
     lv.blahS = (1.414f * 2.0f) * gain;   // Terrain.cpp:231
     lv.blahD = 2.0f * (gain * 1.0f);     // Terrain.cpp:186, X extent not clamped
     lv.blahDh = 2.0f * (gain * 0.5f);    // Terrain.cpp:186, X extent clamped (halved)

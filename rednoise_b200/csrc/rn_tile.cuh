@@ -68,7 +68,6 @@ constexpr int kMaxStageLevels = 4;
 struct StageLevel {
   int n;                       // squares per side
   uint32_t kS, kD1, kD2;       // 1 + call index of the level's first generateSquare / loop-1 / loop-2 draw, mod 2^32
-  Jump jn, jn1;                // LCG jumps over n and n+1 draws: one row of generateSquare / loop-1 calls, one row of loop-2 calls
   float blahS, blahD, blahDh;  // Terrain.cpp:231 ; :186 unclamped ; :186 with the X extent clamped
 };
 
@@ -116,10 +115,11 @@ struct LevelRange {
 
 // Shared-memory geometry of a stage (offsets in 4-byte words).
 //
-// The copy-out reads, per quarter warp, 4 consecutive corners K + 4 consecutive mids M1 (even
-// rows) or 4 M2 + 4 centres C (odd rows) with one LDS.128 each.  That is conflict-free iff the
-// 16-byte slots of the two runs differ by 4 (mod 8): the row pitches of LAT and of the class
-// arrays are congruent mod 8 and the array bases are padded accordingly (PAD_M1, PAD_M2).
+// LAT, the step-2 lattice the in-place levels work on, is stored as two halves by column parity
+// (even columns, then odd columns, each NLAT x PH).  A level with half-step h >= 2 then touches
+// unit-stride runs of one half (no bank conflicts for h == 2, 2-way for h == 4), and the last
+// level, which reads consecutive columns, alternates between the halves; with the half offset
+// congruent to 4 (mod 8) 16-byte slots a quarter warp's LDS.128 covers 8 distinct bank groups.
 template <int L, int T>
 struct TileGeo {
   static_assert(L >= 1 && L <= kMaxStageLevels, "1..4 fused levels");
@@ -127,36 +127,32 @@ struct TileGeo {
   static constexpr int H = stage_halo(L);        // halo, fine units
   static constexpr int HL = H / 2;               // halo, LAT units
   static constexpr int NLAT = (T + 2 * H) / 2 + 1;
+  static constexpr int PH = (NLAT + 1) / 2;      // row pitch of one LAT half (E4)
+  static constexpr int LATOFF = NLAT * PH + mod8_(4 - NLAT * PH);  // E4 offset of the odd-column half, == 4 (mod 8)
+  static constexpr int LATSLOTS = LATOFF + NLAT * PH;
   static constexpr int NC = T / 2 + 2;           // last-level class arrays: cells -1 .. T/2
   static constexpr int PC = NC;                  // row pitch (E4 / float)
-  static constexpr int PLAT = NLAT + mod8_(PC - NLAT);  // LAT row pitch (E4), congruent to PC mod 8
   static constexpr int NTS = NC + 2;             // TS keeps a second ring (cells -2 .. T/2+1)
   static constexpr int PTS = NTS;
   static constexpr int NR = NC + 1;              // rows of an RNG row table, columns of the jump table
   // E4-slot offsets
   static constexpr int LAT4 = 0;
-  static constexpr int CARR4 = LAT4 + NLAT * PLAT;
-  static constexpr int M1RAW4 = CARR4 + NC * PC;
-  // want (LAT4 + HL*PLAT + HL) - (M1ARR4 + PC + 1) == 4 (mod 8)
-  static constexpr int PAD_M1 = mod8_((LAT4 + HL * PLAT + HL) - (M1RAW4 + PC + 1) - 4);
-  static constexpr int M1ARR4 = M1RAW4 + PAD_M1;
-  static constexpr int M2RAW4 = M1ARR4 + NC * PC;
-  // want M2ARR4 - CARR4 == 4 (mod 8)
-  static constexpr int PAD_M2 = mod8_(CARR4 + 4 - M2RAW4);
-  static constexpr int M2ARR4 = M2RAW4 + PAD_M2;
-  static_assert(mod8_((LAT4 + HL * PLAT + HL) - (M1ARR4 + PC + 1)) == 4 && mod8_(M2ARR4 - CARR4) == 4, "copy-out bank alignment");
+  static constexpr int CARR4 = LAT4 + LATSLOTS;
+  static constexpr int M1ARR4 = CARR4 + NC * PC;
+  static constexpr int M2ARR4 = M1ARR4 + NC * PC;
   // word offsets
   static constexpr int LAT = 4 * LAT4, CARR = 4 * CARR4, M1ARR = 4 * M1ARR4, M2ARR = 4 * M2ARR4;
-  static constexpr int TL = M1ARR;  // loss plane of the in-place levels: dead before M1/M2 are written
-  static_assert(NLAT * PLAT <= 4 * (M2ARR4 + NC * PC - M1ARR4), "in-place loss plane must fit in the M1/M2 arrays");
+  static constexpr int TL = M1ARR;  // loss plane of the in-place levels (indexed like LAT): dead before M1/M2 are written
+  static_assert(LATSLOTS <= 4 * 2 * NC * PC, "in-place loss plane must fit in the M1/M2 arrays");
   static constexpr int TS = M2ARR + 4 * NC * PC;
   static constexpr int TD1 = TS + NTS * PTS;
   static constexpr int TD2 = TD1 + NC * PC;
   static constexpr int JUMP = ((TD2 + NC * PC + 1) / 2) * 2;  // NR x (a, c), 8-byte aligned
   static constexpr int ROWS = JUMP + 2 * NR;                  // L x 3 x NR row start states
-  static constexpr int STARTS = ROWS + L * 3 * NR;            // L x 3 tile start states
-  static constexpr int WORDS = ((STARTS + L * 3 + 3) / 4) * 4;
+  static constexpr int WORDS = ((ROWS + L * 3 * NR + 3) / 4) * 4;
   static constexpr size_t BYTES = (size_t)WORDS * 4;
+  // slot of LAT point (row p, column q)
+  static RN_HD int lat_slot(int p, int q) { return (q & 1) * LATOFF + p * PH + (q >> 1); }
 };
 
 // Addressing of one level.  h == 1: the last level (class arrays); h >= 2: in place on LAT.
@@ -166,38 +162,39 @@ struct View {
   float* sm;
   RN_HD explicit View(float* s) : sm(s) {}
   RN_HD E4* e4(int off) const { return reinterpret_cast<E4*>(sm + off); }
-  RN_HD int kidx(int a, int b) const { return (a * h + G::HL) * G::PLAT + (b * h + G::HL); }
+  // LAT slot of the lattice point (a*h + dp, b*h + dq) in cell units + LAT offsets
+  RN_HD int lidx(int a, int b, int dp, int dq) const { return G::lat_slot(a * h + G::HL + dp, b * h + G::HL + dq); }
   RN_HD int cidx(int a, int b) const { return (a + 1) * G::PC + (b + 1); }
-  RN_HD E4& K(int a, int b) const { return e4(G::LAT)[kidx(a, b)]; }
+  RN_HD E4& K(int a, int b) const { return e4(G::LAT)[lidx(a, b, 0, 0)]; }
   RN_HD E4& C(int a, int b) const
   {
     if constexpr (h == 1) return e4(G::CARR)[cidx(a, b)];
-    else return e4(G::LAT)[kidx(a, b) + (h / 2) * G::PLAT + (h / 2)];
+    else return e4(G::LAT)[lidx(a, b, h / 2, h / 2)];
   }
   RN_HD E4& M1(int a, int b) const
   {
     if constexpr (h == 1) return e4(G::M1ARR)[cidx(a, b)];
-    else return e4(G::LAT)[kidx(a, b) + (h / 2)];
+    else return e4(G::LAT)[lidx(a, b, 0, h / 2)];
   }
   RN_HD E4& M2(int a, int b) const
   {
     if constexpr (h == 1) return e4(G::M2ARR)[cidx(a, b)];
-    else return e4(G::LAT)[kidx(a, b) + (h / 2) * G::PLAT];
+    else return e4(G::LAT)[lidx(a, b, h / 2, 0)];
   }
   RN_HD float& TS(int a, int b) const
   {
     if constexpr (h == 1) return sm[G::TS + (a + 2) * G::PTS + (b + 2)];
-    else return sm[G::TL + kidx(a, b) + (h / 2) * G::PLAT + (h / 2)];
+    else return sm[G::TL + lidx(a, b, h / 2, h / 2)];
   }
   RN_HD float& TD1(int a, int b) const
   {
     if constexpr (h == 1) return sm[G::TD1 + cidx(a, b)];
-    else return sm[G::TL + kidx(a, b) + (h / 2)];
+    else return sm[G::TL + lidx(a, b, 0, h / 2)];
   }
   RN_HD float& TD2(int a, int b) const
   {
     if constexpr (h == 1) return sm[G::TD2 + cidx(a, b)];
-    else return sm[G::TL + kidx(a, b) + (h / 2) * G::PLAT];
+    else return sm[G::TL + lidx(a, b, h / 2, 0)];
   }
 };
 
@@ -213,28 +210,42 @@ RN_HD uint32_t lcg_state_after32(uint32_t seed, uint32_t k)
   return s;
 }
 
-// state after r repetitions of the jump j (r small: a row index inside a tile)
-RN_HD uint32_t jump_apply_pow(Jump j, uint32_t r, uint32_t s)
+// The LCG jump over 2^B draws, folded at compile time: (A^(2^B), C * (A^(2^B) - 1) / (A - 1)) mod 2^32.
+template <int B>
+struct LcgPow2 {
+  static constexpr uint32_t a = LcgPow2<B - 1>::a * LcgPow2<B - 1>::a;
+  static constexpr uint32_t c = (LcgPow2<B - 1>::a + 1u) * LcgPow2<B - 1>::c;
+};
+template <>
+struct LcgPow2<0> {
+  static constexpr uint32_t a = kLcgA, c = kLcgC;
+};
+// State after k draws from `s`: one multiply-add with immediate constants per set bit of k
+// (a chain of at most 32 IMADs, no squaring chain, no table loads).
+template <int B = 0>
+RN_HD uint32_t lcg_skip(uint32_t s, uint32_t k)
 {
-  while (r) {
-    if (r & 1u) s = jump_apply(j, s);
-    j = jump_compose(j, j);
-    r >>= 1;
-  }
-  return s;
+  if (k & (1u << B)) s = LcgPow2<B>::a * s + LcgPow2<B>::c;
+  if constexpr (B < 31) return lcg_skip<B + 1>(s, k);
+  else return s;
 }
 
 // addVolcano, Terrain.cpp:129-137, for one sample whose squared index distance from the volcano is
 // r2 = fx*fx + fy*fy.  d /= maxWidth is a multiplication by the exact power of two inv_w.
 // r2 is either 0 (the centre sample) or >= 1, so sqrt / reciprocal see normal numbers.
+// FAR: the caller guarantees d >= minRad (the tile lies outside the crater), so the crater
+// branch (:133-136) is not compiled in.
+template <bool FAR>
 RN_HD float volcano_height_r2(float r2, float inv_w, float gain)
 {
   float d = sqrt_rn_normal(r2) * inv_w;
   float height = rcp_rn_normal(d);
-  const float minRad = 0.02f;
-  if (!(d >= minRad)) {  // also taken by the centre sample, where the approximations above see 0
-    if (r2 == 0.0f) d = 0.0f;
-    height = 60000.f * (d * d - minRad * minRad) + (1.0f / minRad);
+  if (!FAR) {
+    const float minRad = 0.02f;
+    if (!(d >= minRad)) {  // also taken by the centre sample, where the approximations above see 0
+      if (r2 == 0.0f) d = 0.0f;
+      height = 60000.f * (d * d - minRad * minRad) + (1.0f / minRad);
+    }
   }
   return height * gain;
 }
@@ -270,7 +281,7 @@ RN_HD void for_cells(int tid, F&& f)
 template <int L, int T, int NT, bool EDGE>
 struct Tile {
   using G = TileGeo<L, T>;
-  static constexpr int NPHASES = 3 + 3 * L;
+  static constexpr int NPHASES = 2 + 3 * L;
 
   static RN_HD bool is_edge(const TileCtx& cx, int Wout)
   {
@@ -279,35 +290,58 @@ struct Tile {
 
   // ------------------------------------------------------------------ phase 0 ----
   // Input lattice, LCG column jumps (A^c, C_c) and, per level and draw table (generateSquare,
-  // loop 1, loop 2), the LCG state in front of the tile's first cell (one 32-step skip-ahead each).
+  // loop 1, loop 2), the LCG state in front of the first cell of every cell row.
   template <int M>
-  static RN_HD void fill_start(const StageParams& sp, const TileCtx& cx, float* sm, int which)
+  static RN_HD uint32_t row_state(const StageParams& sp, const TileCtx& cx, int e)
   {
     constexpr int h = 1 << (L - 1 - M);
     using R = LevelRange<h, T>;
     const StageLevel& lv = sp.lev[M];
+    const int which = e / G::NR, r = e - which * G::NR;
     const int A0 = cx.I0 >> (L - M), B0 = cx.J0 >> (L - M);
     const uint32_t n = (uint32_t)lv.n;
     uint32_t k;
-    if (which == 0) k = lv.kS + (uint32_t)(A0 + R::S_lo) * n + (uint32_t)(B0 + R::S_lo);
-    else if (which == 1) k = lv.kD1 + (uint32_t)(A0 + R::D_lo) * n + (uint32_t)(B0 + R::D_lo);
-    else k = lv.kD2 + (uint32_t)(A0 + R::D_lo) * (n + 1u) + (uint32_t)(B0 + R::D_lo);
-    reinterpret_cast<uint32_t*>(sm + G::STARTS)[M * 3 + which] = lcg_state_after32(cx.seed, k);
+    if (which == 0) k = lv.kS + (uint32_t)(A0 + R::S_lo + r) * n + (uint32_t)(B0 + R::S_lo);
+    else if (which == 1) k = lv.kD1 + (uint32_t)(A0 + R::D_lo + r) * n + (uint32_t)(B0 + R::D_lo);
+    else k = lv.kD2 + (uint32_t)(A0 + R::D_lo + r) * (n + 1u) + (uint32_t)(B0 + R::D_lo);
+    return lcg_skip(cx.seed, k);
   }
   template <int M>
-  static RN_HD void fill_start_dispatch(const StageParams& sp, const TileCtx& cx, float* sm, int m, int which)
+  static RN_HD uint32_t row_state_dispatch(const StageParams& sp, const TileCtx& cx, int m, int e)
   {
-    if (m == M) fill_start<M>(sp, cx, sm, which);
-    else if constexpr (M + 1 < L) fill_start_dispatch<M + 1>(sp, cx, sm, m, which);
+    if constexpr (M + 1 < L) {
+      if (m != M) return row_state_dispatch<M + 1>(sp, cx, m, e);
+    }
+    return row_state<M>(sp, cx, e);
   }
 
   static RN_HD void phase_init(const StageParams& sp, const TileCtx& cx, float* sm, int tid)
   {
-    static_assert(NT >= 64 + 3 * kMaxStageLevels, "thread roles of phase_init");
-    // the last 3L threads (a different warp from the lattice loaders of small tiles) do the skip-aheads
-    if (tid >= NT - 3 * L) {
-      const int e = tid - (NT - 3 * L);
-      fill_start_dispatch<0>(sp, cx, sm, e / 3, e % 3);
+    // input lattice: LAT indices that are multiples of 2^(L-1) <-> input grid points.  The global
+    // loads are issued first so that their latency overlaps the RNG table arithmetic below.
+    constexpr int NIN = (T + 2 * G::H) / (1 << L) + 1;
+    constexpr int STEP = 1 << (L - 1);
+    constexpr int NLOAD = (NIN * NIN + NT - 1) / NT;
+    E4* lat = reinterpret_cast<E4*>(sm + G::LAT);
+    const int gi0 = (cx.I0 - G::H) >> L, gj0 = (cx.J0 - G::H) >> L;  // arithmetic shift: I0-H is a multiple of 2^L
+    const int Win = 1 << sp.din;
+    E4 v[NLOAD];
+    int slot[NLOAD];
+#pragma unroll
+    for (int q = 0; q < NLOAD; q++) {
+      const int idx = tid + q * NT;
+      const int li = idx / NIN, lj = idx - li * NIN;
+      const int gi = gi0 + li, gj = gj0 + lj;
+      slot[q] = -1;
+      if (idx < NIN * NIN && (!EDGE || (gi >= 0 && gj >= 0 && gi <= Win && gj <= Win))) {
+        slot[q] = G::lat_slot(li * STEP, lj * STEP);
+        if (cx.gin) {
+          v[q] = cx.gin[(size_t)gi * sp.gin_pitch + (size_t)gj];
+        } else {
+          const Elem e = initial_elem(gi, gj, Win);  // Terrain.cpp:46-56
+          v[q] = e4_of(pos_of(e), e.shade);
+        }
+      }
     }
     uint32_t* jump = reinterpret_cast<uint32_t*>(sm + G::JUMP);
     for (int c = tid; c < G::NR; c += NT) {
@@ -315,52 +349,14 @@ struct Tile {
       jump[2 * c] = j.a;
       jump[2 * c + 1] = j.c;
     }
-    // input lattice: LAT indices that are multiples of 2^(L-1) <-> input grid points
-    constexpr int NIN = (T + 2 * G::H) / (1 << L) + 1;
-    constexpr int STEP = 1 << (L - 1);
-    E4* lat = reinterpret_cast<E4*>(sm + G::LAT);
-    const int gi0 = (cx.I0 - G::H) >> L, gj0 = (cx.J0 - G::H) >> L;  // arithmetic shift: I0-H is a multiple of 2^L
-    const int Win = 1 << sp.din;
-    for (int idx = tid; idx < NIN * NIN; idx += NT) {
-      const int li = idx / NIN, lj = idx - li * NIN;
-      const int gi = gi0 + li, gj = gj0 + lj;
-      if (EDGE && (gi < 0 || gj < 0 || gi > Win || gj > Win)) continue;
-      E4 v;
-      if (cx.gin) {
-        v = cx.gin[(size_t)gi * sp.gin_pitch + (size_t)gj];
-      } else {
-        const Elem e = initial_elem(gi, gj, Win);  // Terrain.cpp:46-56
-        v = e4_of(pos_of(e), e.shade);
-      }
-      lat[(li * STEP) * G::PLAT + lj * STEP] = v;
-    }
-  }
-
-  // ------------------------------------------------------------------ phase 1 ----
-  // Row start states: row r of a table = the tile start state advanced by r rows of draws.
-  template <int M>
-  static RN_HD void fill_rows(const StageParams& sp, float* sm, int e)
-  {
-    constexpr int h = 1 << (L - 1 - M);
-    using R = LevelRange<h, T>;
-    const int which = e / G::NR, r = e - which * G::NR;
-    if (r >= (which == 0 ? R::NS : R::ND)) return;
-    const StageLevel& lv = sp.lev[M];
-    const uint32_t start = reinterpret_cast<const uint32_t*>(sm + G::STARTS)[M * 3 + which];
-    reinterpret_cast<uint32_t*>(sm + G::ROWS)[M * 3 * G::NR + e] = jump_apply_pow(which == 2 ? lv.jn1 : lv.jn, (uint32_t)r, start);
-  }
-  template <int M>
-  static RN_HD void fill_rows_dispatch(const StageParams& sp, float* sm, int m, int e)
-  {
-    if (m == M) fill_rows<M>(sp, sm, e);
-    else if constexpr (M + 1 < L) fill_rows_dispatch<M + 1>(sp, sm, m, e);
-  }
-  static RN_HD void phase_rows(const StageParams& sp, float* sm, int tid)
-  {
-    for (int idx = tid; idx < L * 3 * G::NR; idx += NT) {
+    uint32_t* rows = reinterpret_cast<uint32_t*>(sm + G::ROWS);
+    for (int idx = NT - 1 - tid; idx < L * 3 * G::NR; idx += NT) {  // highest threads first: not the lattice loaders
       const int m = idx / (3 * G::NR);
-      fill_rows_dispatch<0>(sp, sm, m, idx - m * 3 * G::NR);
+      rows[idx] = row_state_dispatch<0>(sp, cx, m, idx - m * 3 * G::NR);
     }
+#pragma unroll
+    for (int q = 0; q < NLOAD; q++)
+      if (slot[q] >= 0) lat[slot[q]] = v[q];
   }
 
   template <int M, int WHICH>
@@ -544,7 +540,7 @@ struct Tile {
     const int A = r >> 1, B = c >> 1;
     const int ci = (A + 1) * G::PC + (B + 1);
     if (r & 1) return (c & 1) ? G::CARR4 + ci : G::M2ARR4 + ci;
-    return (c & 1) ? G::M1ARR4 + ci : G::LAT4 + (A + G::HL) * G::PLAT + (B + G::HL);
+    return (c & 1) ? G::M1ARR4 + ci : G::LAT4 + G::lat_slot(A + G::HL, B + G::HL);
   }
 
   static RN_HD void store_point(const StageParams& sp, const TileCtx& cx, const float* sm, int r, int c, int Wout, float inv_w)
@@ -555,7 +551,7 @@ struct Tile {
     E4 e = reinterpret_cast<const E4*>(sm)[out_slot(r, c)];
     if (sp.volcano) {
       const float fx = (float)(gi - Wout / 2), fy = (float)(gj - Wout / 2);
-      e.y = e.y + volcano_height_r2(fx * fx + fy * fy, inv_w, sp.volcano_gain);
+      e.y = e.y + volcano_height_r2<false>(fx * fx + fy * fy, inv_w, sp.volcano_gain);
     }
     cx.gout[(size_t)wi * sp.gout_pitch + (size_t)wj] = e;
   }
@@ -571,28 +567,59 @@ struct Tile {
     if (!EDGE && inside) {
       // Fast path: the whole T x T tile is stored.  A thread owns one column c and the rows
       // r0, r0+RS, ...; RS is even, so its samples all come from the same class array and both
-      // the shared-memory slot and the global pointer advance by constants.
+      // the shared-memory slot and the global pointer advance by constants.  Within a warp (32
+      // consecutive columns of one row) the lane -> column map is permuted so that each quarter
+      // warp reads 8 consecutive slots of ONE array (conflict-free LDS.128) while the warp as a
+      // whole still stores 512 contiguous bytes.
       constexpr int RS = NT / T;
-      static_assert(RS % 2 == 0, "row parity must stay fixed per thread");
-      const int c = tid % T, r0 = tid / T;
+      static_assert(RS % 2 == 0 && T % 32 == 0, "row parity must stay fixed per thread; whole warps per row");
+      const int lane = tid & 31, r0 = tid / T;
+      const int q = lane >> 3, k = lane & 7;
+      int c32;
+      if (r0 & 1) c32 = (q & 1) * 16 + 2 * k + (q >> 1);                 // M2 runs (even columns), then C runs (odd columns)
+      else c32 = (q < 2) ? 4 * k + 2 * q : (q & 1) * 16 + 2 * k + 1;     // K: columns 4k / 4k+2 (one LAT half each); M1 runs
+      const int c = (tid % T) - lane + c32;
       const E4* src = reinterpret_cast<const E4*>(sm) + out_slot(r0, c);
-      const int sstep = (RS / 2) * ((r0 & 1) || (c & 1) ? G::PC : G::PLAT);
+      const int sstep = (RS / 2) * ((r0 & 1) || (c & 1) ? G::PC : G::PH);
       E4* dst = cx.gout + (size_t)(wi0 + r0) * sp.gout_pitch + (size_t)(wj0 + c);
       const size_t dstep = (size_t)RS * sp.gout_pitch;
+      if (!sp.volcano) {
+#pragma unroll 4
+        for (int kk = 0; kk < T / RS; kk++) {
+          *dst = *src;
+          src += sstep;
+          dst += dstep;
+        }
+        return;
+      }
       const float fy = (float)(cx.J0 + c - Wout / 2);
       const float fy2 = fy * fy;
       int xi = cx.I0 + r0 - Wout / 2;
+      // crater test for the whole tile: index distance of its nearest sample from the volcano
+      const int di = imax_(imax_(cx.I0 - Wout / 2, Wout / 2 - (cx.I0 + T - 1)), 0);
+      const int dj = imax_(imax_(cx.J0 - Wout / 2, Wout / 2 - (cx.J0 + T - 1)), 0);
+      const float dmin = sqrtf((float)di * (float)di + (float)dj * (float)dj) * inv_w;
+      if (dmin > 0.0205f) {  // every sample has d >= minRad with margin for rounding
 #pragma unroll 4
-      for (int k = 0; k < T / RS; k++) {
-        E4 e = *src;
-        if (sp.volcano) {
+        for (int kk = 0; kk < T / RS; kk++) {
+          E4 e = *src;
           const float fx = (float)xi;
-          e.y = e.y + volcano_height_r2(fx * fx + fy2, inv_w, sp.volcano_gain);
+          e.y = e.y + volcano_height_r2<true>(fx * fx + fy2, inv_w, sp.volcano_gain);
+          *dst = e;
+          src += sstep;
+          dst += dstep;
+          xi += RS;
         }
-        *dst = e;
-        src += sstep;
-        dst += dstep;
-        xi += RS;
+      } else {
+        for (int kk = 0; kk < T / RS; kk++) {
+          E4 e = *src;
+          const float fx = (float)xi;
+          e.y = e.y + volcano_height_r2<false>(fx * fx + fy2, inv_w, sp.volcano_gain);
+          *dst = e;
+          src += sstep;
+          dst += dstep;
+          xi += RS;
+        }
       }
       return;
     }
@@ -609,16 +636,15 @@ struct Tile {
   }
 
   // ---------------------------------------------------------------- dispatch ----
-  // phase 0 = init, 1 = RNG rows, then per level m: 2+3m = S, 3+3m = D, 4+3m = G, last = copy-out.
+  // phase 0 = init, then per level m: 1+3m = S, 2+3m = D, 3+3m = G, last = copy-out.
   template <int P>
   static RN_HD void phase(const StageParams& sp, const TileCtx& cx, float* sm, int tid)
   {
     if constexpr (P == 0) phase_init(sp, cx, sm, tid);
-    else if constexpr (P == 1) phase_rows(sp, sm, tid);
     else if constexpr (P == NPHASES - 1) phase_out(sp, cx, sm, tid);
-    else if constexpr ((P - 2) % 3 == 0) phase_S<(P - 2) / 3>(sp, cx, sm, tid);
-    else if constexpr ((P - 2) % 3 == 1) phase_D<(P - 2) / 3>(sp, cx, sm, tid);
-    else phase_G<(P - 2) / 3>(sp, cx, sm, tid);
+    else if constexpr ((P - 1) % 3 == 0) phase_S<(P - 1) / 3>(sp, cx, sm, tid);
+    else if constexpr ((P - 1) % 3 == 1) phase_D<(P - 1) / 3>(sp, cx, sm, tid);
+    else phase_G<(P - 1) / 3>(sp, cx, sm, tid);
   }
 };
 

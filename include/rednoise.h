@@ -114,6 +114,11 @@ uint64_t rn_launch_count(const rn_context* ctx);
  * global-memory kernels (one launch set per level), 2 = fused tile kernels. */
 int rn_set_algorithm(rn_context* ctx, int algo);
 
+/* Call pipelining (algorithm 2, on by default): the small coarse stages of a call run on the
+ * context's high-priority side stream into one of two scratch slots, so back-to-back calls
+ * overlap them with the output stage of the previous call.  Results are unaffected. */
+int rn_set_pipelining(rn_context* ctx, int enable);
+
 /* Stage profiling (algorithm 2): when enabled, every launch of the stage chain is bracketed by
  * CUDA events on the launching stream; rn_last_stage_times() then synchronizes and returns the
  * device time in ms of each launch of the most recent rn_terrain2d / rn_terrain2d_batch call

@@ -21,7 +21,7 @@ RN_MIN_DEPTH, RN_MAX_DEPTH = 3, 14
 SYMBOLS = [
     "rn_version", "rn_last_error_string", "rn_status_string", "rn_params_default", "rn_terrain2d_side",
     "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
-    "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device", "rn_selftest_math",
+    "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_set_pipelining", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device", "rn_selftest_math",
 ]
 
 
@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
     L.rn_launch_count.argtypes = [vp]
     L.rn_set_algorithm.argtypes = [vp, i32]
     L.rn_set_profiling.argtypes = [vp, i32]
+    L.rn_set_pipelining.argtypes = [vp, i32]
     L.rn_last_stage_times.argtypes = [vp, C.POINTER(C.c_float), i32]
     L.rn_terrain2d.argtypes = [vp, C.POINTER(Params), C.POINTER(Window), vp, sz, i32, vp, C.POINTER(C.c_float)]
     L.rn_terrain2d_batch.argtypes = [vp, C.POINTER(Params), C.POINTER(u32), i32, vp, sz, i32, vp]
@@ -137,6 +138,9 @@ class Context:
 
     def set_algorithm(self, algo: int):
         _check(lib().rn_set_algorithm(self._h, algo))
+
+    def set_pipelining(self, on: bool):
+        _check(lib().rn_set_pipelining(self._h, 1 if on else 0))
 
     def set_profiling(self, on: bool):
         _check(lib().rn_set_profiling(self._h, 1 if on else 0))

@@ -23,6 +23,16 @@ struct rn_context {
   void* field = nullptr;   size_t field_bytes = 0;    // full-field staging when dst is a window / host memory
   void* plane = nullptr;   size_t plane_bytes = 0;    // algorithm 1: offset plane; algorithm 2: coarse grids
   void* small = nullptr;   size_t small_bytes = 0;    // staging for rn_lcg_draws_device with a host dst; batch seeds
+  // algorithm 2 pipelining: the coarse stages run on a high-priority side stream into one of two
+  // scratch slots, so that they overlap the output stage of the previous call
+  cudaStream_t coarse_stream = nullptr;
+  void* slot[2] = {nullptr, nullptr};
+  size_t slot_bytes[2] = {0, 0};
+  cudaEvent_t coarse_done[2] = {nullptr, nullptr};  // coarse stages of the call using slot s have finished
+  cudaEvent_t slot_free[2] = {nullptr, nullptr};    // the output stage that read slot s has finished
+  bool slot_used[2] = {false, false};
+  uint64_t seq = 0;
+  int overlap = 1;
   // stage profiling
   int profiling = 0;
   cudaEvent_t ev[9] = {};
@@ -119,14 +129,22 @@ int synth_window_fused(rn_context* ctx, const rn_params* p, const rn_window& w, 
 {
   const Law law = law_of(p);
   const size_t need = fused_scratch_bytes(p->depth, nfields);
-  int st = ensure(&ctx->plane, &ctx->plane_bytes, need ? need : 256);
+  const int sl = (int)(ctx->seq & 1);
+  ctx->seq++;
+  int st = ensure(&ctx->slot[sl], &ctx->slot_bytes[sl], need ? need : 256);
   if (st != RN_OK) return st;
   if (ctx->profiling && !ctx->ev[0])
     for (int k = 0; k < 9; k++) RN_CUDA(cudaEventCreate(&ctx->ev[k]));
   ctx->ev_stages = 0;
+  const bool overlap = ctx->overlap && !ctx->profiling && ctx->coarse_stream;
+  if (ctx->slot_used[sl])  // the previous user of this scratch slot must have consumed it
+    RN_CUDA(cudaStreamWaitEvent(overlap ? ctx->coarse_stream : stream, ctx->slot_free[sl], 0));
   RN_CUDA(fused_generate(g, pitch, field_stride, p->depth, w.i0, w.j0, w.ni, w.nj, law, p->persistence, p->seed, dev_seeds, nfields,
-                         p->apply_volcano != 0, p->amplitude, ctx->plane, stream, &ctx->launches, ctx->profiling ? ctx->ev : nullptr,
-                         ctx->profiling ? &ctx->ev_stages : nullptr));
+                         p->apply_volcano != 0, p->amplitude, ctx->slot[sl], stream, &ctx->launches, ctx->profiling ? ctx->ev : nullptr,
+                         ctx->profiling ? &ctx->ev_stages : nullptr, overlap ? ctx->coarse_stream : nullptr,
+                         overlap ? ctx->coarse_done[sl] : nullptr));
+  RN_CUDA(cudaEventRecord(ctx->slot_free[sl], stream));
+  ctx->slot_used[sl] = true;
   return RN_OK;
 }
 
@@ -239,6 +257,17 @@ int rn_create(int device, rn_context** out_ctx)
     delete ctx;
     return fail_cuda(e, "cudaStreamCreateWithFlags");
   }
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  e = cudaStreamCreateWithPriority(&ctx->coarse_stream, cudaStreamNonBlocking, prio_hi);
+  for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+    e = cudaEventCreateWithFlags(&ctx->coarse_done[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slot_free[k], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) {
+    rn_destroy(ctx);
+    return fail_cuda(e, "side stream / events");
+  }
   *out_ctx = ctx;
   return RN_OK;
 }
@@ -247,9 +276,18 @@ int rn_destroy(rn_context* ctx)
 {
   if (!ctx) return RN_OK;
   DeviceGuard guard(ctx->device);
+  if (ctx->coarse_stream) {
+    cudaStreamSynchronize(ctx->coarse_stream);
+    cudaStreamDestroy(ctx->coarse_stream);
+  }
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
+  }
+  for (int k = 0; k < 2; k++) {
+    if (ctx->coarse_done[k]) cudaEventDestroy(ctx->coarse_done[k]);
+    if (ctx->slot_free[k]) cudaEventDestroy(ctx->slot_free[k]);
+    cudaFree(ctx->slot[k]);
   }
   for (int k = 0; k < 9; k++)
     if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
@@ -267,6 +305,13 @@ int rn_set_algorithm(rn_context* ctx, int algo)
   if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
   if (algo < 0 || algo > 2) return fail(RN_ERR_BAD_PARAM, "algorithm must be 0 (auto), 1 (level-synchronous) or 2 (fused tiles)");
   ctx->algo = algo;
+  return RN_OK;
+}
+
+int rn_set_pipelining(rn_context* ctx, int enable)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  ctx->overlap = enable != 0;
   return RN_OK;
 }
 

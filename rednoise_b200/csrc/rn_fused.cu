@@ -64,9 +64,14 @@ size_t fused_scratch_bytes(int depth, int nfields) { return chain_scratch_bytes(
 //   dst     element (i0, j0) of field 0; row pitch `pitch`, field stride `field_stride` (elements)
 //   seeds   device pointer to nfields seeds, or nullptr (then every field uses `seed`)
 //   scratch fused_scratch_bytes(depth, nfields) bytes of device memory
+//   coarse_stream / coarse_done (optional): every stage but the last is launched on coarse_stream
+//   and the last stage waits for it through the event, so that the small, latency-bound coarse
+//   stages of one call overlap the output stage of the previous call (the caller must make sure
+//   `scratch` is no longer read by an earlier call before coarse_stream reaches this one).
 cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int depth, int i0, int j0, int ni, int nj, const Law& law,
                            float persistence, uint32_t seed, const uint32_t* seeds, int nfields, int volcano, float amplitude,
-                           void* scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events, int* nstages)
+                           void* scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events, int* nstages,
+                           cudaStream_t coarse_stream, cudaEvent_t coarse_done)
 {
   StageLaunch chain[kMaxStages];
   const int ns = build_chain(chain, depth, i0, j0, ni, nj, reinterpret_cast<E4*>(dst), pitch, field_stride, scratch, nfields, law,
@@ -76,14 +81,22 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
     cudaError_t e0 = cudaEventRecord(events[0], stream);
     if (e0 != cudaSuccess) return e0;
   }
+  const bool split = coarse_stream && coarse_done && coarse_stream != stream && !events && ns > 1;
   for (int k = 0; k < ns; k++) {
     const dim3 grid(chain[k].gx, chain[k].gy, (unsigned)nfields);
+    cudaStream_t s = (split && k + 1 < ns) ? coarse_stream : stream;
     cudaError_t e;
+    if (split && k + 1 == ns) {
+      e = cudaEventRecord(coarse_done, coarse_stream);
+      if (e != cudaSuccess) return e;
+      e = cudaStreamWaitEvent(stream, coarse_done, 0);
+      if (e != cudaSuccess) return e;
+    }
     switch (chain[k].L) {
-      case 1: e = launch_stage<1>(chain[k].sp, grid, stream); break;
-      case 2: e = launch_stage<2>(chain[k].sp, grid, stream); break;
-      case 3: e = launch_stage<3>(chain[k].sp, grid, stream); break;
-      default: e = launch_stage<4>(chain[k].sp, grid, stream); break;
+      case 1: e = launch_stage<1>(chain[k].sp, grid, s); break;
+      case 2: e = launch_stage<2>(chain[k].sp, grid, s); break;
+      case 3: e = launch_stage<3>(chain[k].sp, grid, s); break;
+      default: e = launch_stage<4>(chain[k].sp, grid, s); break;
     }
     if (e != cudaSuccess) return e;
     if (events) {

@@ -23,8 +23,12 @@ struct StagePlan {
   int L;    // levels fused in this stage (1..4)
 };
 
-// Split the depth-2 levels into stages: the first stage (one CTA, its input is the analytic
-// initial lattice) takes 2..4 levels, every later stage exactly 3.
+// Split the depth-2 levels into stages.  The last stage -- the one that touches every output
+// sample -- fuses kLastStageLevels levels (one in-place level + the unit-stride last level: the
+// in-place levels are the latency-bound part of a tile, and the coarser grid it then starts from
+// is 1/16 of the output and stays in L2); every stage before it fuses 3, and the first stage
+// (its input is the analytic initial lattice) takes the remaining 1..3.
+constexpr int kLastStageLevels = 2;
 inline int plan_stages(int depth, StagePlan* out)
 {
   const int NL = depth - 2;
@@ -33,8 +37,9 @@ inline int plan_stages(int depth, StagePlan* out)
     out[ns++] = StagePlan{2, NL};
     return ns;
   }
-  const int k = (NL - 4 + 2) / 3;  // ceil((NL-4)/3) stages of 3 levels after the first
-  const int first = NL - 3 * k;    // 2..4
+  const int rest = NL - kLastStageLevels;       // >= 3
+  const int first = (rest - 1) % 3 + 1;         // 1..3
+  const int k = (rest - first) / 3;             // stages of 3 levels in between
   int d = 2;
   out[ns++] = StagePlan{d, first};
   d += first;
@@ -42,6 +47,7 @@ inline int plan_stages(int depth, StagePlan* out)
     out[ns++] = StagePlan{d, 3};
     d += 3;
   }
+  out[ns++] = StagePlan{d, kLastStageLevels};
   return ns;
 }
 

@@ -42,6 +42,18 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", {}
 
 
+def ncu_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the output-stage kernel per launch, from the committed
+    `ncu --set full` capture of this command (profiles/roofline_traffic.json); None for other workloads."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        if args.workload == "field" and args.depth == d.get("depth"):
+            return d.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------- clocks ---
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
@@ -171,17 +183,27 @@ def run_reference_arm(args):
 
 def workload_config(args):
     side = (1 << args.depth) + 1
+    what = {
+        "field": f"{side}x{side} 2D red-noise heightfield per rank (Terrain depth={args.depth}: {args.depth - 2} displacement levels/'octaves'), "
+                 f"amplitude 0.2, size 500, seed {BASE_SEED}+rank, addVolcano on",
+        "slab": f"row slabs of ONE {side}x{side} field (depth={args.depth}, seed {BASE_SEED}) sharded over the ranks"
+                + (", assembled on every rank by one NCCL all-gather" if getattr(args, "gather", False) else ""),
+        "batch": f"batch of {getattr(args, 'tiles', 0)} independent {side}x{side} fields (depth={args.depth}, seeds {BASE_SEED}+k), round-robin over the ranks",
+    }[args.workload]
+    par = {"field": f"dp{args.gpus}: one process per GPU, one independent field each, no collective",
+           "slab": f"slab{args.gpus}: equal row slabs, dependency cone recomputed per rank, no data-path collective",
+           "batch": f"dp{args.gpus}: fields round-robin over the ranks, no collective"}[args.workload]
     return {
-        "workload": f"{side}x{side} 2D red-noise heightfield (Terrain depth={args.depth}: {args.depth - 2} displacement levels/'octaves'), "
-                    f"amplitude 0.2, size 500, seed {BASE_SEED}+rank, addVolcano on" if args.workload == "field" else
-                    f"row slabs of ONE {side}x{side} field (depth={args.depth}) sharded over the ranks",
-        "baseline_config": "configs[1]: 4096x4096 2D heightfield, 12 octaves, single B200" if args.depth == 12 else f"depth {args.depth}",
-        "fields_per_step_per_rank": 1,
+        "workload": what,
+        "baseline_config": {"field": "configs[1]: 4096x4096 2D heightfield, 12 octaves, single B200",
+                            "slab": "2D analogue of configs[3] (slab-sharded large field; the reference has no 3D generator)",
+                            "batch": "configs[4]: batch of independent 1024x1024 tiles with distinct seeds"}[args.workload]
+                           if args.depth in (10, 12, 14) else f"depth {args.depth}",
+        "fields_per_step_per_rank": 1 if args.workload != "batch" else None,
         "samples_per_field": side * side,
         "bytes_per_sample": ELEM_BYTES,
-        "cache_policy": "output (268 MB at depth 12) is larger than the 126 MB L2 and there is no input; no explicit L2 flush",
-        "parallelism": f"dp{args.gpus}: one process per GPU, independent units, no collective" if args.workload == "field" else
-                       f"slab{args.gpus}: row slabs, halo recomputed, no collective",
+        "cache_policy": "the output of a step (268 MB at depth 12) is larger than the 126 MB L2 and there is no input; no explicit L2 flush",
+        "parallelism": par,
     }
 
 
@@ -214,21 +236,42 @@ def run_ours(args):
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
+    from rednoise_b200 import sharding
+    gathered = None
     if args.workload == "field":
         p = capi.default_params(seed=BASE_SEED + rank, depth=depth, apply_volcano=1)
         win = None
         ni, nj = side, side
-    else:  # one field, row slabs; the shared boundary row is produced by the lower rank only
-        p = capi.default_params(seed=BASE_SEED, depth=depth, apply_volcano=1)
-        rows = (side + world - 1) // world
-        i0 = rank * rows
-        ni, nj = max(0, min(rows, side - i0)), side
-        win = capi.Window(i0, 0, ni, nj)
-    my_samples = ni * nj
-    dst = torch.empty((ni, nj, 4), device="cuda", dtype=torch.float32)
+        my_samples = ni * nj
+        dst = torch.empty((ni, nj, 4), device="cuda", dtype=torch.float32)
 
-    def step():
-        ctx.terrain2d_ptr(p, dst.data_ptr(), window=win, dst_is_device=True, stream=stream)
+        def step():
+            ctx.terrain2d_ptr(p, dst.data_ptr(), window=win, dst_is_device=True, stream=stream)
+    elif args.workload == "slab":  # one field, equal row slabs, halo recomputed per rank, optional NCCL assembly
+        p = capi.default_params(seed=BASE_SEED, depth=depth, apply_volcano=1)
+        rows = sharding.slab_rows(side, world)
+        i0, j0, ni, nj = sharding.slab_window(side, rank, world)
+        win = capi.Window(i0, j0, max(ni, 1), nj)
+        my_samples = ni * nj
+        dst = torch.zeros((rows, nj, 4), device="cuda", dtype=torch.float32)
+
+        def step():
+            if ni:
+                ctx.terrain2d_ptr(p, dst.data_ptr(), window=win, dst_is_device=True, stream=stream)
+            if args.gather and world > 1:
+                sharding.all_gather_slabs(dst, side)
+    else:  # batch: args.tiles independent fields with distinct seeds, round-robin over the ranks
+        p = capi.default_params(seed=BASE_SEED, depth=depth, apply_volcano=1)
+        win = None
+        mine = sharding.batch_shard(args.tiles, rank, world)
+        seeds = [BASE_SEED + k for k in mine]
+        ni, nj = side, side
+        my_samples = len(mine) * side * side
+        dst = torch.empty((max(len(mine), 1), side, side, 4), device="cuda", dtype=torch.float32)
+
+        def step():
+            if seeds:
+                ctx.terrain2d_batch_ptr(p, seeds, dst.data_ptr(), dst_is_device=True, stream=stream)
 
     def barrier():
         if world > 1:
@@ -268,28 +311,45 @@ def run_ours(args):
             stage_ms = {"launch_ms": mean, "final_ms": mean[-1], "final_name": "k_stage<2,64,512> (last stage: 2 fused levels + addVolcano + store)",
                         "share_of_chain": mean[-1] / sum(mean)}
 
-    # ---- e2e: the same call with a HOST destination (pinned), D2H inside the timed region ----
-    host = torch.empty((ni, nj, 4), dtype=torch.float32, pin_memory=True)
+    # ---- e2e: the same C-ABI call with a HOST destination (pinned), D2H inside the timed region ----
     e2e_steps = max(2, min(args.steps, 5))
-    ctx.terrain2d_ptr(p, host.data_ptr(), window=win, dst_is_device=False)
+    if args.workload == "batch":
+        e2e_tiles = min(len(seeds), 32)  # bounded pinned buffer; the metric is a rate
+        host = torch.empty((max(e2e_tiles, 1), side, side, 4), dtype=torch.float32, pin_memory=True)
+        e2e_samples = e2e_tiles * side * side
+
+        def e2e_step():
+            if e2e_tiles:
+                ctx.terrain2d_batch_ptr(p, seeds[:e2e_tiles], host.data_ptr(), dst_is_device=False)
+                return float(host[e2e_tiles - 1, side // 2, side // 2, 1])
+            return 0.0
+    else:
+        host = torch.empty((max(ni, 1), nj, 4), dtype=torch.float32, pin_memory=True)
+        e2e_samples = my_samples
+
+        def e2e_step():
+            if ni:
+                ctx.terrain2d_ptr(p, host.data_ptr(), window=win, dst_is_device=False)  # blocking: synth + D2H + sync
+                return float(host[ni // 2, nj // 2, 1])  # the host reads the step's result
+            return 0.0
+    e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.terrain2d_ptr(p, host.data_ptr(), window=win, dst_is_device=False)  # blocking: synth + D2H + sync
-        _ = float(host[ni // 2, nj // 2, 1])  # the host reads the step's result
+        e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([total_ms, e2e_s, float(my_samples)], device="cuda", dtype=torch.float64)
+    t = torch.tensor([total_ms, e2e_s, float(my_samples), float(e2e_samples)], device="cuda", dtype=torch.float64)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, e2e_s, all_samples = float(tmax[0]), float(tmax[1]), float(tsum[2])
+        total_ms, e2e_s, all_samples, all_e2e_samples = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tsum[3])
     else:
-        all_samples = float(my_samples)
+        all_samples, all_e2e_samples = float(my_samples), float(e2e_samples)
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -306,14 +366,16 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak" if args.workload == "field" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args),
                          "kernel": k_name, "kernel_ms": k_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": my_samples * ELEM_BYTES,
                          "samples_per_s_bound_hbm": peak * 1e9 / ELEM_BYTES / 1e9},
-            "e2e": {"value": all_samples / e2e_s / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 48,
-                    "d2h_bytes_per_step": my_samples * ELEM_BYTES, "ms_per_step": e2e_s * 1e3,
-                    "note": "rn_terrain2d() with a pinned HOST destination: synthesis + D2H of the field + host read; "
-                            "the only input is the 48-byte rn_params"},
+            "e2e": {"value": all_e2e_samples / e2e_s / 1e9, "unit": "Gsamples/s",
+                    "h2d_bytes_per_step": 48 + (4 * len(seeds[:32]) if args.workload == "batch" else 0),
+                    "d2h_bytes_per_step": e2e_samples * ELEM_BYTES, "ms_per_step": e2e_s * 1e3,
+                    "note": "rn_terrain2d()/rn_terrain2d_batch() with a pinned HOST destination: synthesis + D2H of the samples + host read; "
+                            "the only inputs are the 48-byte rn_params (and the seeds of a batch)"},
             "gpu_launches": int(launches), "clocks": clocks, "algorithm": args.algo,
             "per_step_ms": {"min": min(per_step), "median": statistics.median(per_step), "max": max(per_step)},
         }
@@ -344,7 +406,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="field", choices=["field", "slab"])
+    ap.add_argument("--workload", default="field", choices=["field", "slab", "batch"])
+    ap.add_argument("--tiles", type=int, default=1024, help="batch workload: independent fields per step (all ranks together)")
+    ap.add_argument("--gather", action="store_true", help="slab workload: assemble the field on every rank with one NCCL all-gather per step")
     ap.add_argument("--depth", type=int, default=None)
     ap.add_argument("--algo", type=int, default=0)
     ap.add_argument("--cpu-procs", type=int, default=16, help="reference arm: concurrent single-threaded generators")
@@ -352,7 +416,7 @@ def main():
     ap.add_argument("--no-pipelining", action="store_true", help="run the coarse stages on the caller's stream (no overlap between calls)")
     args = ap.parse_args()
     if args.depth is None:
-        args.depth = 12 if args.workload == "field" else 14
+        args.depth = {"field": 12, "slab": 14, "batch": 10}[args.workload]
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)

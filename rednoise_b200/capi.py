@@ -147,8 +147,8 @@ class Context:
 
     def last_stage_times(self):
         """Device ms of each launch of the last call (coarse to fine); needs set_profiling(True)."""
-        buf = (C.c_float * 8)()
-        n = lib().rn_last_stage_times(self._h, buf, 8)
+        buf = (C.c_float * 16)()
+        n = lib().rn_last_stage_times(self._h, buf, 16)
         if n < 0:
             _check(-n)
         return [float(buf[k]) for k in range(n)]

@@ -35,7 +35,7 @@ struct rn_context {
   int overlap = 1;
   // stage profiling
   int profiling = 0;
-  cudaEvent_t ev[9] = {};
+  cudaEvent_t ev[17] = {};
   int ev_stages = 0;
 };
 
@@ -134,7 +134,7 @@ int synth_window_fused(rn_context* ctx, const rn_params* p, const rn_window& w, 
   int st = ensure(&ctx->slot[sl], &ctx->slot_bytes[sl], need ? need : 256);
   if (st != RN_OK) return st;
   if (ctx->profiling && !ctx->ev[0])
-    for (int k = 0; k < 9; k++) RN_CUDA(cudaEventCreate(&ctx->ev[k]));
+    for (int k = 0; k < 17; k++) RN_CUDA(cudaEventCreate(&ctx->ev[k]));
   ctx->ev_stages = 0;
   const bool overlap = ctx->overlap && !ctx->profiling && ctx->coarse_stream;
   if (ctx->slot_used[sl])  // the previous user of this scratch slot must have consumed it
@@ -289,7 +289,7 @@ int rn_destroy(rn_context* ctx)
     if (ctx->slot_free[k]) cudaEventDestroy(ctx->slot_free[k]);
     cudaFree(ctx->slot[k]);
   }
-  for (int k = 0; k < 9; k++)
+  for (int k = 0; k < 17; k++)
     if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
   cudaFree(ctx->field);
   cudaFree(ctx->plane);

@@ -27,9 +27,11 @@ template <int L, int T, int NT>
 __global__ void __launch_bounds__(NT, (TileGeo<L, T>::BYTES <= 113 * 1024) ? 2 : 1) k_stage(const __grid_constant__ StageParams sp)
 {
   extern __shared__ __align__(16) float sm[];
+  const int ti = sp.tile_i0 + (int)blockIdx.y, tj = sp.tile_j0 + (int)blockIdx.x;
+  if (ti >= sp.hole_i0 && ti < sp.hole_i1 && tj >= sp.hole_j0 && tj < sp.hole_j1) return;  // streamed interior (k_stream)
   TileCtx cx;
-  cx.I0 = (sp.tile_i0 + (int)blockIdx.y) * T;
-  cx.J0 = (sp.tile_j0 + (int)blockIdx.x) * T;
+  cx.I0 = ti * T;
+  cx.J0 = tj * T;
   const unsigned f = blockIdx.z;
   cx.seed = sp.seeds ? sp.seeds[f] : sp.seed;
   cx.gin = sp.gin ? sp.gin + (size_t)f * sp.gin_field_stride : nullptr;
@@ -37,6 +39,52 @@ __global__ void __launch_bounds__(NT, (TileGeo<L, T>::BYTES <= 113 * 1024) ? 2 :
   // interior tiles (no part of the dependency cone outside the lattice) take the lean instantiation
   if (Tile<L, T, NT, true>::is_edge(cx, 1 << sp.dout)) run_phases<L, T, NT, true, 0>(sp, cx, sm);
   else run_phases<L, T, NT, false, 0>(sp, cx, sm);
+}
+
+// Streaming form of one level (rn_stream.cuh): blockIdx.x = column strip, blockIdx.y = row segment.
+template <int NT>
+__global__ void __launch_bounds__(NT, 4) k_stream(const __grid_constant__ StreamParams sp)
+{
+  extern __shared__ __align__(16) float sm[];
+  using S = Stream<NT>;
+  StreamCtx cx;
+  cx.B0 = sp.b_lo + (int)blockIdx.x * sp.strip_cols;
+  cx.CW = min(sp.strip_cols, sp.b_hi - cx.B0);
+  cx.a0 = sp.a_lo + (int)blockIdx.y * sp.seg_rows;
+  cx.a1 = min(cx.a0 + sp.seg_rows, sp.a_hi);
+  const unsigned f = blockIdx.z;
+  cx.seed = sp.seeds ? sp.seeds[f] : sp.seed;
+  cx.gin = sp.gin + (size_t)f * sp.gin_field_stride;
+  cx.gout = sp.gout + (size_t)f * sp.gout_field_stride;
+  const int c = (int)threadIdx.x;
+  StreamThread th;
+  S::init(sp, cx, sm, th, c);
+  __syncthreads();
+  for (int u = cx.a0 - 1; u <= cx.a1; u++) {
+    S::interval1(sp, cx, sm, th, u, c);
+    __syncthreads();
+    S::interval2(sp, cx, sm, th, u, c);
+    __syncthreads();
+    S::interval3(sp, cx, sm, th, u, c);
+    __syncthreads();
+  }
+  S::store_rows(sp, cx, sm, cx.a1 - 1, c);
+}
+
+cudaError_t launch_stream(const StreamParams& st, dim3 grid, cudaStream_t stream)
+{
+  using G = StreamGeo<kStreamThreads>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64 && !configured[dev]) {
+    e = cudaFuncSetAttribute(k_stream<kStreamThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  k_stream<kStreamThreads><<<grid, kStreamThreads, G::BYTES, stream>>>(st);
+  return cudaGetLastError();
 }
 
 template <int L>
@@ -73,30 +121,39 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
                            void* scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events, int* nstages,
                            cudaStream_t coarse_stream, cudaEvent_t coarse_done)
 {
-  StageLaunch chain[kMaxStages];
-  const int ns = build_chain(chain, depth, i0, j0, ni, nj, reinterpret_cast<E4*>(dst), pitch, field_stride, scratch, nfields, law,
+  StageLaunch chain[kMaxLaunches];
+  const int nl = build_chain(chain, depth, i0, j0, ni, nj, reinterpret_cast<E4*>(dst), pitch, field_stride, scratch, nfields, law,
                              persistence, seed, seeds, volcano, amplitude);
-  if (nstages) *nstages = ns;
+  if (nstages) *nstages = nl;
   if (events) {
     cudaError_t e0 = cudaEventRecord(events[0], stream);
     if (e0 != cudaSuccess) return e0;
   }
-  const bool split = coarse_stream && coarse_done && coarse_stream != stream && !events && ns > 1;
-  for (int k = 0; k < ns; k++) {
-    const dim3 grid(chain[k].gx, chain[k].gy, (unsigned)nfields);
-    cudaStream_t s = (split && k + 1 < ns) ? coarse_stream : stream;
+  bool has_coarse = false;
+  for (int k = 0; k < nl; k++) has_coarse = has_coarse || !chain[k].last;
+  const bool split = coarse_stream && coarse_done && coarse_stream != stream && !events && has_coarse;
+  bool joined = false;
+  for (int k = 0; k < nl; k++) {
+    const StageLaunch& sl = chain[k];
+    const dim3 grid(sl.gx, sl.gy, (unsigned)nfields);
+    cudaStream_t s = (split && !sl.last) ? coarse_stream : stream;
     cudaError_t e;
-    if (split && k + 1 == ns) {
+    if (split && sl.last && !joined) {  // the output stage waits for the coarse stages
       e = cudaEventRecord(coarse_done, coarse_stream);
       if (e != cudaSuccess) return e;
       e = cudaStreamWaitEvent(stream, coarse_done, 0);
       if (e != cudaSuccess) return e;
+      joined = true;
     }
-    switch (chain[k].L) {
-      case 1: e = launch_stage<1>(chain[k].sp, grid, s); break;
-      case 2: e = launch_stage<2>(chain[k].sp, grid, s); break;
-      case 3: e = launch_stage<3>(chain[k].sp, grid, s); break;
-      default: e = launch_stage<4>(chain[k].sp, grid, s); break;
+    if (sl.kind == 1) {
+      e = launch_stream(sl.st, grid, s);
+    } else {
+      switch (sl.L) {
+        case 1: e = launch_stage<1>(sl.sp, grid, s); break;
+        case 2: e = launch_stage<2>(sl.sp, grid, s); break;
+        case 3: e = launch_stage<3>(sl.sp, grid, s); break;
+        default: e = launch_stage<4>(sl.sp, grid, s); break;
+      }
     }
     if (e != cudaSuccess) return e;
     if (events) {
@@ -104,7 +161,7 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
       if (e != cudaSuccess) return e;
     }
   }
-  if (launches) *launches += (uint64_t)ns;
+  if (launches) *launches += (uint64_t)nl;
   return cudaSuccess;
 }
 

@@ -12,10 +12,16 @@
 #include <stdint.h>
 #include "rn_math.cuh"
 #include "rn_tile.cuh"
+#include "rn_stream.cuh"
 
 namespace rn {
 
 constexpr int kMaxStages = 8;
+constexpr int kMaxLaunches = 2 * kMaxStages;
+constexpr int kStreamThreads = 256;   // threads (= cell columns incl. 2 halo columns) of a streaming CTA
+constexpr int kStreamLevels = 2;      // the last levels of a field are streamed (rn_stream.cuh) ...
+constexpr int kStreamMinDepth = 10;   // ... when the field is at least this deep
+constexpr int kStreamCtasTarget = 592;  // 4 CTAs per SM x 148 SMs
 constexpr int kTile = 64;  // output tile edge of every stage
 
 struct StagePlan {
@@ -29,15 +35,14 @@ struct StagePlan {
 // is 1/16 of the output and stays in L2); every stage before it fuses 3, and the first stage
 // (its input is the analytic initial lattice) takes the remaining 1..3.
 constexpr int kLastStageLevels = 2;
-inline int plan_stages(int depth, StagePlan* out)
+inline int plan_tile_levels(int NL, int last, StagePlan* out)
 {
-  const int NL = depth - 2;
   int ns = 0;
   if (NL <= 4) {
     out[ns++] = StagePlan{2, NL};
     return ns;
   }
-  const int rest = NL - kLastStageLevels;       // >= 3
+  const int rest = NL - last;                   // >= 3 for every caller
   const int first = (rest - 1) % 3 + 1;         // 1..3
   const int k = (rest - first) / 3;             // stages of 3 levels in between
   int d = 2;
@@ -47,7 +52,19 @@ inline int plan_stages(int depth, StagePlan* out)
     out[ns++] = StagePlan{d, 3};
     d += 3;
   }
-  out[ns++] = StagePlan{d, kLastStageLevels};
+  if (last > 0) out[ns++] = StagePlan{d, last};
+  return ns;
+}
+
+// Deep fields: tile stages up to depth - kStreamLevels, then one single-level stage per remaining
+// level; the interior of those is streamed (rn_stream.cuh), their frame of border tiles goes through
+// the L = 1 tile kernel.
+inline bool plan_uses_streaming(int depth) { return depth >= kStreamMinDepth; }
+inline int plan_stages(int depth, StagePlan* out)
+{
+  if (!plan_uses_streaming(depth)) return plan_tile_levels(depth - 2, kLastStageLevels, out);
+  int ns = plan_tile_levels(depth - 2 - kStreamLevels, 0, out);
+  for (int q = kStreamLevels; q > 0; q--) out[ns++] = StagePlan{depth - q, 1};
   return ns;
 }
 
@@ -96,14 +113,15 @@ inline void input_range_1d(int d, int L, int t0, int t1, int* lo, int* hi)
   if (*hi > (W >> L)) *hi = W >> L;
 }
 
-// One launch of the chain: the stage parameters (pointers resolved), its tile grid and where
-// its output lives (scratch offset in bytes, or the caller's destination for the last stage).
+// One launch of the chain.
 struct StageLaunch {
-  StageParams sp;
+  int kind;               // 0 = tile kernel k_stage<L>, 1 = streaming kernel k_stream
+  int stage;              // index of the stage this launch belongs to
+  int last;               // belongs to the last stage (runs on the caller's stream)
+  StageParams sp;         // kind 0
+  StreamParams st;        // kind 1
   int L;
-  unsigned gx, gy;        // tiles in j, tiles in i
-  size_t scratch_offset;  // intermediate stages: byte offset of field 0 inside the scratch buffer
-  size_t field_bytes;     // intermediate stages: bytes per field (256-byte aligned)
+  unsigned gx, gy;        // kind 0: tiles in j, tiles in i; kind 1: strips, segments
 };
 
 inline size_t stage_grid_bytes(int d) { const size_t side = ((size_t)1 << d) + 1; return ((side * side * sizeof(E4) + 255) / 256) * 256; }
@@ -119,13 +137,14 @@ inline size_t chain_scratch_bytes(int depth, int nfields)
 
 // Builds the launches that synthesize the window [i0,i0+ni) x [j0,j0+nj) of `nfields` depth-`depth`
 // fields into dst (element (i0,j0) of field 0; row pitch / field stride in elements).  Earlier
-// stages only compute the tiles the window's dependency cone touches.
+// stages only compute the tiles the window's dependency cone touches.  Returns the launch count.
 inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int nj, E4* dst, size_t pitch, size_t field_stride,
                        void* scratch, int nfields, const Law& law, float persistence, uint32_t seed, const uint32_t* seeds, int volcano,
                        float amplitude)
 {
   StagePlan plan[kMaxStages];
   const int ns = plan_stages(depth, plan);
+  const bool streaming = plan_uses_streaming(depth);
   int t_i0[kMaxStages], t_i1[kMaxStages], t_j0[kMaxStages], t_j1[kMaxStages];
   t_i0[ns - 1] = tile_of(depth, i0);
   t_i1[ns - 1] = tile_of(depth, i0 + ni - 1);
@@ -143,18 +162,17 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
   }
   const E4* gin = nullptr;
   size_t gin_pitch = 0, gin_stride = 0, off = 0;
+  int nl = 0;
   for (int k = 0; k < ns; k++) {
-    StageLaunch& sl = out[k];
-    sl = StageLaunch{};
-    StageParams& sp = sl.sp;
-    sl.L = plan[k].L;
+    StageParams sp{};
     sp.din = plan[k].din;
     sp.dout = plan[k].din + plan[k].L;
     sp.gin = gin;
     sp.gin_pitch = gin_pitch;
     sp.gin_field_stride = gin_stride;
     const size_t side = ((size_t)1 << sp.dout) + 1;
-    if (k == ns - 1) {
+    const bool last = (k == ns - 1);
+    if (last) {
       sp.gout = dst;
       sp.gout_pitch = pitch;
       sp.gout_field_stride = field_stride;
@@ -162,12 +180,11 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
       sp.volcano = volcano;
       sp.volcano_gain = amplitude * 0.008f;  // Terrain.cpp:137
     } else {
-      sl.scratch_offset = off;
-      sl.field_bytes = stage_grid_bytes(sp.dout);
+      const size_t fbytes = stage_grid_bytes(sp.dout);
       sp.gout = reinterpret_cast<E4*>(static_cast<char*>(scratch) + off);
       sp.gout_pitch = side;
-      sp.gout_field_stride = sl.field_bytes / sizeof(E4);
-      off += sl.field_bytes * (size_t)nfields;
+      sp.gout_field_stride = fbytes / sizeof(E4);
+      off += fbytes * (size_t)nfields;
       sp.win_i0 = 0; sp.win_j0 = 0; sp.win_ni = (int)side; sp.win_nj = (int)side;
     }
     sp.tile_i0 = t_i0[k];
@@ -176,13 +193,51 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
     sp.seeds = seeds;
     sp.law = law;
     fill_stage_levels(sp, persistence);
+    sp.hole_i0 = sp.hole_i1 = sp.hole_j0 = sp.hole_j1 = 0;
+    // streamed interior of a single-level stage: the tiles that are neither on the lattice border nor outside the needed rectangle
+    if (streaming && plan[k].L == 1 && k >= ns - kStreamLevels) {
+      const int nt = tiles_per_side(sp.dout);
+      const int si0 = t_i0[k] > 1 ? t_i0[k] : 1, si1 = t_i1[k] < nt - 2 ? t_i1[k] : nt - 2;
+      const int sj0 = t_j0[k] > 1 ? t_j0[k] : 1, sj1 = t_j1[k] < nt - 2 ? t_j1[k] : nt - 2;
+      if (si0 <= si1 && sj0 <= sj1) {
+        StageLaunch& sl = out[nl++];
+        sl = StageLaunch{};
+        sl.kind = 1; sl.stage = k; sl.last = last; sl.L = 1;
+        StreamParams& st = sl.st;
+        st.gin = sp.gin; st.gin_pitch = sp.gin_pitch; st.gin_field_stride = sp.gin_field_stride;
+        st.gout = sp.gout; st.gout_pitch = sp.gout_pitch; st.gout_field_stride = sp.gout_field_stride;
+        st.dout = sp.dout;
+        st.win_i0 = sp.win_i0; st.win_j0 = sp.win_j0; st.win_ni = sp.win_ni; st.win_nj = sp.win_nj;
+        st.a_lo = si0 * (kTile / 2); st.a_hi = (si1 + 1) * (kTile / 2);
+        st.b_lo = sj0 * (kTile / 2); st.b_hi = (sj1 + 1) * (kTile / 2);
+        const int cols = st.b_hi - st.b_lo, rows = st.a_hi - st.a_lo;
+        const int strips = (cols + (kStreamThreads - 2) - 1) / (kStreamThreads - 2);
+        st.strip_cols = (cols + strips - 1) / strips;
+        int nseg = kStreamCtasTarget / (strips * (nfields > 0 ? nfields : 1));
+        if (nseg > rows / 8) nseg = rows / 8;
+        if (nseg < 1) nseg = 1;
+        st.seg_rows = (rows + nseg - 1) / nseg;
+        st.seed = seed; st.seeds = seeds; st.law = law;
+        st.lev = sp.lev[0];
+        st.jn = jump_of((uint64_t)st.lev.n);
+        st.jn1 = jump_of((uint64_t)st.lev.n + 1);
+        st.volcano = sp.volcano; st.volcano_gain = sp.volcano_gain;
+        sl.gx = (unsigned)strips;
+        sl.gy = (unsigned)((rows + st.seg_rows - 1) / st.seg_rows);
+        sp.hole_i0 = si0; sp.hole_i1 = si1 + 1; sp.hole_j0 = sj0; sp.hole_j1 = sj1 + 1;
+      }
+    }
+    StageLaunch& sl = out[nl++];
+    sl = StageLaunch{};
+    sl.kind = 0; sl.stage = k; sl.last = last; sl.L = plan[k].L;
+    sl.sp = sp;
     sl.gx = (unsigned)(t_j1[k] - t_j0[k] + 1);
     sl.gy = (unsigned)(t_i1[k] - t_i0[k] + 1);
     gin = sp.gout;
     gin_pitch = sp.gout_pitch;
     gin_stride = sp.gout_field_stride;
   }
-  return ns;
+  return nl;
 }
 
 }  // namespace rn

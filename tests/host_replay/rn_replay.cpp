@@ -47,9 +47,11 @@ int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
     for (unsigned by = 0; by < sl.gy; by++)
       for (unsigned bx = 0; bx < sl.gx; bx++) {
         for (size_t i = 0; i < (size_t)G::WORDS + 2 * GUARD; i++) base[i] = poison ? nanv : 0.0f;
+        const int ti = sl.sp.tile_i0 + (int)by, tj = sl.sp.tile_j0 + (int)bx;
+        if (ti >= sl.sp.hole_i0 && ti < sl.sp.hole_i1 && tj >= sl.sp.hole_j0 && tj < sl.sp.hole_j1) continue;
         TileCtx cx;
-        cx.I0 = (sl.sp.tile_i0 + (int)by) * kTile;
-        cx.J0 = (sl.sp.tile_j0 + (int)bx) * kTile;
+        cx.I0 = ti * kTile;
+        cx.J0 = tj * kTile;
         cx.seed = seeds ? seeds[f] : sl.sp.seed;
         cx.gin = sl.sp.gin ? sl.sp.gin + (size_t)f * sl.sp.gin_field_stride : nullptr;
         cx.gout = sl.sp.gout + (size_t)f * sl.sp.gout_field_stride;
@@ -61,6 +63,52 @@ int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
             memcpy(&a, &base[i], 4);
             memcpy(&b, &sm[G::WORDS + i], 4);
             if (a != nanbits || b != nanbits) bad = 1;  // a write outside the tile's shared memory
+          }
+        }
+      }
+  return bad;
+}
+
+int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison)
+{
+  constexpr int SNT = kStreamThreads;
+  using S = Stream<SNT>;
+  using G = StreamGeo<SNT>;
+  const StreamParams& sp = sl.st;
+  std::vector<float> buf((size_t)G::WORDS + 2 * GUARD + 4);
+  float* base = buf.data();
+  while ((reinterpret_cast<uintptr_t>(base + GUARD) & 15u) != 0) base++;
+  float* sm = base + GUARD;
+  uint32_t nanbits = 0x7fc0dead;
+  float nanv;
+  memcpy(&nanv, &nanbits, 4);
+  int bad = 0;
+  std::vector<StreamThread> th(SNT);
+  for (int f = 0; f < nfields; f++)
+    for (unsigned by = 0; by < sl.gy; by++)
+      for (unsigned bx = 0; bx < sl.gx; bx++) {
+        for (size_t i = 0; i < (size_t)G::WORDS + 2 * GUARD; i++) base[i] = poison ? nanv : 0.0f;
+        StreamCtx cx;
+        cx.B0 = sp.b_lo + (int)bx * sp.strip_cols;
+        cx.CW = sp.strip_cols < sp.b_hi - cx.B0 ? sp.strip_cols : sp.b_hi - cx.B0;
+        cx.a0 = sp.a_lo + (int)by * sp.seg_rows;
+        cx.a1 = cx.a0 + sp.seg_rows < sp.a_hi ? cx.a0 + sp.seg_rows : sp.a_hi;
+        cx.seed = seeds ? seeds[f] : sp.seed;
+        cx.gin = sp.gin + (size_t)f * sp.gin_field_stride;
+        cx.gout = sp.gout + (size_t)f * sp.gout_field_stride;
+        for (int c = 0; c < SNT; c++) S::init(sp, cx, sm, th[c], c);
+        for (int u = cx.a0 - 1; u <= cx.a1; u++) {
+          for (int c = 0; c < SNT; c++) S::interval1(sp, cx, sm, th[c], u, c);
+          for (int c = 0; c < SNT; c++) S::interval2(sp, cx, sm, th[c], u, c);
+          for (int c = 0; c < SNT; c++) S::interval3(sp, cx, sm, th[c], u, c);
+        }
+        for (int c = 0; c < SNT; c++) S::store_rows(sp, cx, sm, cx.a1 - 1, c);
+        if (poison) {
+          for (int i = 0; i < GUARD; i++) {
+            uint32_t a, b;
+            memcpy(&a, &base[i], 4);
+            memcpy(&b, &sm[G::WORDS + i], 4);
+            if (a != nanbits || b != nanbits) bad = 1;
           }
         }
       }
@@ -114,11 +162,16 @@ int replay_terrain2d(const rn_params* p, const rn_window* win, rn_element* dst, 
   void* scratch = nullptr;
   if (sbytes && posix_memalign(&scratch, 256, sbytes) != 0) return RN_ERR_OOM;
   if (sbytes && poison) memset(scratch, 0xff, sbytes);  // NaN: untouched intermediate samples must never be consumed
-  StageLaunch chain[kMaxStages];
+  std::vector<StageLaunch> chainv(kMaxLaunches);
+  StageLaunch* chain = chainv.data();
   const int ns = build_chain(chain, p->depth, w.i0, w.j0, w.ni, w.nj, reinterpret_cast<E4*>(dst), pitch_elems, 0, scratch, 1, law,
                              p->persistence, p->seed, nullptr, p->apply_volcano, p->amplitude);
   int bad = 0;
   for (int k = 0; k < ns; k++) {
+    if (chain[k].kind == 1) {
+      bad |= run_stream(chain[k], 1, nullptr, poison & 1);
+      continue;
+    }
     switch (chain[k].L) {
       case 1: bad |= run_stage<1>(chain[k], 1, nullptr, poison & 1, (poison >> 1) & 1); break;
       case 2: bad |= run_stage<2>(chain[k], 1, nullptr, poison & 1, (poison >> 1) & 1); break;

@@ -25,7 +25,7 @@ class Win(C.Structure):
 
 @pytest.fixture(scope="module")
 def replay():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rn_tile.cuh", "rn_plan.h", "rn_math.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rn_tile.cuh", "rn_stream.cuh", "rn_plan.h", "rn_math.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", SO, SRC], check=True)
     L = C.CDLL(SO)
@@ -86,6 +86,23 @@ def test_replay_windows_are_seam_exact(replay, oracle):
     wins = [(0, 0, 1, 1), (S - 1, S - 1, 1, 1), (0, 0, S, 1), (0, S - 1, S, 1), (100, 37, 64, 64), (255, 255, 3, 3), (0, 0, 129, S),
             (384, 0, S - 384, S), (64, 64, 64, 64), (63, 63, 2, 2), (512, 0, 1, S)]
     for _ in range(10):
+        i0, j0 = (int(x) for x in rng.integers(0, S - 1, 2))
+        wins.append((i0, j0, int(rng.integers(1, S - i0 + 1)), int(rng.integers(1, S - j0 + 1))))
+    for (i0, j0, ni, nj) in wins:
+        got = run(replay, p, Win(i0, j0, ni, nj), pitch=nj + 3)
+        assert np.array_equal(got[:, :nj].view(np.uint32), full[i0:i0 + ni, j0:j0 + nj].view(np.uint32)), (i0, j0, ni, nj)
+        assert (got[:, nj:] == -7.0).all()
+
+
+def test_replay_streamed_levels_windows(replay, oracle):
+    """Depth 10 uses the streaming kernel (rn_stream.cuh) for its last two levels: windows stay seam-exact."""
+    depth = 10
+    S = (1 << depth) + 1
+    p = oracle_lib.params(seed=4711, depth=depth, apply_volcano=1)
+    full = oracle.terrain2d(p)
+    rng = np.random.default_rng(7)
+    wins = [(100, 37, 300, 500), (513, 0, 512, S), (0, 0, 129, S), (64, 64, 64, 64), (63, 63, 130, 130), (512, 512, 1, 1), (200, 200, 700, 3)]
+    for _ in range(5):
         i0, j0 = (int(x) for x in rng.integers(0, S - 1, 2))
         wins.append((i0, j0, int(rng.integers(1, S - i0 + 1)), int(rng.integers(1, S - j0 + 1))))
     for (i0, j0, ni, nj) in wins:

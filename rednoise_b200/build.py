@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librednoise_b200.so")
 SOURCES = ["rn_abi.cu", "rn_levelsync.cu", "rn_util.cu", "rn_fused.cu"]
-HEADERS = ["rn_math.cuh", "rn_kernels.h", "rn_fused.cuh", os.path.join("..", "..", "include", "rednoise.h")]
+HEADERS = ["rn_math.cuh", "rn_kernels.h", "rn_tile.cuh", "rn_stream.cuh", "rn_plan.h", os.path.join("..", "..", "include", "rednoise.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -44,10 +44,13 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    if os.environ.get("RN_LIB"):
+        return os.environ["RN_LIB"]
     if not force and not _stale():
         return OUT
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + srcs
+    extra = os.environ.get("RN_NVCC_EXTRA", "").split()  # experiments, e.g. -DRN_STREAM_THREADS=160
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + srcs
     if verbose:
         print(" ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librednoise_b200.so")
+LIB_PATH = os.environ.get("RN_LIB") or os.path.join(HERE, "librednoise_b200.so")  # RN_LIB: build experiments only
 
 RN_OK, RN_ERR_BAD_PARAM, RN_ERR_UNSUPPORTED, RN_ERR_NO_DEVICE, RN_ERR_CUDA, RN_ERR_OOM = range(6)
 RN_MIN_DEPTH, RN_MAX_DEPTH = 3, 14

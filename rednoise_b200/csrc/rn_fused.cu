@@ -42,25 +42,15 @@ __global__ void __launch_bounds__(NT, (TileGeo<L, T>::BYTES <= 113 * 1024) ? 2 :
 }
 
 // Streaming form of one level (rn_stream.cuh): blockIdx.x = column strip, blockIdx.y = row segment.
-template <int NT>
-__global__ void __launch_bounds__(NT, 4) k_stream(const __grid_constant__ StreamParams sp)
+template <int NT, bool EDGE>
+__device__ __forceinline__ void stream_march(const StreamParams& sp, const StreamCtx& cx, float* sm)
 {
-  extern __shared__ __align__(16) float sm[];
-  using S = Stream<NT>;
-  StreamCtx cx;
-  cx.B0 = sp.b_lo + (int)blockIdx.x * sp.strip_cols;
-  cx.CW = min(sp.strip_cols, sp.b_hi - cx.B0);
-  cx.a0 = sp.a_lo + (int)blockIdx.y * sp.seg_rows;
-  cx.a1 = min(cx.a0 + sp.seg_rows, sp.a_hi);
-  const unsigned f = blockIdx.z;
-  cx.seed = sp.seeds ? sp.seeds[f] : sp.seed;
-  cx.gin = sp.gin + (size_t)f * sp.gin_field_stride;
-  cx.gout = sp.gout + (size_t)f * sp.gout_field_stride;
+  using S = Stream<NT, EDGE>;
   const int c = (int)threadIdx.x;
   StreamThread th;
   S::init(sp, cx, sm, th, c);
   __syncthreads();
-  for (int u = cx.a0 - 1; u <= cx.a1; u++) {
+  for (int u = cx.a0 - 1; u <= cx.a1e; u++) {
     S::interval1(sp, cx, sm, th, u, c);
     __syncthreads();
     S::interval2(sp, cx, sm, th, u, c);
@@ -68,7 +58,16 @@ __global__ void __launch_bounds__(NT, 4) k_stream(const __grid_constant__ Stream
     S::interval3(sp, cx, sm, th, u, c);
     __syncthreads();
   }
-  S::store_rows(sp, cx, sm, cx.a1 - 1, c);
+  S::store_rows(sp, cx, sm, th, cx.a1e - 1);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, kStreamMinBlocks) k_stream(const __grid_constant__ StreamParams sp)
+{
+  extern __shared__ __align__(16) float sm[];
+  const StreamCtx cx = stream_ctx(sp, (int)blockIdx.x, (int)blockIdx.y, blockIdx.z);
+  if (stream_is_edge(sp, cx)) stream_march<NT, true>(sp, cx, sm);
+  else stream_march<NT, false>(sp, cx, sm);
 }
 
 cudaError_t launch_stream(const StreamParams& st, dim3 grid, cudaStream_t stream)
@@ -119,7 +118,7 @@ size_t fused_scratch_bytes(int depth, int nfields) { return chain_scratch_bytes(
 cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int depth, int i0, int j0, int ni, int nj, const Law& law,
                            float persistence, uint32_t seed, const uint32_t* seeds, int nfields, int volcano, float amplitude,
                            void* scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events, int* nstages,
-                           cudaStream_t coarse_stream, cudaEvent_t coarse_done)
+                           cudaStream_t coarse_stream, cudaEvent_t coarse_done, cudaEvent_t frame_done)
 {
   StageLaunch chain[kMaxLaunches];
   const int nl = build_chain(chain, depth, i0, j0, ni, nj, reinterpret_cast<E4*>(dst), pitch, field_stride, scratch, nfields, law,
@@ -132,11 +131,16 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
   bool has_coarse = false;
   for (int k = 0; k < nl; k++) has_coarse = has_coarse || !chain[k].last;
   const bool split = coarse_stream && coarse_done && coarse_stream != stream && !events && has_coarse;
-  bool joined = false;
+  bool joined = false, frame_on_side = false;
   for (int k = 0; k < nl; k++) {
     const StageLaunch& sl = chain[k];
     const dim3 grid(sl.gx, sl.gy, (unsigned)nfields);
     cudaStream_t s = (split && !sl.last) ? coarse_stream : stream;
+    // frame tiles of a partly streamed output stage (not produced by the current planner) run on the side stream
+    if (split && sl.last && sl.kind == 0 && sl.sp.hole_i1 > sl.sp.hole_i0 && frame_done) {
+      s = coarse_stream;
+      frame_on_side = true;
+    }
     cudaError_t e;
     if (split && sl.last && !joined) {  // the output stage waits for the coarse stages
       e = cudaEventRecord(coarse_done, coarse_stream);
@@ -160,6 +164,12 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
       e = cudaEventRecord(events[k + 1], stream);
       if (e != cudaSuccess) return e;
     }
+  }
+  if (frame_on_side) {  // the call is complete when the frame is, too
+    cudaError_t e = cudaEventRecord(frame_done, coarse_stream);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamWaitEvent(stream, frame_done, 0);
+    if (e != cudaSuccess) return e;
   }
   if (launches) *launches += (uint64_t)nl;
   return cudaSuccess;

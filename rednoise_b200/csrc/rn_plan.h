@@ -18,10 +18,17 @@ namespace rn {
 
 constexpr int kMaxStages = 8;
 constexpr int kMaxLaunches = 2 * kMaxStages;
-constexpr int kStreamThreads = 256;   // threads (= cell columns incl. 2 halo columns) of a streaming CTA
+#ifndef RN_STREAM_THREADS
+#define RN_STREAM_THREADS 128
+#endif
+#ifndef RN_STREAM_MINBLOCKS
+#define RN_STREAM_MINBLOCKS 7
+#endif
+constexpr int kStreamThreads = RN_STREAM_THREADS;      // threads (= cell columns incl. 3 halo / loader columns) of a streaming CTA
+constexpr int kStreamMinBlocks = RN_STREAM_MINBLOCKS;  // resident CTAs per SM the kernel is compiled for
 constexpr int kStreamLevels = 2;      // the last levels of a field are streamed (rn_stream.cuh) ...
 constexpr int kStreamMinDepth = 10;   // ... when the field is at least this deep
-constexpr int kStreamCtasTarget = 592;  // 4 CTAs per SM x 148 SMs
+constexpr int kStreamCtasTarget = 148 * kStreamMinBlocks;
 constexpr int kTile = 64;  // output tile edge of every stage
 
 struct StagePlan {
@@ -194,38 +201,40 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
     sp.law = law;
     fill_stage_levels(sp, persistence);
     sp.hole_i0 = sp.hole_i1 = sp.hole_j0 = sp.hole_j1 = 0;
-    // streamed interior of a single-level stage: the tiles that are neither on the lattice border nor outside the needed rectangle
+    // a streamed single-level stage: the whole needed rectangle goes through k_stream (no tile launch)
     if (streaming && plan[k].L == 1 && k >= ns - kStreamLevels) {
       const int nt = tiles_per_side(sp.dout);
-      const int si0 = t_i0[k] > 1 ? t_i0[k] : 1, si1 = t_i1[k] < nt - 2 ? t_i1[k] : nt - 2;
-      const int sj0 = t_j0[k] > 1 ? t_j0[k] : 1, sj1 = t_j1[k] < nt - 2 ? t_j1[k] : nt - 2;
-      if (si0 <= si1 && sj0 <= sj1) {
-        StageLaunch& sl = out[nl++];
-        sl = StageLaunch{};
-        sl.kind = 1; sl.stage = k; sl.last = last; sl.L = 1;
-        StreamParams& st = sl.st;
-        st.gin = sp.gin; st.gin_pitch = sp.gin_pitch; st.gin_field_stride = sp.gin_field_stride;
-        st.gout = sp.gout; st.gout_pitch = sp.gout_pitch; st.gout_field_stride = sp.gout_field_stride;
-        st.dout = sp.dout;
-        st.win_i0 = sp.win_i0; st.win_j0 = sp.win_j0; st.win_ni = sp.win_ni; st.win_nj = sp.win_nj;
-        st.a_lo = si0 * (kTile / 2); st.a_hi = (si1 + 1) * (kTile / 2);
-        st.b_lo = sj0 * (kTile / 2); st.b_hi = (sj1 + 1) * (kTile / 2);
-        const int cols = st.b_hi - st.b_lo, rows = st.a_hi - st.a_lo;
-        const int strips = (cols + (kStreamThreads - 2) - 1) / (kStreamThreads - 2);
-        st.strip_cols = (cols + strips - 1) / strips;
-        int nseg = kStreamCtasTarget / (strips * (nfields > 0 ? nfields : 1));
-        if (nseg > rows / 8) nseg = rows / 8;
-        if (nseg < 1) nseg = 1;
-        st.seg_rows = (rows + nseg - 1) / nseg;
-        st.seed = seed; st.seeds = seeds; st.law = law;
-        st.lev = sp.lev[0];
-        st.jn = jump_of((uint64_t)st.lev.n);
-        st.jn1 = jump_of((uint64_t)st.lev.n + 1);
-        st.volcano = sp.volcano; st.volcano_gain = sp.volcano_gain;
-        sl.gx = (unsigned)strips;
-        sl.gy = (unsigned)((rows + st.seg_rows - 1) / st.seg_rows);
-        sp.hole_i0 = si0; sp.hole_i1 = si1 + 1; sp.hole_j0 = sj0; sp.hole_j1 = sj1 + 1;
-      }
+      const int n = 1 << (sp.dout - 1);
+      StageLaunch& sl = out[nl++];
+      sl = StageLaunch{};
+      sl.kind = 1; sl.stage = k; sl.last = last; sl.L = 1;
+      StreamParams& st = sl.st;
+      st.gin = sp.gin; st.gin_pitch = sp.gin_pitch; st.gin_field_stride = sp.gin_field_stride;
+      st.gout = sp.gout; st.gout_pitch = sp.gout_pitch; st.gout_field_stride = sp.gout_field_stride;
+      st.dout = sp.dout;
+      st.win_i0 = sp.win_i0; st.win_j0 = sp.win_j0; st.win_ni = sp.win_ni; st.win_nj = sp.win_nj;
+      st.a_lo = t_i0[k] * (kTile / 2); st.a_hi = (t_i1[k] + 1) * (kTile / 2) < n ? (t_i1[k] + 1) * (kTile / 2) : n;
+      st.b_lo = t_j0[k] * (kTile / 2); st.b_hi = (t_j1[k] + 1) * (kTile / 2) < n ? (t_j1[k] + 1) * (kTile / 2) : n;
+      st.close_i = t_i1[k] == nt - 1;
+      st.close_j = t_j1[k] == nt - 1;
+      const int cols = st.b_hi - st.b_lo, rows = st.a_hi - st.a_lo;
+      const int strips = (cols + (kStreamThreads - 3) - 1) / (kStreamThreads - 3);
+      st.strip_cols = (cols + strips - 1) / strips;
+      int nseg = kStreamCtasTarget / (strips * (nfields > 0 ? nfields : 1));
+      if (nseg > rows / 8) nseg = rows / 8;
+      if (nseg < 1) nseg = 1;
+      st.seg_rows = (rows + nseg - 1) / nseg;
+      st.seed = seed; st.seeds = seeds; st.law = law;
+      st.lev = sp.lev[0];
+      st.jn = jump_of((uint64_t)st.lev.n);
+      st.jn1 = jump_of((uint64_t)st.lev.n + 1);
+      st.volcano = sp.volcano; st.volcano_gain = sp.volcano_gain;
+      sl.gx = (unsigned)((cols + st.strip_cols - 1) / st.strip_cols);
+      sl.gy = (unsigned)((rows + st.seg_rows - 1) / st.seg_rows);
+      gin = sp.gout;
+      gin_pitch = sp.gout_pitch;
+      gin_stride = sp.gout_field_stride;
+      continue;
     }
     StageLaunch& sl = out[nl++];
     sl = StageLaunch{};

@@ -10,8 +10,9 @@
 // The level's input is the complete coarser grid in global memory (L2-resident: it is 1/4 of the
 // level's output); the output is stored as full 128-bit coalesced rows, like the tile kernels.
 //
-// Only INTERIOR regions are streamed (every cell the strip touches exists); the frame of 64-sample
-// tiles along the lattice border is produced by the tile kernel (rn_tile.cuh) in the same stage.
+// Strips / segments that touch the lattice border run the EDGE instantiation (existence tests, the
+// border forms of averageDiamond / generateDiamond, the closing row and column W); all others run
+// the lean one.
 //
 // Step u of a strip (cell row u; cell (u,c) has its corner at output (2u, 2c')):
 //   interval 1   S(u): centre C(u,c) from lattice rows u, u+1        (averageSquare+generateSquare)
@@ -36,10 +37,11 @@ struct StreamParams {
   size_t gout_pitch, gout_field_stride;
   int dout;
   int win_i0, win_j0, win_ni, win_nj;
-  int a_lo, a_hi;  // owned cell rows [a_lo, a_hi) of the streamed region
-  int b_lo, b_hi;  // owned cell columns
+  int a_lo, a_hi;  // cell rows [a_lo, a_hi) of the streamed region (a_hi <= n); close_i: output row W as well
+  int b_lo, b_hi;  // cell columns; close_j: output column W as well
+  int close_i, close_j;
   int seg_rows;    // cell rows per CTA (blockIdx.y)
-  int strip_cols;  // owned cell columns per CTA (blockIdx.x), <= NT-2
+  int strip_cols;  // cell columns per CTA (blockIdx.x), <= NT-3
   uint32_t seed;
   const uint32_t* seeds;
   Law law;
@@ -52,17 +54,54 @@ struct StreamParams {
 // registers of one thread that live across barrier intervals
 struct StreamThread {
   uint32_t sS, sD1, sD2;  // LCG states whose extraction is the draw of this column's next S / loop-1 / loop-2 call
-  E4 pre, pre_x;          // prefetched lattice point(s) of row u+2 (pre_x: the extra last column, thread 0)
-  int have_pre;
+  E4 pre;                 // prefetched lattice point of row u+2 in this thread's column
+  // copy-out: this thread stores the output columns out_j and out_j + NT (relative to 2*B0) of every finished row
+  int out_j;
+  int out_ok;             // bit p: column out_j + p*NT is owned by the strip and inside the stored window
+  float out_fy2[2];       // squared column distance from the volcano
 };
 
 struct StreamCtx {
-  int B0, CW;   // first owned cell column, owned columns of this strip
-  int a0, a1;   // owned cell rows [a0, a1)
+  int B0, CW;   // first cell column, cell columns of this strip: cells [B0, B0+CW)
+  int CWe;      // CW + 1 if the strip also owns the closing output column W
+  int a0, a1;   // cell rows [a0, a1)
+  int a1e;      // a1 + 1 if the segment also owns the closing output row W
   uint32_t seed;
   const E4* gin;
   E4* gout;
+  int far;      // every sample of this CTA lies outside the volcano's crater (d >= minRad)
 };
+
+// crater test for a CTA: index distance of the nearest sample of its box from the volcano
+RN_HD int stream_box_is_far(int i_lo, int i_hi, int j_lo, int j_hi, int W)
+{
+  const int ci = W / 2;
+  const int di = imax_(imax_(i_lo - ci, ci - i_hi), 0), dj = imax_(imax_(j_lo - ci, ci - j_hi), 0);
+  const float dmin = sqrtf((float)di * (float)di + (float)dj * (float)dj) / (float)W;
+  return dmin > 0.0205f;
+}
+
+RN_HD StreamCtx stream_ctx(const StreamParams& sp, int bx, int by, unsigned f)
+{
+  StreamCtx cx;
+  cx.B0 = sp.b_lo + bx * sp.strip_cols;
+  cx.CW = imin_(sp.strip_cols, sp.b_hi - cx.B0);
+  cx.CWe = cx.CW + ((sp.close_j && cx.B0 + cx.CW == sp.b_hi) ? 1 : 0);
+  cx.a0 = sp.a_lo + by * sp.seg_rows;
+  cx.a1 = imin_(cx.a0 + sp.seg_rows, sp.a_hi);
+  cx.a1e = cx.a1 + ((sp.close_i && cx.a1 == sp.a_hi) ? 1 : 0);
+  cx.seed = sp.seeds ? sp.seeds[f] : sp.seed;
+  cx.gin = sp.gin + (size_t)f * sp.gin_field_stride;
+  cx.gout = sp.gout + (size_t)f * sp.gout_field_stride;
+  cx.far = stream_box_is_far(2 * cx.a0, 2 * cx.a1e - 1, 2 * cx.B0, 2 * (cx.B0 + cx.CWe) - 1, 1 << sp.dout);
+  return cx;
+}
+// A CTA whose cells, their neighbours and lattice points all exist can run the lean instantiation.
+RN_HD bool stream_is_edge(const StreamParams& sp, const StreamCtx& cx)
+{
+  const int n = sp.lev.n;
+  return cx.B0 < 1 || cx.B0 + cx.CW > n - 1 || cx.a0 < 2 || cx.a1 > n - 1 || cx.CWe != cx.CW || cx.a1e != cx.a1;
+}
 
 template <int NT>
 struct StreamGeo {
@@ -83,19 +122,30 @@ struct StreamGeo {
   static constexpr size_t BYTES = (size_t)WORDS * 4;
 };
 
-template <int NT>
+template <int NT, bool EDGE>
 struct Stream {
   using G = StreamGeo<NT>;
   static RN_HD E4* e4(float* sm, int row_off, int c) { return reinterpret_cast<E4*>(sm) + row_off + (c + 1); }
   static RN_HD float* f32(float* sm, int row_off, int c) { return sm + row_off + (c + 1); }
-  static RN_HD int mod(int u, int m) { return ((u % m) + m) % m; }
+  static RN_HD int mod(int u, int m) { return m == 4 ? (u & 3) : m == 2 ? (u & 1) : (int)((unsigned)(u + 3) % 3u); }  // u >= -3
 
-  static RN_HD bool active(const StreamCtx& cx, int c) { return c <= cx.CW + 1; }
+  static RN_HD bool active(const StreamCtx& cx, int c) { return c <= cx.CW + 1; }   // threads with a cell
+  static RN_HD bool loader(const StreamCtx& cx, int c) { return c <= cx.CW + 2; }   // threads with a lattice column
+  static RN_HD int steps_last(const StreamCtx& cx) { return cx.a1e; }  // steps u = a0-1 .. a1e
 
-  // lattice point (row r, cell column index c) from the coarser grid
+  // lattice point (row r, thread column c) from the coarser grid; EDGE: only if it exists
+  static RN_HD bool lattice_exists(const StreamParams& sp, const StreamCtx& cx, int r, int c)
+  {
+    const int k = cx.B0 - 1 + c, n = sp.lev.n;
+    return !EDGE || (r >= 0 && r <= n && k >= 0 && k <= n);
+  }
   static RN_HD E4 lattice(const StreamParams& sp, const StreamCtx& cx, int r, int c)
   {
     return cx.gin[(size_t)r * sp.gin_pitch + (size_t)(cx.B0 - 1 + c)];
+  }
+  static RN_HD void load_row_now(const StreamParams& sp, const StreamCtx& cx, float* sm, int r, int c)
+  {
+    if (lattice_exists(sp, cx, r, c)) *e4(sm, G::KROW + mod(r, 4) * G::P, c) = lattice(sp, cx, r, c);
   }
 
   // ------------------------------------------------------------------ start-up ----
@@ -107,155 +157,189 @@ struct Stream {
     th.sS = lcg_skip(cx.seed, sp.lev.kS + (uint32_t)u0 * n + bcol);
     th.sD1 = lcg_skip(cx.seed, sp.lev.kD1 + (uint32_t)u0 * n + bcol);
     th.sD2 = lcg_skip(cx.seed, sp.lev.kD2 + (uint32_t)(u0 - 1) * (n + 1u) + bcol);
-    th.have_pre = 0;
-    if (active(cx, c)) {
-      *e4(sm, G::KROW + mod(u0, 4) * G::P, c) = lattice(sp, cx, u0, c);
-      *e4(sm, G::KROW + mod(u0 + 1, 4) * G::P, c) = lattice(sp, cx, u0 + 1, c);
-      if (c == 0) {  // the column to the right of the last cell
-        *e4(sm, G::KROW + mod(u0, 4) * G::P, cx.CW + 2) = lattice(sp, cx, u0, cx.CW + 2);
-        *e4(sm, G::KROW + mod(u0 + 1, 4) * G::P, cx.CW + 2) = lattice(sp, cx, u0 + 1, cx.CW + 2);
+    {
+      // Lane -> column permutation inside every 32-column group: each quarter warp reads 8 consecutive
+      // slots of one class row (conflict-free LDS.128), the warp stores 512 contiguous bytes.
+      const int Wout = 1 << sp.dout;
+      const int lane = c & 31, q = lane >> 3, k = lane & 7;
+      th.out_j = (c - lane) + (q & 1) * 16 + 2 * k + (q >> 1);
+      th.out_ok = 0;
+      for (int pass = 0; pass < 2; pass++) {
+        const int j = th.out_j + pass * NT;  // column relative to 2*B0
+        const int gj = 2 * cx.B0 + j;
+        const float fy = (float)(gj - Wout / 2);
+        const bool owned = j < 2 * cx.CW || (j == 2 * cx.CW && cx.CWe != cx.CW);
+        if (owned && (unsigned)(gj - sp.win_j0) < (unsigned)sp.win_nj) th.out_ok |= 1 << pass;
+        th.out_fy2[pass] = fy * fy;
       }
+    }
+    if (loader(cx, c)) {
+      load_row_now(sp, cx, sm, u0, c);
+      load_row_now(sp, cx, sm, u0 + 1, c);
     }
   }
 
   // ------------------------------------------------------------------ interval 1 ----
-  static RN_HD void store_rows(const StreamParams& sp, const StreamCtx& cx, float* sm, int a, int c)
+  template <bool VOLCANO, bool FAR>
+  static RN_HD void store_rows_t(const StreamParams& sp, const StreamCtx& cx, float* sm, const StreamThread& th, int a)
   {
-    // output rows 2a (corners K(a,.) / mids M1(a,.)) and 2a+1 (mids M2(a,.) / centres C(a,.)),
-    // columns 2*B0 .. 2*(B0+CW)-1.  Lane -> column permutation inside every 32-column group: each
-    // quarter warp reads 8 consecutive slots of one class row, the warp stores 512 contiguous bytes.
+    // output rows 2a (corners K(a,.) / mids M1(a,.)) and 2a+1 (mids M2(a,.) / centres C(a,.))
     const int Wout = 1 << sp.dout;
     const float inv_w = 1.0f / (float)Wout;
-    const int lane = c & 31, q = lane >> 3, k = lane & 7;
-    const int c32 = (q & 1) * 16 + 2 * k + (q >> 1);
-    const int m1slot = mod(a, 2);
-    for (int pass = 0; pass < 2; pass++) {
-      const int j = pass * NT + (c - lane) + c32;  // column relative to 2*B0
-      if (j >= 2 * cx.CW) continue;
-      const int cc = (j >> 1) + 1;                 // thread index of the cell that owns the sample
-      const int gj = 2 * cx.B0 + j;
-      const int wj = gj - sp.win_j0;
-      if ((unsigned)wj >= (unsigned)sp.win_nj) continue;
-      const float fy = (float)(gj - Wout / 2);
-      const float fy2 = fy * fy;
-      for (int r = 0; r < 2; r++) {
-        const int gi = 2 * a + r;
-        const int wi = gi - sp.win_i0;
-        if ((unsigned)wi >= (unsigned)sp.win_ni) continue;
-        int row;
-        if (r == 0) row = (j & 1) ? G::M1ROW + m1slot * G::P : G::OUTK;
-        else row = (j & 1) ? G::OUTC : G::M2ROW;
-        E4 e = *e4(sm, row, cc);
-        if (sp.volcano) {
-          const float fx = (float)(gi - Wout / 2);
-          e.y = e.y + volcano_height_r2<false>(fx * fx + fy2, inv_w, sp.volcano_gain);
+    const E4* smE = reinterpret_cast<const E4*>(sm);
+    const bool odd = th.out_j & 1;
+    const int cc0 = (th.out_j >> 1) + 2, cc1 = cc0 + NT / 2;  // slot of the owning cell inside a class row (its c + 1)
+    const uint32_t wj0 = (uint32_t)(2 * cx.B0 - sp.win_j0 + th.out_j), wj1 = wj0 + NT;
+    const bool ok0 = th.out_ok & 1, ok1 = th.out_ok & 2;
+    const uint32_t pitch = (uint32_t)sp.gout_pitch;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int gi = 2 * a + r;
+      const int wi = gi - sp.win_i0;
+      if ((unsigned)wi < (unsigned)sp.win_ni && gi <= Wout) {  // uniform
+        const uint32_t rowoff = (uint32_t)wi * pitch;
+        const float fx = (float)(gi - Wout / 2);
+        const float fx2 = fx * fx;
+        const int src = r == 0 ? (odd ? G::M1ROW + (a & 1) * G::P : G::OUTK) : (odd ? G::OUTC : G::M2ROW);
+        if (ok0) {
+          E4 e = smE[src + cc0];
+          if (VOLCANO) e.y = e.y + volcano_height_r2<FAR>(fx2 + th.out_fy2[0], inv_w, sp.volcano_gain);
+          cx.gout[rowoff + wj0] = e;
         }
-        cx.gout[(size_t)wi * sp.gout_pitch + (size_t)wj] = e;
+        if (ok1) {
+          E4 e = smE[src + cc1];
+          if (VOLCANO) e.y = e.y + volcano_height_r2<FAR>(fx2 + th.out_fy2[1], inv_w, sp.volcano_gain);
+          cx.gout[rowoff + wj1] = e;
+        }
       }
     }
+  }
+  static RN_HD void store_rows(const StreamParams& sp, const StreamCtx& cx, float* sm, const StreamThread& th, int a)
+  {
+    if (!sp.volcano) store_rows_t<false, true>(sp, cx, sm, th, a);
+    else if (cx.far) store_rows_t<true, true>(sp, cx, sm, th, a);
+    else store_rows_t<true, false>(sp, cx, sm, th, a);
   }
 
   static RN_HD void interval1(const StreamParams& sp, const StreamCtx& cx, float* sm, StreamThread& th, int u, int c)
   {
     if (active(cx, c)) {
-      // S(u): averageSquare (Terrain.cpp:216-222) + generateSquare (:224-258)
-      const int r0 = G::KROW + mod(u, 4) * G::P, r1 = G::KROW + mod(u + 1, 4) * G::P;
-      const E4 k00 = *e4(sm, r0, c), k01 = *e4(sm, r0, c + 1), k10 = *e4(sm, r1, c), k11 = *e4(sm, r1, c + 1);
-      const V3 avg = vmul(vadd(vadd(vadd(pos4(k00), pos4(k10)), pos4(k01)), pos4(k11)), 0.25f);
-      const float sh = (k00.w + k10.w + k01.w + k11.w) * 0.25f;
+      const int n = sp.lev.n;
+      const int bg = cx.B0 - 1 + c;
+      const bool ex = !EDGE || (u >= 0 && u < n && bg >= 0 && bg < n);
+      float loss = 0.0f;
       const uint32_t draw = lcg_draw_from_state(th.sS);
       th.sS = jump_apply(sp.jn, th.sS);
-      const Displaced dp = displace<true>(sp.law, avg, vsub(pos4(k11), pos4(k00)), vsub(pos4(k10), pos4(k01)), sp.lev.blahS, draw);
-      *e4(sm, G::CROW + mod(u, 2) * G::P, c) = e4_of(dp.pos, sh + shade_gain(sp.law, dp.offset));
-      *f32(sm, G::TS + mod(u, 3) * G::P, c) = shade_loss(sp.law, dp.offset);
+      if (ex) {
+        // S(u): averageSquare (Terrain.cpp:216-222) + generateSquare (:224-258)
+        const int r0 = G::KROW + mod(u, 4) * G::P, r1 = G::KROW + mod(u + 1, 4) * G::P;
+        const E4 k00 = *e4(sm, r0, c), k01 = *e4(sm, r0, c + 1), k10 = *e4(sm, r1, c), k11 = *e4(sm, r1, c + 1);
+        const V3 avg = vmul(vadd(vadd(vadd(pos4(k00), pos4(k10)), pos4(k01)), pos4(k11)), 0.25f);
+        const float sh = (k00.w + k10.w + k01.w + k11.w) * 0.25f;
+        const Displaced dp = displace<true>(sp.law, avg, vsub(pos4(k11), pos4(k00)), vsub(pos4(k10), pos4(k01)), sp.lev.blahS, draw);
+        *e4(sm, G::CROW + mod(u, 2) * G::P, c) = e4_of(dp.pos, sh + shade_gain(sp.law, dp.offset));
+        loss = shade_loss(sp.law, dp.offset);
+      }
+      *f32(sm, G::TS + mod(u, 3) * G::P, c) = loss;
     }
     // the rows G(u-1) finished: cell row u-2
-    if (u - 2 >= cx.a0 && u - 2 < cx.a1) store_rows(sp, cx, sm, u - 2, c);
+    if (u - 2 >= cx.a0 && u - 2 < cx.a1e) store_rows(sp, cx, sm, th, u - 2);
   }
 
   // ------------------------------------------------------------------ interval 2 ----
-  static RN_HD E4 mid(const Law& law, const E4& ex0, const E4& ex1, const E4& ey0, const E4& ey1, float blah, uint32_t draw, float* loss_out)
-  {
-    const V3 avg = vmul(vadd(vadd(vadd(pos4(ex0), pos4(ex1)), pos4(ey0)), pos4(ey1)), 0.25f);
-    const float sh = (ex0.w + ex1.w + ey0.w + ey1.w) * 0.25f;
-    const Displaced dp = displace<true>(law, avg, vsub(pos4(ex0), pos4(ex1)), vsub(pos4(ey1), pos4(ey0)), blah, draw);
-    *loss_out = shade_loss(law, dp.offset);
-    return e4_of(dp.pos, sh + shade_gain(law, dp.offset));
-  }
-
   static RN_HD void interval2(const StreamParams& sp, const StreamCtx& cx, float* sm, StreamThread& th, int u, int c)
   {
-    // prefetch lattice row u+2 (needed by S(u+1)); it lands in shared memory in interval 3
-    th.have_pre = 0;
-    if (active(cx, c) && u + 1 <= cx.a1) {
-      th.pre = lattice(sp, cx, u + 2, c);
-      if (c == 0) th.pre_x = lattice(sp, cx, u + 2, cx.CW + 2);
-      th.have_pre = 1;
-    }
+    // prefetch lattice row u+2 (needed by S(u+1) and D(u+2)); it lands in shared memory in interval 3
+    if (loader(cx, c) && u + 1 <= cx.a1e && lattice_exists(sp, cx, u + 2, c)) th.pre = lattice(sp, cx, u + 2, c);
     if (!active(cx, c)) return;
-    const int ts2 = G::TS + mod(u - 2, 3) * G::P, ts1 = G::TS + mod(u - 1, 3) * G::P, ts0 = G::TS + mod(u, 3) * G::P;
-    const int kr = G::KROW + mod(u, 4) * G::P, krm = G::KROW + mod(u - 1, 4) * G::P;
-    const int cr = G::CROW + mod(u, 2) * G::P, crm = G::CROW + mod(u - 1, 2) * G::P;
-    // corner shades as generateSquare left them (Terrain.cpp:252-255): minus the scatter of the 4 surrounding centres
-    const float t1m = *f32(sm, ts1, c - 1), t10 = *f32(sm, ts1, c), t0m = *f32(sm, ts0, c - 1), t00 = *f32(sm, ts0, c);
-    E4 k00 = *e4(sm, kr, c);  // K(u, c)
-    k00.w = (((k00.w - t1m) - t10) - t0m) - t00;
-    {  // loop 1: M1(u, c) at output (2u, 2c'+1): x neighbours C(u-1,c), C(u,c); y neighbours K(u,c), K(u,c+1)
-      E4 k01 = *e4(sm, kr, c + 1);
-      k01.w = (((k01.w - t10) - *f32(sm, ts1, c + 1)) - t00) - *f32(sm, ts0, c + 1);
-      const uint32_t draw = lcg_draw_from_state(th.sD1);
-      th.sD1 = jump_apply(sp.jn, th.sD1);
-      float loss;
-      const E4 m = mid(sp.law, *e4(sm, crm, c), *e4(sm, cr, c), k00, k01, sp.lev.blahD, draw, &loss);
-      *e4(sm, G::M1ROW + mod(u, 2) * G::P, c) = m;
-      *f32(sm, G::TD1 + mod(u, 2) * G::P, c) = loss;
+    const int n = sp.lev.n;
+    const int bg = cx.B0 - 1 + c;
+    bool v1 = true, v2 = true;  // M1(u, c), M2(u-1, c) exist
+    if (EDGE) {
+      v1 = u >= 0 && u <= n && bg >= 0 && bg < n;
+      v2 = u - 1 >= 0 && u - 1 < n && bg >= 0 && bg <= n;
     }
-    {  // loop 2: M2(u-1, c) at output (2u-1, 2c'): x neighbours K(u-1,c), K(u,c); y neighbours C(u-1,c-1), C(u-1,c)
-      E4 km = *e4(sm, krm, c);  // K(u-1, c)
-      km.w = (((km.w - *f32(sm, ts2, c - 1)) - *f32(sm, ts2, c)) - t1m) - t10;
-      const uint32_t draw = lcg_draw_from_state(th.sD2);
-      th.sD2 = jump_apply(sp.jn1, th.sD2);
-      float loss;
-      const E4 m = mid(sp.law, km, k00, *e4(sm, crm, c - 1), *e4(sm, crm, c), sp.lev.blahD, draw, &loss);
-      *e4(sm, G::M2ROW, c) = m;
-      *f32(sm, G::TD2 + mod(u - 1, 2) * G::P, c) = loss;
+    const uint32_t draw1 = lcg_draw_from_state(th.sD1), draw2 = lcg_draw_from_state(th.sD2);
+    th.sD1 = jump_apply(sp.jn, th.sD1);
+    th.sD2 = jump_apply(sp.jn1, th.sD2);
+    float loss1 = 0.0f, loss2 = 0.0f;
+    if (v1 || v2) {
+      const int ts2 = G::TS + mod(u - 2, 3) * G::P, ts1 = G::TS + mod(u - 1, 3) * G::P, ts0 = G::TS + mod(u, 3) * G::P;
+      const int kr = G::KROW + mod(u, 4) * G::P, krm = G::KROW + mod(u - 1, 4) * G::P;
+      const int cr = G::CROW + mod(u, 2) * G::P, crm = G::CROW + mod(u - 1, 2) * G::P;
+      // corner shades as generateSquare left them (Terrain.cpp:252-255): minus the scatter of the 4 surrounding centres
+      const float t1m = *f32(sm, ts1, c - 1), t10 = *f32(sm, ts1, c), t0m = *f32(sm, ts0, c - 1), t00 = *f32(sm, ts0, c);
+      E4 k00 = *e4(sm, kr, c);  // K(u, c)
+      k00.w = (((k00.w - t1m) - t10) - t0m) - t00;
+      if (v1) {  // loop 1: M1(u, c) at output (2u, 2c'+1): x neighbours C(u-1,c), C(u,c); y neighbours K(u,c), K(u,c+1)
+        E4 k01 = *e4(sm, kr, c + 1);
+        k01.w = (((k01.w - t10) - *f32(sm, ts1, c + 1)) - t00) - *f32(sm, ts0, c + 1);
+        E4 m;
+        if (EDGE && (u == 0 || u == n)) {
+          const E4 dummy = k00;
+          m = mid_border(sp.law, u == 0 ? dummy : *e4(sm, crm, c), u == n ? dummy : *e4(sm, cr, c), k00, k01, u == 0, u == n, false, false,
+                         sp.lev.blahDh, draw1, &loss1);
+        } else {
+          m = mid_interior(sp.law, *e4(sm, crm, c), *e4(sm, cr, c), k00, k01, sp.lev.blahD, draw1, &loss1);
+        }
+        *e4(sm, G::M1ROW + mod(u, 2) * G::P, c) = m;
+      }
+      if (v2) {  // loop 2: M2(u-1, c) at output (2u-1, 2c'): x neighbours K(u-1,c), K(u,c); y neighbours C(u-1,c-1), C(u-1,c)
+        E4 km = *e4(sm, krm, c);  // K(u-1, c)
+        km.w = (((km.w - *f32(sm, ts2, c - 1)) - *f32(sm, ts2, c)) - t1m) - t10;
+        E4 m;
+        if (EDGE && (bg == 0 || bg == n)) {
+          const E4 dummy = k00;
+          m = mid_border(sp.law, km, k00, bg == 0 ? dummy : *e4(sm, crm, c - 1), bg == n ? dummy : *e4(sm, crm, c), false, false, bg == 0, bg == n,
+                         sp.lev.blahD, draw2, &loss2);
+        } else {
+          m = mid_interior(sp.law, km, k00, *e4(sm, crm, c - 1), *e4(sm, crm, c), sp.lev.blahD, draw2, &loss2);
+        }
+        *e4(sm, G::M2ROW, c) = m;
+      }
     }
+    *f32(sm, G::TD1 + mod(u, 2) * G::P, c) = loss1;
+    *f32(sm, G::TD2 + mod(u - 1, 2) * G::P, c) = loss2;
   }
 
   // ------------------------------------------------------------------ interval 3 ----
   static RN_HD void interval3(const StreamParams& sp, const StreamCtx& cx, float* sm, StreamThread& th, int u, int c)
   {
     if (active(cx, c)) {
+      const int n = sp.lev.n;
+      const int bg = cx.B0 - 1 + c;
       const int ts2 = G::TS + mod(u - 2, 3) * G::P, ts1 = G::TS + mod(u - 1, 3) * G::P;
       const int td1m = G::TD1 + mod(u - 1, 2) * G::P, td10 = G::TD1 + mod(u, 2) * G::P;
       const int td2mm = G::TD2 + mod(u - 2, 2) * G::P, td2m = G::TD2 + mod(u - 1, 2) * G::P;
-      // corner K(u-1, c): generateSquare scatter of 4 squares, then loop 1 (same row), loop 2 (same column)
-      E4 k = *e4(sm, G::KROW + mod(u - 1, 4) * G::P, c);
-      float sh = k.w;
-      sh -= *f32(sm, ts2, c - 1);
-      sh -= *f32(sm, ts2, c);
-      sh -= *f32(sm, ts1, c - 1);
-      sh -= *f32(sm, ts1, c);
-      sh -= *f32(sm, td1m, c - 1);
-      sh -= *f32(sm, td1m, c);
-      sh -= *f32(sm, td2mm, c);
-      sh -= *f32(sm, td2m, c);
-      k.w = sh;
-      *e4(sm, G::OUTK, c) = k;
-      // centre C(u-1, c): loop-1 mids above and below, loop-2 mids left and right
-      E4 ce = *e4(sm, G::CROW + mod(u - 1, 2) * G::P, c);
-      float shc = ce.w;
-      shc -= *f32(sm, td1m, c);
-      shc -= *f32(sm, td10, c);
-      shc -= *f32(sm, td2m, c);
-      shc -= *f32(sm, td2m, c + 1);
-      ce.w = shc;
-      *e4(sm, G::OUTC, c) = ce;
+      if (!EDGE || (u - 1 >= 0 && u - 1 <= n && bg >= 0 && bg <= n)) {
+        // corner K(u-1, c): generateSquare scatter of 4 squares, then loop 1 (same row), loop 2 (same column)
+        E4 k = *e4(sm, G::KROW + mod(u - 1, 4) * G::P, c);
+        float sh = k.w;
+        sh -= *f32(sm, ts2, c - 1);
+        sh -= *f32(sm, ts2, c);
+        sh -= *f32(sm, ts1, c - 1);
+        sh -= *f32(sm, ts1, c);
+        sh -= *f32(sm, td1m, c - 1);
+        sh -= *f32(sm, td1m, c);
+        sh -= *f32(sm, td2mm, c);
+        sh -= *f32(sm, td2m, c);
+        k.w = sh;
+        *e4(sm, G::OUTK, c) = k;
+      }
+      if (!EDGE || (u - 1 >= 0 && u - 1 < n && bg >= 0 && bg < n)) {
+        // centre C(u-1, c): loop-1 mids above and below, loop-2 mids left and right
+        E4 ce = *e4(sm, G::CROW + mod(u - 1, 2) * G::P, c);
+        float shc = ce.w;
+        shc -= *f32(sm, td1m, c);
+        shc -= *f32(sm, td10, c);
+        shc -= *f32(sm, td2m, c);
+        shc -= *f32(sm, td2m, c + 1);
+        ce.w = shc;
+        *e4(sm, G::OUTC, c) = ce;
+      }
     }
-    if (th.have_pre) {
-      *e4(sm, G::KROW + mod(u + 2, 4) * G::P, c) = th.pre;
-      if (c == 0) *e4(sm, G::KROW + mod(u + 2, 4) * G::P, cx.CW + 2) = th.pre_x;
-    }
+    // the row prefetched in interval 2
+    if (loader(cx, c) && u + 1 <= cx.a1e && lattice_exists(sp, cx, u + 2, c)) *e4(sm, G::KROW + mod(u + 2, 4) * G::P, c) = th.pre;
   }
 };
 

@@ -251,6 +251,41 @@ RN_HD float volcano_height_r2(float r2, float inv_w, float gain)
   return height * gain;
 }
 
+// Border form of averageDiamond + generateDiamond (one clamped neighbour is the midpoint
+// itself: fresh average as position, untouched 1.0f as shade; Terrain.cpp:149-167,175-182).
+RN_HD E4 mid_border(const Law& law, E4 ex0, E4 ex1, E4 ey0, E4 ey1, bool sx0, bool sx1, bool sy0, bool sy1, float blah,
+                           uint32_t draw, float* loss_out)
+{
+  const bool xb = sx0 || sx1;
+  if (sx0) ex0.w = 1.0f;
+  if (sx1) ex1.w = 1.0f;
+  if (sy0) ey0.w = 1.0f;
+  if (sy1) ey1.w = 1.0f;
+  V3 avg;
+  if (xb) avg = vmul(vadd(pos4(ey0), pos4(ey1)), 0.5f);
+  else avg = vmul(vadd(pos4(ex0), pos4(ex1)), 0.5f);
+  float sh = (ex0.w + ex1.w + ey0.w + ey1.w) * 0.25f;
+  const V3 px0 = sx0 ? avg : pos4(ex0), px1 = sx1 ? avg : pos4(ex1);
+  const V3 py0 = sy0 ? avg : pos4(ey0), py1 = sy1 ? avg : pos4(ey1);
+  const Displaced dp = displace<true>(law, avg, vsub(px0, px1), vsub(py1, py0), blah, draw);
+  const float loss = shade_loss(law, dp.offset);
+  sh += shade_gain(law, dp.offset);
+  sh -= loss;  // the scatter onto the clamped index lands on the midpoint itself
+  *loss_out = loss;
+  return e4_of(dp.pos, sh);
+}
+
+RN_HD E4 mid_interior(const Law& law, const E4& ex0, const E4& ex1, const E4& ey0, const E4& ey1, float blah, uint32_t draw,
+                             float* loss_out)
+{
+  const V3 avg = vmul(vadd(vadd(vadd(pos4(ex0), pos4(ex1)), pos4(ey0)), pos4(ey1)), 0.25f);
+  const float sh = (ex0.w + ex1.w + ey0.w + ey1.w) * 0.25f;
+  const Displaced dp = displace<true>(law, avg, vsub(pos4(ex0), pos4(ex1)), vsub(pos4(ey1), pos4(ey0)), blah, draw);
+  *loss_out = shade_loss(law, dp.offset);
+  return e4_of(dp.pos, sh + shade_gain(law, dp.offset));
+}
+
+
 struct TileCtx {
   int I0, J0;        // output-grid coordinates of the tile origin
   uint32_t seed;
@@ -397,40 +432,6 @@ struct Tile {
   }
 
   // ------------------------------------------------------------------ phase D ----
-  // Border form of averageDiamond + generateDiamond (one clamped neighbour is the midpoint
-  // itself: fresh average as position, untouched 1.0f as shade; Terrain.cpp:149-167,175-182).
-  static RN_HD E4 mid_border(const Law& law, E4 ex0, E4 ex1, E4 ey0, E4 ey1, bool sx0, bool sx1, bool sy0, bool sy1, float blah,
-                             uint32_t draw, float* loss_out)
-  {
-    const bool xb = sx0 || sx1;
-    if (sx0) ex0.w = 1.0f;
-    if (sx1) ex1.w = 1.0f;
-    if (sy0) ey0.w = 1.0f;
-    if (sy1) ey1.w = 1.0f;
-    V3 avg;
-    if (xb) avg = vmul(vadd(pos4(ey0), pos4(ey1)), 0.5f);
-    else avg = vmul(vadd(pos4(ex0), pos4(ex1)), 0.5f);
-    float sh = (ex0.w + ex1.w + ey0.w + ey1.w) * 0.25f;
-    const V3 px0 = sx0 ? avg : pos4(ex0), px1 = sx1 ? avg : pos4(ex1);
-    const V3 py0 = sy0 ? avg : pos4(ey0), py1 = sy1 ? avg : pos4(ey1);
-    const Displaced dp = displace<true>(law, avg, vsub(px0, px1), vsub(py1, py0), blah, draw);
-    const float loss = shade_loss(law, dp.offset);
-    sh += shade_gain(law, dp.offset);
-    sh -= loss;  // the scatter onto the clamped index lands on the midpoint itself
-    *loss_out = loss;
-    return e4_of(dp.pos, sh);
-  }
-
-  static RN_HD E4 mid_interior(const Law& law, const E4& ex0, const E4& ex1, const E4& ey0, const E4& ey1, float blah, uint32_t draw,
-                               float* loss_out)
-  {
-    const V3 avg = vmul(vadd(vadd(vadd(pos4(ex0), pos4(ex1)), pos4(ey0)), pos4(ey1)), 0.25f);
-    const float sh = (ex0.w + ex1.w + ey0.w + ey1.w) * 0.25f;
-    const Displaced dp = displace<true>(law, avg, vsub(pos4(ex0), pos4(ex1)), vsub(pos4(ey1), pos4(ey0)), blah, draw);
-    *loss_out = shade_loss(law, dp.offset);
-    return e4_of(dp.pos, sh + shade_gain(law, dp.offset));
-  }
-
   template <int M>
   static RN_HD void phase_D(const StageParams& sp, const TileCtx& cx, float* sm, int tid)
   {

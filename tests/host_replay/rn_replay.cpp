@@ -69,12 +69,25 @@ int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
   return bad;
 }
 
-int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison)
+template <bool EDGE>
+void stream_march_host(const StreamParams& sp, const StreamCtx& cx, float* sm, std::vector<StreamThread>& th)
 {
   constexpr int SNT = kStreamThreads;
-  using S = Stream<SNT>;
+  using S = Stream<SNT, EDGE>;
+  for (int c = 0; c < SNT; c++) S::init(sp, cx, sm, th[c], c);
+  for (int u = cx.a0 - 1; u <= cx.a1e; u++) {
+    for (int c = 0; c < SNT; c++) S::interval1(sp, cx, sm, th[c], u, c);
+    for (int c = 0; c < SNT; c++) S::interval2(sp, cx, sm, th[c], u, c);
+    for (int c = 0; c < SNT; c++) S::interval3(sp, cx, sm, th[c], u, c);
+  }
+  for (int c = 0; c < SNT; c++) S::store_rows(sp, cx, sm, th[c], cx.a1e - 1);
+}
+
+int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
+{
+  constexpr int SNT = kStreamThreads;
   using G = StreamGeo<SNT>;
-  const StreamParams& sp = sl.st;
+  const StreamParams& sp0 = sl.st;
   std::vector<float> buf((size_t)G::WORDS + 2 * GUARD + 4);
   float* base = buf.data();
   while ((reinterpret_cast<uintptr_t>(base + GUARD) & 15u) != 0) base++;
@@ -88,21 +101,12 @@ int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int po
     for (unsigned by = 0; by < sl.gy; by++)
       for (unsigned bx = 0; bx < sl.gx; bx++) {
         for (size_t i = 0; i < (size_t)G::WORDS + 2 * GUARD; i++) base[i] = poison ? nanv : 0.0f;
-        StreamCtx cx;
-        cx.B0 = sp.b_lo + (int)bx * sp.strip_cols;
-        cx.CW = sp.strip_cols < sp.b_hi - cx.B0 ? sp.strip_cols : sp.b_hi - cx.B0;
-        cx.a0 = sp.a_lo + (int)by * sp.seg_rows;
-        cx.a1 = cx.a0 + sp.seg_rows < sp.a_hi ? cx.a0 + sp.seg_rows : sp.a_hi;
-        cx.seed = seeds ? seeds[f] : sp.seed;
-        cx.gin = sp.gin + (size_t)f * sp.gin_field_stride;
-        cx.gout = sp.gout + (size_t)f * sp.gout_field_stride;
-        for (int c = 0; c < SNT; c++) S::init(sp, cx, sm, th[c], c);
-        for (int u = cx.a0 - 1; u <= cx.a1; u++) {
-          for (int c = 0; c < SNT; c++) S::interval1(sp, cx, sm, th[c], u, c);
-          for (int c = 0; c < SNT; c++) S::interval2(sp, cx, sm, th[c], u, c);
-          for (int c = 0; c < SNT; c++) S::interval3(sp, cx, sm, th[c], u, c);
-        }
-        for (int c = 0; c < SNT; c++) S::store_rows(sp, cx, sm, cx.a1 - 1, c);
+        StreamParams sp = sp0;
+        if (seeds) { sp.seeds = nullptr; sp.seed = seeds[f]; }
+        const StreamCtx cx = stream_ctx(sp, (int)bx, (int)by, (unsigned)f);
+        memset(th.data(), poison ? 0xff : 0, sizeof(StreamThread) * th.size());
+        if (force_edge || stream_is_edge(sp, cx)) stream_march_host<true>(sp, cx, sm, th);
+        else stream_march_host<false>(sp, cx, sm, th);
         if (poison) {
           for (int i = 0; i < GUARD; i++) {
             uint32_t a, b;
@@ -169,7 +173,7 @@ int replay_terrain2d(const rn_params* p, const rn_window* win, rn_element* dst, 
   int bad = 0;
   for (int k = 0; k < ns; k++) {
     if (chain[k].kind == 1) {
-      bad |= run_stream(chain[k], 1, nullptr, poison & 1);
+      bad |= run_stream(chain[k], 1, nullptr, poison & 1, (poison >> 1) & 1);
       continue;
     }
     switch (chain[k].L) {

@@ -220,6 +220,8 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
       const int cols = st.b_hi - st.b_lo, rows = st.a_hi - st.a_lo;
       const int strips = (cols + (kStreamThreads - 3) - 1) / (kStreamThreads - 3);
       st.strip_cols = (cols + strips - 1) / strips;
+      // a segment costs 2 warm-up steps, but small levels are latency-bound: filling every CTA slot wins
+      // (measured: 1025 -> 2049 level 40 us with 8-row segments, 52 us with 24-row segments)
       int nseg = kStreamCtasTarget / (strips * (nfields > 0 ? nfields : 1));
       if (nseg > rows / 8) nseg = rows / 8;
       if (nseg < 1) nseg = 1;

@@ -55,6 +55,7 @@ struct StreamParams {
 struct StreamThread {
   uint32_t sS, sD1, sD2;  // LCG states whose extraction is the draw of this column's next S / loop-1 / loop-2 call
   E4 pre;                 // prefetched lattice point of row u+2 in this thread's column
+  float sg0, sg1;         // shade of corners K(u,c) / K(u-1,c) after generateSquare's scatter (carried from step to step)
   // copy-out: this thread stores the output columns out_j and out_j + NT (relative to 2*B0) of every finished row
   int out_j;
   int out_ok;             // bit p: column out_j + p*NT is owned by the strip and inside the stored window
@@ -157,6 +158,7 @@ struct Stream {
     th.sS = lcg_skip(cx.seed, sp.lev.kS + (uint32_t)u0 * n + bcol);
     th.sD1 = lcg_skip(cx.seed, sp.lev.kD1 + (uint32_t)u0 * n + bcol);
     th.sD2 = lcg_skip(cx.seed, sp.lev.kD2 + (uint32_t)(u0 - 1) * (n + 1u) + bcol);
+    th.sg0 = th.sg1 = 0.0f;
     {
       // Lane -> column permutation inside every 32-column group: each quarter warp reads 8 consecutive
       // slots of one class row (conflict-free LDS.128), the warp stores 512 contiguous bytes.
@@ -263,14 +265,18 @@ struct Stream {
     th.sD1 = jump_apply(sp.jn, th.sD1);
     th.sD2 = jump_apply(sp.jn1, th.sD2);
     float loss1 = 0.0f, loss2 = 0.0f;
+    // corner shades as generateSquare left them (Terrain.cpp:252-255): minus the scatter of the 4 surrounding
+    // centres.  sg(u,c) is computed here once and carried to the next step (as sg(u-1,c)) and to interval 3.
+    const int ts1 = G::TS + mod(u - 1, 3) * G::P, ts0 = G::TS + mod(u, 3) * G::P;
+    const int kr = G::KROW + mod(u, 4) * G::P;
+    const float t10 = *f32(sm, ts1, c), t00 = *f32(sm, ts0, c);
+    E4 k00 = *e4(sm, kr, c);  // K(u, c)
+    k00.w = (((k00.w - *f32(sm, ts1, c - 1)) - t10) - *f32(sm, ts0, c - 1)) - t00;
+    th.sg1 = th.sg0;   // sg(u-1, c)
+    th.sg0 = k00.w;    // sg(u, c)
     if (v1 || v2) {
-      const int ts2 = G::TS + mod(u - 2, 3) * G::P, ts1 = G::TS + mod(u - 1, 3) * G::P, ts0 = G::TS + mod(u, 3) * G::P;
-      const int kr = G::KROW + mod(u, 4) * G::P, krm = G::KROW + mod(u - 1, 4) * G::P;
+      const int krm = G::KROW + mod(u - 1, 4) * G::P;
       const int cr = G::CROW + mod(u, 2) * G::P, crm = G::CROW + mod(u - 1, 2) * G::P;
-      // corner shades as generateSquare left them (Terrain.cpp:252-255): minus the scatter of the 4 surrounding centres
-      const float t1m = *f32(sm, ts1, c - 1), t10 = *f32(sm, ts1, c), t0m = *f32(sm, ts0, c - 1), t00 = *f32(sm, ts0, c);
-      E4 k00 = *e4(sm, kr, c);  // K(u, c)
-      k00.w = (((k00.w - t1m) - t10) - t0m) - t00;
       if (v1) {  // loop 1: M1(u, c) at output (2u, 2c'+1): x neighbours C(u-1,c), C(u,c); y neighbours K(u,c), K(u,c+1)
         E4 k01 = *e4(sm, kr, c + 1);
         k01.w = (((k01.w - t10) - *f32(sm, ts1, c + 1)) - t00) - *f32(sm, ts0, c + 1);
@@ -286,7 +292,7 @@ struct Stream {
       }
       if (v2) {  // loop 2: M2(u-1, c) at output (2u-1, 2c'): x neighbours K(u-1,c), K(u,c); y neighbours C(u-1,c-1), C(u-1,c)
         E4 km = *e4(sm, krm, c);  // K(u-1, c)
-        km.w = (((km.w - *f32(sm, ts2, c - 1)) - *f32(sm, ts2, c)) - t1m) - t10;
+        km.w = th.sg1;
         E4 m;
         if (EDGE && (bg == 0 || bg == n)) {
           const E4 dummy = k00;
@@ -308,17 +314,12 @@ struct Stream {
     if (active(cx, c)) {
       const int n = sp.lev.n;
       const int bg = cx.B0 - 1 + c;
-      const int ts2 = G::TS + mod(u - 2, 3) * G::P, ts1 = G::TS + mod(u - 1, 3) * G::P;
       const int td1m = G::TD1 + mod(u - 1, 2) * G::P, td10 = G::TD1 + mod(u, 2) * G::P;
       const int td2mm = G::TD2 + mod(u - 2, 2) * G::P, td2m = G::TD2 + mod(u - 1, 2) * G::P;
       if (!EDGE || (u - 1 >= 0 && u - 1 <= n && bg >= 0 && bg <= n)) {
-        // corner K(u-1, c): generateSquare scatter of 4 squares, then loop 1 (same row), loop 2 (same column)
+        // corner K(u-1, c): generateSquare's scatter (carried sg), then loop 1 (same row), loop 2 (same column)
         E4 k = *e4(sm, G::KROW + mod(u - 1, 4) * G::P, c);
-        float sh = k.w;
-        sh -= *f32(sm, ts2, c - 1);
-        sh -= *f32(sm, ts2, c);
-        sh -= *f32(sm, ts1, c - 1);
-        sh -= *f32(sm, ts1, c);
+        float sh = th.sg1;
         sh -= *f32(sm, td1m, c - 1);
         sh -= *f32(sm, td1m, c);
         sh -= *f32(sm, td2mm, c);

@@ -308,7 +308,7 @@ def run_ours(args):
         if acc and acc[0]:
             ns = len(acc[0])
             mean = [statistics.mean(a[k] for a in acc) for k in range(ns)]
-            stage_ms = {"launch_ms": mean, "final_ms": mean[-1], "final_name": "k_stream<256> (last level, streamed interior) + k_stage<1,64,512> (frame tiles)",
+            stage_ms = {"launch_ms": mean, "final_ms": mean[-1], "final_name": "k_stream<128> (last level 2049^2 -> 4097^2, streamed: S, D, G intervals + addVolcano + coalesced store)",
                         "share_of_chain": mean[-1] / sum(mean)}
 
     # ---- e2e: the same C-ABI call with a HOST destination (pinned), D2H inside the timed region ----

@@ -26,7 +26,10 @@ constexpr int kMaxLaunches = 2 * kMaxStages;
 #endif
 constexpr int kStreamThreads = RN_STREAM_THREADS;      // threads (= cell columns incl. 3 halo / loader columns) of a streaming CTA
 constexpr int kStreamMinBlocks = RN_STREAM_MINBLOCKS;  // resident CTAs per SM the kernel is compiled for
-constexpr int kStreamLevels = 2;      // the last levels of a field are streamed (rn_stream.cuh) ...
+#ifndef RN_STREAM_LEVELS
+#define RN_STREAM_LEVELS 2
+#endif
+constexpr int kStreamLevels = RN_STREAM_LEVELS;  // the last levels of a field are streamed (rn_stream.cuh) ...
 constexpr int kStreamMinDepth = 10;   // ... when the field is at least this deep
 constexpr int kStreamCtasTarget = 148 * kStreamMinBlocks;
 constexpr int kTile = 64;  // output tile edge of every stage

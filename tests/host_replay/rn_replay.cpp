@@ -21,12 +21,14 @@ using namespace rn;
 namespace {
 
 constexpr int NT = 512;
+static int g_reverse = 0;  // visit the threads of a phase in descending order: a phase whose threads depended on
+                           // one another's writes (a race on the GPU) would give different bits
 constexpr int GUARD = 4096;  // words on each side
 
 template <int L, bool EDGE, int P>
 void run_phase(const StageParams& sp, const TileCtx& cx, float* sm)
 {
-  for (int tid = 0; tid < NT; tid++) Tile<L, kTile, NT, EDGE>::template phase<P>(sp, cx, sm, tid);
+  for (int q = 0; q < NT; q++) Tile<L, kTile, NT, EDGE>::template phase<P>(sp, cx, sm, g_reverse ? NT - 1 - q : q);
   if constexpr (P + 1 < Tile<L, kTile, NT, EDGE>::NPHASES) run_phase<L, EDGE, P + 1>(sp, cx, sm);
 }
 
@@ -74,13 +76,15 @@ void stream_march_host(const StreamParams& sp, const StreamCtx& cx, float* sm, s
 {
   constexpr int SNT = kStreamThreads;
   using S = Stream<SNT, EDGE>;
-  for (int c = 0; c < SNT; c++) S::init(sp, cx, sm, th[c], c);
+#define RN_ALL_THREADS(call) for (int q = 0; q < SNT; q++) { const int c = g_reverse ? SNT - 1 - q : q; call; }
+  RN_ALL_THREADS(S::init(sp, cx, sm, th[c], c))
   for (int u = cx.a0 - 1; u <= cx.a1e; u++) {
-    for (int c = 0; c < SNT; c++) S::interval1(sp, cx, sm, th[c], u, c);
-    for (int c = 0; c < SNT; c++) S::interval2(sp, cx, sm, th[c], u, c);
-    for (int c = 0; c < SNT; c++) S::interval3(sp, cx, sm, th[c], u, c);
+    RN_ALL_THREADS(S::interval1(sp, cx, sm, th[c], u, c))
+    RN_ALL_THREADS(S::interval2(sp, cx, sm, th[c], u, c))
+    RN_ALL_THREADS(S::interval3(sp, cx, sm, th[c], u, c))
   }
-  for (int c = 0; c < SNT; c++) S::store_rows(sp, cx, sm, th[c], cx.a1e - 1);
+  RN_ALL_THREADS(S::store_rows(sp, cx, sm, th[c], cx.a1e - 1))
+#undef RN_ALL_THREADS
 }
 
 int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
@@ -145,7 +149,8 @@ int replay_plan(int depth, int* din, int* L)
 }
 
 // Same contract as rn_terrain2d with a host destination (window may be NULL).  poison bit 0: NaN-fill
-// shared memory and scratch; bit 1: run every tile through the EDGE instantiation.  Returns 0 on
+// shared memory and scratch; bit 1: run every tile through the EDGE instantiation; bit 2: visit the
+// threads of every phase in descending order.  Returns 0 on
 // success, 100 if a tile wrote outside its shared memory.
 int replay_terrain2d(const rn_params* p, const rn_window* win, rn_element* dst, size_t pitch_elems, int poison)
 {
@@ -154,6 +159,7 @@ int replay_terrain2d(const rn_params* p, const rn_window* win, rn_element* dst, 
   rn_window w{0, 0, side, side};
   if (win) w = *win;
   if (pitch_elems == 0) pitch_elems = (size_t)w.nj;
+  g_reverse = (poison >> 2) & 1;
   Law law;
   law.amplitude = p->amplitude;
   law.sideways_scale = p->sideways_scale;

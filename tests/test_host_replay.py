@@ -60,6 +60,15 @@ def test_replay_edge_instantiation_equals_interior(replay, oracle, depth, seed):
     assert np.array_equal(a.view(np.uint32), oracle.terrain2d(p).view(np.uint32))
 
 
+@pytest.mark.parametrize("depth,seed", [(6, 3), (9, 12345), (11, 5)])
+def test_replay_thread_order_does_not_matter(replay, oracle, depth, seed):
+    """Threads of a phase visited in descending order give the same bits: no phase reads what another thread of
+    the same phase writes (which would be a race between barriers on the GPU)."""
+    p = oracle_lib.params(seed=seed, depth=depth, apply_volcano=1)
+    a = run(replay, p, poison=5)
+    assert np.array_equal(a.view(np.uint32), oracle.terrain2d(p).view(np.uint32))
+
+
 def test_replay_depth12_digest(replay, oracle):
     """BASELINE config 2 against the reference digest (tests/golden)."""
     import json

@@ -61,8 +61,8 @@ __device__ __forceinline__ void stream_march(const StreamParams& sp, const Strea
   S::store_rows(sp, cx, sm, th, cx.a1e - 1);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, kStreamMinBlocks) k_stream(const __grid_constant__ StreamParams sp)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_stream(const __grid_constant__ StreamParams sp)
 {
   extern __shared__ __align__(16) float sm[];
   const StreamCtx cx = stream_ctx(sp, (int)blockIdx.x, (int)blockIdx.y, blockIdx.z);
@@ -70,20 +70,27 @@ __global__ void __launch_bounds__(NT, kStreamMinBlocks) k_stream(const __grid_co
   else stream_march<NT, false>(sp, cx, sm);
 }
 
-cudaError_t launch_stream(const StreamParams& st, dim3 grid, cudaStream_t stream)
+template <int NT, int MINB>
+cudaError_t launch_stream_t(const StreamParams& st, dim3 grid, cudaStream_t stream)
 {
-  using G = StreamGeo<kStreamThreads>;
+  using G = StreamGeo<NT>;
   static bool configured[64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 64 && !configured[dev]) {
-    e = cudaFuncSetAttribute(k_stream<kStreamThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES);
+    e = cudaFuncSetAttribute(k_stream<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  k_stream<kStreamThreads><<<grid, kStreamThreads, G::BYTES, stream>>>(st);
+  k_stream<NT, MINB><<<grid, NT, G::BYTES, stream>>>(st);
   return cudaGetLastError();
+}
+
+cudaError_t launch_stream(const StreamParams& st, int nt, dim3 grid, cudaStream_t stream)
+{
+  if (nt == kStreamThreadsSmall) return launch_stream_t<kStreamThreadsSmall, kStreamMinBlocksSmall>(st, grid, stream);
+  return launch_stream_t<kStreamThreads, kStreamMinBlocks>(st, grid, stream);
 }
 
 template <int L>
@@ -150,7 +157,7 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
       joined = true;
     }
     if (sl.kind == 1) {
-      e = launch_stream(sl.st, grid, s);
+      e = launch_stream(sl.st, sl.nt, grid, s);
     } else {
       switch (sl.L) {
         case 1: e = launch_stage<1>(sl.sp, grid, s); break;

@@ -31,7 +31,9 @@ constexpr int kStreamMinBlocks = RN_STREAM_MINBLOCKS;  // resident CTAs per SM t
 #endif
 constexpr int kStreamLevels = RN_STREAM_LEVELS;  // the last levels of a field are streamed (rn_stream.cuh) ...
 constexpr int kStreamMinDepth = 10;   // ... when the field is at least this deep
-constexpr int kStreamCtasTarget = 148 * kStreamMinBlocks;
+constexpr int kStreamThreadsSmall = 64;   // narrower strips for small levels (more CTAs, fewer warm-up rows per sample)
+constexpr int kStreamMinBlocksSmall = 14;
+constexpr int kStreamSmallCols = 1536;    // levels with fewer cell columns than this use the small configuration
 constexpr int kTile = 64;  // output tile edge of every stage
 
 struct StagePlan {
@@ -131,6 +133,7 @@ struct StageLaunch {
   StageParams sp;         // kind 0
   StreamParams st;        // kind 1
   int L;
+  int nt;                 // kind 1: threads per CTA (kStreamThreads or kStreamThreadsSmall)
   unsigned gx, gy;        // kind 0: tiles in j, tiles in i; kind 1: strips, segments
 };
 
@@ -221,11 +224,13 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
       st.close_i = t_i1[k] == nt - 1;
       st.close_j = t_j1[k] == nt - 1;
       const int cols = st.b_hi - st.b_lo, rows = st.a_hi - st.a_lo;
-      const int strips = (cols + (kStreamThreads - 3) - 1) / (kStreamThreads - 3);
+      sl.nt = cols < kStreamSmallCols ? kStreamThreadsSmall : kStreamThreads;
+      const int ctas_target = 148 * (cols < kStreamSmallCols ? kStreamMinBlocksSmall : kStreamMinBlocks);
+      const int strips = (cols + (sl.nt - 3) - 1) / (sl.nt - 3);
       st.strip_cols = (cols + strips - 1) / strips;
       // a segment costs 2 warm-up steps, but small levels are latency-bound: filling every CTA slot wins
       // (measured: 1025 -> 2049 level 40 us with 8-row segments, 52 us with 24-row segments)
-      int nseg = kStreamCtasTarget / (strips * (nfields > 0 ? nfields : 1));
+      int nseg = ctas_target / (strips * (nfields > 0 ? nfields : 1));
       if (nseg > rows / 8) nseg = rows / 8;
       if (nseg < 1) nseg = 1;
       st.seg_rows = (rows + nseg - 1) / nseg;

@@ -71,10 +71,9 @@ int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
   return bad;
 }
 
-template <bool EDGE>
+template <int SNT, bool EDGE>
 void stream_march_host(const StreamParams& sp, const StreamCtx& cx, float* sm, std::vector<StreamThread>& th)
 {
-  constexpr int SNT = kStreamThreads;
   using S = Stream<SNT, EDGE>;
 #define RN_ALL_THREADS(call) for (int q = 0; q < SNT; q++) { const int c = g_reverse ? SNT - 1 - q : q; call; }
   RN_ALL_THREADS(S::init(sp, cx, sm, th[c], c))
@@ -87,9 +86,9 @@ void stream_march_host(const StreamParams& sp, const StreamCtx& cx, float* sm, s
 #undef RN_ALL_THREADS
 }
 
-int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
+template <int SNT>
+int run_stream_t(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
 {
-  constexpr int SNT = kStreamThreads;
   using G = StreamGeo<SNT>;
   const StreamParams& sp0 = sl.st;
   std::vector<float> buf((size_t)G::WORDS + 2 * GUARD + 4);
@@ -109,8 +108,8 @@ int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int po
         if (seeds) { sp.seeds = nullptr; sp.seed = seeds[f]; }
         const StreamCtx cx = stream_ctx(sp, (int)bx, (int)by, (unsigned)f);
         memset(th.data(), poison ? 0xff : 0, sizeof(StreamThread) * th.size());
-        if (force_edge || stream_is_edge(sp, cx)) stream_march_host<true>(sp, cx, sm, th);
-        else stream_march_host<false>(sp, cx, sm, th);
+        if (force_edge || stream_is_edge(sp, cx)) stream_march_host<SNT, true>(sp, cx, sm, th);
+        else stream_march_host<SNT, false>(sp, cx, sm, th);
         if (poison) {
           for (int i = 0; i < GUARD; i++) {
             uint32_t a, b;
@@ -121,6 +120,12 @@ int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int po
         }
       }
   return bad;
+}
+
+int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
+{
+  if (sl.nt == kStreamThreadsSmall) return run_stream_t<kStreamThreadsSmall>(sl, nfields, seeds, poison, force_edge);
+  return run_stream_t<kStreamThreads>(sl, nfields, seeds, poison, force_edge);
 }
 
 }  // namespace

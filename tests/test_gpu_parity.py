@@ -102,6 +102,53 @@ def test_windows_are_seam_exact(ctx, rnlib, oracle, algo):
         assert_bitwise(got, full[i0:i0 + ni, j0:j0 + nj], f"window {(i0, j0, ni, nj)}")
 
 
+def test_streamed_levels_windows_and_pitch(ctx, rnlib, oracle):
+    """Depth 10/11 fields take the streaming kernel (k_stream) for their last two levels: windows of any shape,
+    padded pitches and device destinations stay seam-exact (EDGE and lean strips, partial segments)."""
+    import torch
+    ctx.set_algorithm(0)
+    for depth, seed in ((10, 4711), (11, 99)):
+        S = (1 << depth) + 1
+        p = rnlib.default_params(seed=seed, depth=depth, apply_volcano=1)
+        full = oracle.terrain2d(oracle_lib.params(seed=seed, depth=depth, apply_volcano=1))
+        rng = np.random.default_rng(depth)
+        wins = [(0, 0, S, S), (100, 37, 300, 500), (S // 2, 0, S - S // 2, S), (0, 0, 129, S), (64, 64, 64, 64), (63, 63, 130, 130),
+                (S // 2, S // 2, 1, 1), (200, 200, 700, 3), (S - 1, 0, 1, S), (0, S - 1, S, 1)]
+        for _ in range(4):
+            i0, j0 = (int(x) for x in rng.integers(0, S - 1, 2))
+            wins.append((i0, j0, int(rng.integers(1, S - i0 + 1)), int(rng.integers(1, S - j0 + 1))))
+        for (i0, j0, ni, nj) in wins:
+            pitch = nj + 5
+            d = torch.full((ni, pitch, 4), -1.0, device="cuda", dtype=torch.float32)
+            ctx.terrain2d_ptr(p, d.data_ptr(), window=rnlib.Window(i0, j0, ni, nj), pitch_elems=pitch, dst_is_device=True,
+                              stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            h = d.cpu().numpy()
+            assert_bitwise(h[:, :nj], full[i0:i0 + ni, j0:j0 + nj], f"depth {depth} window {(i0, j0, ni, nj)}")
+            assert (h[:, nj:] == -1.0).all()
+
+
+def test_streamed_batch_and_slabs(ctx, rnlib, oracle):
+    """BASELINE config 5 shape (depth-10 tiles, distinct seeds) through rn_terrain2d_batch, and a depth-12 field
+    generated as 3 row slabs == the oracle's whole field (what the slab-sharded multi-GPU workload relies on)."""
+    ctx.set_algorithm(0)
+    seeds = [12345, 12346, 7, 0xFFFFFFFF]
+    p = rnlib.default_params(depth=10, apply_volcano=1)
+    got = ctx.terrain2d_batch_host(p, seeds)
+    for t, s in enumerate(seeds):
+        want = oracle.terrain2d(oracle_lib.params(seed=s, depth=10, apply_volcano=1))
+        assert_bitwise(got[t], want, f"batch tile {t} seed {s}")
+    from rednoise_b200 import sharding
+    depth, world = 12, 3
+    S = (1 << depth) + 1
+    p12 = rnlib.default_params(seed=2024, depth=depth, apply_volcano=1)
+    want = oracle.terrain2d(oracle_lib.params(seed=2024, depth=depth, apply_volcano=1))
+    for r in range(world):
+        i0, j0, ni, nj = sharding.slab_window(S, r, world)
+        slab = ctx.terrain2d_host(p12, window=rnlib.Window(i0, j0, ni, nj))
+        assert_bitwise(slab, want[i0:i0 + ni], f"slab {r} of {world}")
+
+
 def test_bad_arguments(ctx, rnlib):
     L = rnlib.lib()
     buf = np.empty((9 * 9, 4), np.float32)

@@ -22,7 +22,7 @@
 //   interval 3   G(u): final shade of corner K(u-1,c) and centre C(u-1,c) (ordered gather)
 //                + the prefetched lattice row goes to shared memory
 // Rolling rows: lattice x4, centres x2, M1 x2, M2, final K, final C (float4) and the loss planes
-// TS x3, TD1 x2, TD2 x2 (float).  See rn_tile.cuh for the vocabulary and the shade-order argument.
+// TS x4, TD1 x2, TD2 x2 (float).  See rn_tile.cuh for the vocabulary and the shade-order argument.
 //
 // Compiles as plain C++ for tests/host_replay (per-thread registers live in StreamThread).
 #pragma once
@@ -116,8 +116,8 @@ struct StreamGeo {
   static constexpr int OUTC = OUTK + P;          // final centres
   static constexpr int E4ROWS = OUTC + P;
   // float rows (word offsets)
-  static constexpr int TS = 4 * E4ROWS;          // 3 rows
-  static constexpr int TD1 = TS + 3 * P;         // 2 rows
+  static constexpr int TS = 4 * E4ROWS;          // 4 rows (3 live; a power of two keeps the ring index a mask)
+  static constexpr int TD1 = TS + 4 * P;         // 2 rows
   static constexpr int TD2 = TD1 + 2 * P;        // 2 rows
   static constexpr int WORDS = ((TD2 + 2 * P + 3) / 4) * 4;
   static constexpr size_t BYTES = (size_t)WORDS * 4;
@@ -128,9 +128,10 @@ struct Stream {
   using G = StreamGeo<NT>;
   static RN_HD E4* e4(float* sm, int row_off, int c) { return reinterpret_cast<E4*>(sm) + row_off + (c + 1); }
   static RN_HD float* f32(float* sm, int row_off, int c) { return sm + row_off + (c + 1); }
-  static RN_HD int mod(int u, int m) { return m == 4 ? (u & 3) : m == 2 ? (u & 1) : (int)((unsigned)(u + 3) % 3u); }  // u >= -3
+  static RN_HD int mod(int u, int m) { return u & (m - 1); }  // ring sizes are powers of two
 
-  static RN_HD bool active(const StreamCtx& cx, int c) { return c <= cx.CW + 1; }   // threads with a cell
+  // threads with a cell; the lean instantiation lets the few surplus lanes compute on garbage (all in-bounds, never stored)
+  static RN_HD bool active(const StreamCtx& cx, int c) { return !EDGE || c <= cx.CW + 1; }
   static RN_HD bool loader(const StreamCtx& cx, int c) { return c <= cx.CW + 2; }   // threads with a lattice column
   static RN_HD int steps_last(const StreamCtx& cx) { return cx.a1e; }  // steps u = a0-1 .. a1e
 
@@ -188,6 +189,7 @@ struct Stream {
     // output rows 2a (corners K(a,.) / mids M1(a,.)) and 2a+1 (mids M2(a,.) / centres C(a,.))
     const int Wout = 1 << sp.dout;
     const float inv_w = 1.0f / (float)Wout;
+    const float gain_w = sp.volcano_gain * (float)Wout;
     const E4* smE = reinterpret_cast<const E4*>(sm);
     const bool odd = th.out_j & 1;
     const int cc0 = (th.out_j >> 1) + 2, cc1 = cc0 + NT / 2;  // slot of the owning cell inside a class row (its c + 1)
@@ -205,12 +207,12 @@ struct Stream {
         const int src = r == 0 ? (odd ? G::M1ROW + (a & 1) * G::P : G::OUTK) : (odd ? G::OUTC : G::M2ROW);
         if (ok0) {
           E4 e = smE[src + cc0];
-          if (VOLCANO) e.y = e.y + volcano_height_r2<FAR>(fx2 + th.out_fy2[0], inv_w, sp.volcano_gain);
+          if (VOLCANO) e.y = e.y + volcano_height_r2<FAR>(fx2 + th.out_fy2[0], inv_w, sp.volcano_gain, gain_w);
           cx.gout[rowoff + wj0] = e;
         }
         if (ok1) {
           E4 e = smE[src + cc1];
-          if (VOLCANO) e.y = e.y + volcano_height_r2<FAR>(fx2 + th.out_fy2[1], inv_w, sp.volcano_gain);
+          if (VOLCANO) e.y = e.y + volcano_height_r2<FAR>(fx2 + th.out_fy2[1], inv_w, sp.volcano_gain, gain_w);
           cx.gout[rowoff + wj1] = e;
         }
       }
@@ -242,7 +244,7 @@ struct Stream {
         *e4(sm, G::CROW + mod(u, 2) * G::P, c) = e4_of(dp.pos, sh + shade_gain(sp.law, dp.offset));
         loss = shade_loss(sp.law, dp.offset);
       }
-      *f32(sm, G::TS + mod(u, 3) * G::P, c) = loss;
+      *f32(sm, G::TS + mod(u, 4) * G::P, c) = loss;
     }
     // the rows G(u-1) finished: cell row u-2
     if (u - 2 >= cx.a0 && u - 2 < cx.a1e) store_rows(sp, cx, sm, th, u - 2);
@@ -267,7 +269,7 @@ struct Stream {
     float loss1 = 0.0f, loss2 = 0.0f;
     // corner shades as generateSquare left them (Terrain.cpp:252-255): minus the scatter of the 4 surrounding
     // centres.  sg(u,c) is computed here once and carried to the next step (as sg(u-1,c)) and to interval 3.
-    const int ts1 = G::TS + mod(u - 1, 3) * G::P, ts0 = G::TS + mod(u, 3) * G::P;
+    const int ts1 = G::TS + mod(u - 1, 4) * G::P, ts0 = G::TS + mod(u, 4) * G::P;
     const int kr = G::KROW + mod(u, 4) * G::P;
     const float t10 = *f32(sm, ts1, c), t00 = *f32(sm, ts0, c);
     E4 k00 = *e4(sm, kr, c);  // K(u, c)

@@ -236,17 +236,21 @@ RN_HD uint32_t lcg_skip(uint32_t s, uint32_t k)
 // r2 is either 0 (the centre sample) or >= 1, so sqrt / reciprocal see normal numbers.
 // FAR: the caller guarantees d >= minRad (the tile lies outside the crater), so the crater
 // branch (:133-136) is not compiled in.
+// gain_w = gain * W (exact: W is a power of two).
 template <bool FAR>
-RN_HD float volcano_height_r2(float r2, float inv_w, float gain)
+RN_HD float volcano_height_r2(float r2, float inv_w, float gain, float gain_w)
 {
+  if (FAR) {
+    // height = 1/(sqrt(r2)/W) = W * (1/sqrt(r2)) exactly, and scaling the gain by W instead is exact too:
+    // one multiplication less, same bits.
+    return rcp_rn_normal(sqrt_rn_normal(r2)) * gain_w;
+  }
   float d = sqrt_rn_normal(r2) * inv_w;
   float height = rcp_rn_normal(d);
-  if (!FAR) {
-    const float minRad = 0.02f;
-    if (!(d >= minRad)) {  // also taken by the centre sample, where the approximations above see 0
-      if (r2 == 0.0f) d = 0.0f;
-      height = 60000.f * (d * d - minRad * minRad) + (1.0f / minRad);
-    }
+  const float minRad = 0.02f;
+  if (!(d >= minRad)) {  // also taken by the centre sample, where the approximations above see 0
+    if (r2 == 0.0f) d = 0.0f;
+    height = 60000.f * (d * d - minRad * minRad) + (1.0f / minRad);
   }
   return height * gain;
 }
@@ -553,7 +557,7 @@ struct Tile {
     E4 e = reinterpret_cast<const E4*>(sm)[out_slot(r, c)];
     if (sp.volcano) {
       const float fx = (float)(gi - Wout / 2), fy = (float)(gj - Wout / 2);
-      e.y = e.y + volcano_height_r2<false>(fx * fx + fy * fy, inv_w, sp.volcano_gain);
+      e.y = e.y + volcano_height_r2<false>(fx * fx + fy * fy, inv_w, sp.volcano_gain, 0.0f);
     }
     cx.gout[(size_t)wi * sp.gout_pitch + (size_t)wj] = e;
   }
@@ -596,6 +600,7 @@ struct Tile {
       }
       const float fy = (float)(cx.J0 + c - Wout / 2);
       const float fy2 = fy * fy;
+      const float gain_w = sp.volcano_gain * (float)Wout;
       int xi = cx.I0 + r0 - Wout / 2;
       // crater test for the whole tile: index distance of its nearest sample from the volcano
       const int di = imax_(imax_(cx.I0 - Wout / 2, Wout / 2 - (cx.I0 + T - 1)), 0);
@@ -606,7 +611,7 @@ struct Tile {
         for (int kk = 0; kk < T / RS; kk++) {
           E4 e = *src;
           const float fx = (float)xi;
-          e.y = e.y + volcano_height_r2<true>(fx * fx + fy2, inv_w, sp.volcano_gain);
+          e.y = e.y + volcano_height_r2<true>(fx * fx + fy2, inv_w, sp.volcano_gain, gain_w);
           *dst = e;
           src += sstep;
           dst += dstep;
@@ -616,7 +621,7 @@ struct Tile {
         for (int kk = 0; kk < T / RS; kk++) {
           E4 e = *src;
           const float fx = (float)xi;
-          e.y = e.y + volcano_height_r2<false>(fx * fx + fy2, inv_w, sp.volcano_gain);
+          e.y = e.y + volcano_height_r2<false>(fx * fx + fy2, inv_w, sp.volcano_gain, gain_w);
           *dst = e;
           src += sstep;
           dst += dstep;

@@ -56,54 +56,72 @@ def ncu_traffic(args):
 
 # --------------------------------------------------------------------------- clocks ---
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock + throttle reasons sampled through NVML every ~2 ms by a background thread while the GPU works
+    (nvidia-smi -lms cannot resolve a timed region of a few milliseconds); falls back to nvidia-smi."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4),
+               ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.proc = None
-        self.path = None
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = False
+        self._thr = None
+        self._nvml = None
 
     def start(self):
+        import threading
         try:
-            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
-            self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._nvml = (pynvml, h)
         except Exception:
-            self.proc = None
+            self._nvml = None
+            return
+
+        def loop():
+            pynvml, h = self._nvml
+            while not self._stop:
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    for name, bit in self.REASONS:
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.0002)
+
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": "nvml"}
+        if self._thr is not None:
+            self._stop = True
+            self._thr.join(timeout=2)
+        if self.samples:
+            out.update(sm_mhz=statistics.median(self.samples), reasons=sorted(self.reasons), samples=len(self.samples))
             return out
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        try:
-            for line in open(self.path):
-                c = [x.strip() for x in line.split(",")]
-                if len(c) < 9:
-                    continue
-                try:
-                    sm.append(float(c[1]))
-                    mx.append(float(c[2]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
+        try:  # fallback: one nvidia-smi query
+            q = "clocks.sm,clocks.max.sm"
+            r = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            out.update(sm_mhz=float(r[0]), sm_max_mhz=float(r[1]), samples=1, source="nvidia-smi")
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
         return out
 
 
@@ -292,6 +310,7 @@ def run_ours(args):
         step()
         ev[k + 1].record()
     barrier()
+    clocks = sampler.stop() if rank == 0 else None  # sampled during the timed region only
     total_ms = ev[0].elapsed_time(ev[-1])
     per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     launches = ctx.launches - launches0
@@ -339,8 +358,6 @@ def run_ours(args):
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    clocks = sampler.stop() if rank == 0 else None
-
     t = torch.tensor([total_ms, e2e_s, float(my_samples), float(e2e_samples)], device="cuda", dtype=torch.float64)
     if world > 1:
         tmax = t.clone()

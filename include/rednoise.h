@@ -148,6 +148,32 @@ int rn_terrain2d_batch(rn_context* ctx, const rn_params* p, const uint32_t* seed
 int rn_lcg_draws_device(rn_context* ctx, uint32_t seed, uint64_t first, uint64_t n, uint16_t* dst,
                         int dst_is_device, void* stream);
 
+/* ---- next stage of the reference constructor: field -> Cell quadtree attributes -------------
+ * Replaces the arithmetic of Terrain::generateRecursive (renderEngine/source/Terrain.cpp:260-356,
+ * called at :96) + root->radius *= 4 (:97): for every node of the quadtree over the field (level l
+ * has 4^l nodes, l = 0 .. depth-1; node (l, bx, by) covers lattice [bx*w, (bx+1)*w] x [by*w, (by+1)*w],
+ * w = W >> l) the position relative to its parent, colour, quantised normal and radius.
+ * Nodes are stored level by level; inside a level in the reference's visiting order (depth-first
+ * with children ordered x-then-y, :351-354), i.e. Morton order with the x bit as the low bit of
+ * every digit.  The scene-graph pointers (Cell::parent/children, Cell.h:12-19) are implied by
+ * that order: child k of node e at level l is node 4e+k of level l+1. */
+typedef struct rn_cell {
+  float position[3]; /* Cell::position, w.r.t. the parent's centre (Terrain.cpp:325-328) */
+  float colour[3];   /* Cell::colour (Terrain.cpp:290-324,337-338) */
+  float radius;      /* Cell::radius (Terrain.cpp:342; root x4, :97) */
+  int8_t normal[3];  /* Cell::normal, quantised (Terrain.cpp:330-332) */
+  uint8_t level;
+} rn_cell;
+
+/* nodes of all levels: (4^depth - 1) / 3; first node of `level` */
+uint64_t rn_terrain2d_cell_count(int depth);
+uint64_t rn_terrain2d_cell_level_offset(int level);
+/* field: the finished (W+1)x(W+1) field of `p` (row pitch field_pitch elements, 0 = W+1), device or host memory,
+ * or NULL to synthesize it first (rn_terrain2d with the whole window).  cells: rn_terrain2d_cell_count(p->depth)
+ * entries, device or host memory. */
+int rn_terrain2d_cells(rn_context* ctx, const rn_params* p, const rn_element* field, size_t field_pitch, int field_is_device,
+                       rn_cell* cells, int cells_is_device, void* stream);
+
 /* Device self-test of the arithmetic shortcuts: the normal-range sqrt / reciprocal sequences
  * used by the fused kernels are compared with the IEEE-rounded intrinsics over every binary32
  * value in 2^-100 .. 2^100.  mismatches[0..2] = sqrt, reciprocal, 1/sqrt (all must be 0). */

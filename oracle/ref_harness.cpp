@@ -20,6 +20,7 @@
 #include "Terrain.h"
 #undef private
 #include "Cell.h"
+#include "OrientableCell.h"
 #include <stdint.h>
 #include <chrono>
 
@@ -158,6 +159,95 @@ long long ref_terrain_passes(int depth, float amplitude, float size, unsigned in
 }
 
 int ref_sizeof_element(void) { return (int)sizeof(Terrain::TerrainElement); }
+
+// The reference's own Terrain::generateRecursive (Terrain.cpp:260-356) on a field produced by its own
+// passes + addVolcano, with the cell pool set up as the constructor does (Terrain.cpp:21-42; the pool
+// element mirrors the file-local `TerrainSize` of Terrain.cpp:8-13).  Emits, level by level and in the
+// constructor's visiting order, 8 floats per node: position xyz, colour rgb, radius, and the three
+// quantised normal bytes + level packed into the last word -- the layout of rn_cell (include/rednoise.h).
+struct RnRefPoolElem { Cell cell; Cell* children[4]; };
+long long ref_terrain_cells(int depth, float amplitude, float size, unsigned int seed, float* field_out, void* cells_out)
+{
+  if (depth < 3 || depth > 12 || !cells_out) return -1;
+  Terrain* t = (Terrain*)calloc(1, sizeof(Terrain)); // ctor deliberately not run
+  t->depth = depth;
+  t->amplitude = amplitude;
+  t->levels = new int[depth];
+  t->numEntries = new int[depth];
+  int count = 0, width = 0;
+  for (int i = 0; i < depth; i++)
+  {
+    t->numEntries[i] = 0;
+    width = 1 << i;
+    t->levels[i] = count;
+    count += width * width;
+  }
+  RnRefPoolElem* contiguous = (RnRefPoolElem*)malloc(sizeof(RnRefPoolElem) * (size_t)count);
+  t->cells = new Cell*[count];
+  for (int i = 0; i < count; i++)
+  {
+    if (i >= count - (width * width)) t->cells[i] = new (&(contiguous[i].cell)) Cell(NULL, 0);
+    else t->cells[i] = new (&(contiguous[i].cell)) Cell(NULL, 4, (char*)&(contiguous[i].children));
+  }
+  const int maxWidth = 1 << depth;
+  t->maxWidth = maxWidth;
+  t->baseArray = new Terrain::TerrainElement*[maxWidth + 1];
+  for (int i = 0; i < maxWidth + 1; i++)
+  {
+    float x = 2.0f * (float)(i - maxWidth / 2) / (float)maxWidth;
+    t->baseArray[i] = new Terrain::TerrainElement[maxWidth + 1];
+    for (int j = 0; j < maxWidth + 1; j++)
+    {
+      float z = 2.0f * (float)(j - maxWidth / 2) / (float)maxWidth;
+      t->baseArray[i][j].pos.set(x, z * 0.04f, z);
+      t->baseArray[i][j].shade = 1.0f;
+    }
+  }
+  g_seed_forced = 0;
+  rn_msvc_srand(seed);
+  int step = maxWidth / 4;
+  do
+  {
+    for (int x = 0; x < maxWidth; x += step) for (int y = 0; y < maxWidth; y += step) t->averageSquare(x, y, x + step, y + step);
+    for (int x = 0; x < maxWidth; x += step) for (int y = 0; y < maxWidth; y += step) t->generateSquare(x, y, x + step, y + step);
+    for (int x = -step / 2; x < maxWidth; x += step) for (int y = 0; y < maxWidth; y += step) t->averageDiamond(x, y, x + step, y + step);
+    for (int x = 0; x < maxWidth; x += step) for (int y = -step / 2; y < maxWidth; y += step) t->averageDiamond(x, y, x + step, y + step);
+    for (int x = -step / 2; x < maxWidth; x += step) for (int y = 0; y < maxWidth; y += step) t->generateDiamond(x, y, x + step, y + step);
+    for (int x = 0; x < maxWidth; x += step) for (int y = -step / 2; y < maxWidth; y += step) t->generateDiamond(x, y, x + step, y + step);
+    step /= 2;
+  } while (step > 1);
+  t->addVolcano(size);
+  if (field_out)
+    for (int i = 0; i < maxWidth + 1; i++) memcpy(field_out + (size_t)i * (maxWidth + 1) * 4, t->baseArray[i], (size_t)(maxWidth + 1) * 16);
+  t->root = (OrientableCell*)t->generateRecursive(NULL, Position(0, 0, 0), 0, 0, maxWidth, maxWidth, 0, size, size);
+  t->root->radius *= 4.0f; // Terrain.cpp:97
+  struct Out { float pos[3], col[3], radius; signed char n[3]; unsigned char level; };
+  Out* out = (Out*)cells_out;
+  long long k = 0;
+  for (int l = 0; l < depth; l++)
+  {
+    const int n = 1 << (2 * l);
+    if (t->numEntries[l] != n) return -2;
+    for (int e = 0; e < n; e++)
+    {
+      const Cell* c = (l == 0) ? (const Cell*)t->root : t->cells[t->levels[l] + e];
+      Out& o = out[k++];
+      o.pos[0] = c->position.x; o.pos[1] = c->position.y; o.pos[2] = c->position.z;
+      o.col[0] = c->colour.x; o.col[1] = c->colour.y; o.col[2] = c->colour.z;
+      o.radius = c->radius;
+      o.n[0] = c->normal[0]; o.n[1] = c->normal[1]; o.n[2] = c->normal[2];
+      o.level = (unsigned char)l;
+    }
+  }
+  for (int i = 0; i < maxWidth + 1; i++) delete[] t->baseArray[i];
+  delete[] t->baseArray;
+  delete[] t->cells;
+  delete[] t->levels;
+  delete[] t->numEntries;
+  free(contiguous); // the pool's Cell destructors are deliberately not run (children live inside the pool)
+  free(t);
+  return k;
+}
 
 } // extern "C"
 

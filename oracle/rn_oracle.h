@@ -44,6 +44,10 @@ int rno_terrain2d(const rn_params* p, rn_element* grid, float* volcano_pos);
 /* ntiles independent fields, one per seed, on up to `threads` host threads (OpenMP). */
 int rno_terrain2d_batch(const rn_params* p, const uint32_t* seeds, int ntiles, rn_element* grids, int threads);
 
+/* Terrain::generateRecursive (Terrain.cpp:260-356) + root radius (:97): Cell-quadtree attributes from the finished field. */
+uint64_t rno_cell_count(int depth);
+int rno_terrain2d_cells(const rn_params* p, const rn_element* field, rn_cell* cells);
+
 uint64_t rno_fnv64(const void* data, size_t nbytes);
 
 #ifdef __cplusplus

@@ -22,6 +22,7 @@ SYMBOLS = [
     "rn_version", "rn_last_error_string", "rn_status_string", "rn_params_default", "rn_terrain2d_side",
     "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
     "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_set_pipelining", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device", "rn_selftest_math",
+    "rn_terrain2d_cell_count", "rn_terrain2d_cell_level_offset", "rn_terrain2d_cells",
 ]
 
 
@@ -34,6 +35,10 @@ class Params(C.Structure):
         ("radiosity_strength", C.c_float), ("feature_scale", C.c_float), ("amplitude_variation", C.c_float),
         ("bulgy_rocks", C.c_int32), ("apply_volcano", C.c_int32),
     ]
+
+
+CELL_DTYPE = np.dtype([("position", np.float32, 3), ("colour", np.float32, 3), ("radius", np.float32), ("normal", np.int8, 3),
+                       ("level", np.uint8)])  # rn_cell, 32 bytes
 
 
 class Window(C.Structure):
@@ -84,6 +89,11 @@ def lib() -> C.CDLL:
     L.rn_terrain2d_batch.argtypes = [vp, C.POINTER(Params), C.POINTER(u32), i32, vp, sz, i32, vp]
     L.rn_lcg_draws_device.argtypes = [vp, u32, u64, u64, vp, i32, vp]
     L.rn_selftest_math.argtypes = [vp, C.POINTER(u64)]
+    L.rn_terrain2d_cell_count.restype = u64
+    L.rn_terrain2d_cell_count.argtypes = [i32]
+    L.rn_terrain2d_cell_level_offset.restype = u64
+    L.rn_terrain2d_cell_level_offset.argtypes = [i32]
+    L.rn_terrain2d_cells.argtypes = [vp, C.POINTER(Params), vp, sz, i32, vp, i32, vp]
     _lib = L
     return L
 
@@ -181,6 +191,22 @@ class Context:
         s = side(p.depth)
         out = np.empty((len(seeds), s, s, 4), np.float32)
         self.terrain2d_batch_ptr(p, seeds, out.ctypes.data, dst_is_device=False)
+        return out
+
+    def cells_ptr(self, p: Params, cells_ptr: int, *, field_ptr: int = 0, field_pitch: int = 0, field_is_device: bool = True,
+                  cells_is_device: bool = True, stream: int = 0):
+        _check(lib().rn_terrain2d_cells(self._h, C.byref(p), C.c_void_p(field_ptr) if field_ptr else None, field_pitch,
+                                        1 if field_is_device else 0, C.c_void_p(cells_ptr), 1 if cells_is_device else 0,
+                                        C.c_void_p(stream) if stream else None))
+
+    def cells_host(self, p: Params, field: np.ndarray | None = None) -> np.ndarray:
+        """Cell-quadtree attributes (structured array, CELL_DTYPE) of `field` (host array) or of the field of p."""
+        n = int(lib().rn_terrain2d_cell_count(p.depth))
+        out = np.zeros(n, CELL_DTYPE)
+        if field is not None:
+            field = np.ascontiguousarray(field, np.float32)
+        self.cells_ptr(p, out.ctypes.data, field_ptr=field.ctypes.data if field is not None else 0, field_is_device=False,
+                       cells_is_device=False)
         return out
 
     def selftest_math(self):

@@ -22,6 +22,7 @@ struct rn_context {
   // grow-only scratch
   void* field = nullptr;   size_t field_bytes = 0;    // full-field staging when dst is a window / host memory
   void* plane = nullptr;   size_t plane_bytes = 0;    // algorithm 1: offset plane; algorithm 2: coarse grids
+  void* cells = nullptr;   size_t cells_bytes = 0;    // staging for rn_terrain2d_cells with a host destination
   void* small = nullptr;   size_t small_bytes = 0;    // staging for rn_lcg_draws_device with a host dst; batch seeds
   // algorithm 2 pipelining: the coarse stages run on a high-priority side stream into one of two
   // scratch slots, so that they overlap the output stage of the previous call
@@ -295,6 +296,7 @@ int rn_destroy(rn_context* ctx)
   for (int k = 0; k < 17; k++)
     if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
   cudaFree(ctx->field);
+  cudaFree(ctx->cells);
   cudaFree(ctx->plane);
   cudaFree(ctx->small);
   delete ctx;
@@ -488,6 +490,63 @@ int rn_terrain2d_batch(rn_context* ctx, const rn_params* p, const uint32_t* seed
     }
   }
   if (!(stream_v && dst_is_device)) RN_CUDA(cudaStreamSynchronize(stream));
+  return RN_OK;
+}
+
+uint64_t rn_terrain2d_cell_count(int depth)
+{
+  if (depth < 1 || depth > 31) return 0;
+  return ((1ull << (2 * depth)) - 1) / 3;
+}
+
+uint64_t rn_terrain2d_cell_level_offset(int level)
+{
+  if (level < 0 || level > 31) return 0;
+  return ((1ull << (2 * level)) - 1) / 3;
+}
+
+int rn_terrain2d_cells(rn_context* ctx, const rn_params* p, const rn_element* field, size_t field_pitch, int field_is_device,
+                       rn_cell* cells, int cells_is_device, void* stream_v)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  int st = check_params(p);
+  if (st != RN_OK) return st;
+  if (!cells) return fail(RN_ERR_BAD_PARAM, "cells is NULL");
+  const size_t side = ((size_t)1 << p->depth) + 1;
+  if (field_pitch == 0) field_pitch = side;
+  if (field_pitch < side) return fail(RN_ERR_BAD_PARAM, "field_pitch < side");
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+  const Elem* g = nullptr;
+  size_t gpitch = field_pitch;
+  if (field && field_is_device && reinterpret_cast<uintptr_t>(field) % 16 == 0) {
+    g = reinterpret_cast<const Elem*>(field);
+  } else {
+    st = ensure(&ctx->field, &ctx->field_bytes, sizeof(Elem) * side * side);
+    if (st != RN_OK) return st;
+    gpitch = side;
+    if (field) {
+      RN_CUDA(cudaMemcpy2DAsync(ctx->field, side * sizeof(Elem), field, field_pitch * sizeof(Elem), side * sizeof(Elem), side,
+                                field_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    } else {  // synthesize the field first (Terrain.cpp:44-88), whole window, into the staging buffer
+      st = rn_terrain2d(ctx, p, nullptr, reinterpret_cast<rn_element*>(ctx->field), side, 1, stream, nullptr);
+      if (st != RN_OK) return st;
+    }
+    g = reinterpret_cast<const Elem*>(ctx->field);
+  }
+  const uint64_t n = rn_terrain2d_cell_count(p->depth);
+  void* out = cells;
+  const bool direct = cells_is_device && reinterpret_cast<uintptr_t>(cells) % 16 == 0;
+  if (!direct) {
+    st = ensure(&ctx->cells, &ctx->cells_bytes, n * sizeof(rn_cell));
+    if (st != RN_OK) return st;
+    out = ctx->cells;
+  }
+  RN_CUDA(cells_generate(out, g, gpitch, p->depth, p->feature_scale, p->size, p->amplitude, stream, &ctx->launches));
+  if (!direct)
+    RN_CUDA(cudaMemcpyAsync(cells, out, n * sizeof(rn_cell), cells_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+  if (!(stream_v && cells_is_device)) RN_CUDA(cudaStreamSynchronize(stream));
   return RN_OK;
 }
 

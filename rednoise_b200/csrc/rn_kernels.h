@@ -18,6 +18,10 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
                            void* scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events = nullptr, int* nstages = nullptr,
                            cudaStream_t coarse_stream = nullptr, cudaEvent_t coarse_done = nullptr, cudaEvent_t frame_done = nullptr);
 
+// Cell-quadtree attributes of a finished field (rn_cells.cu; Terrain.cpp:260-356): `cells` = rn_cell[(4^depth-1)/3].
+cudaError_t cells_generate(void* cells, const Elem* field, size_t pitch, int depth, float feature_scale, float size, float amplitude,
+                           cudaStream_t stream, uint64_t* launches);
+
 // Epilogues / utilities (rn_util.cu).
 // addVolcano (Terrain.cpp:121-141) over the window [i0,i0+ni) x [j0,j0+nj) of a depth-`depth` field
 // stored at g with row pitch `pitch` (g points at window element (i0,j0)).

@@ -52,6 +52,12 @@ def main():
             for i in (0, 1, W // 2, W - 1, W):
                 out["rows"].append({"depth": depth, "seed": seed, "row": i, "volcano": 1,
                                     "bits": post[i].view(np.uint32).reshape(-1).tolist()})
+    # Cell quadtree (Terrain::generateRecursive run by the reference itself): digest of the rn_cell array
+    out["cells"] = []
+    for depth, seed in [(3, 12345), (5, 7), (8, 12345), (10, 12345), (11, 2024)]:
+        _, cells = ref.cells(depth, seed)
+        out["cells"].append({"depth": depth, "seed": seed, "count": int(len(cells)), "fnv64": fnv64(cells.view(np.uint8)),
+                             "first": cells[:5].view(np.uint32).reshape(-1).tolist()})
     for seed in (1, 12345, 0, 0xFFFFFFFF):
         out["lcg_kat"][str(seed)] = ref.lcg_draws(seed, 16).tolist()
     path = os.path.join(HERE, "terrain2d_golden.json")

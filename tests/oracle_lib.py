@@ -30,6 +30,20 @@ class Params(C.Structure):
     ]
 
 
+class Cell(C.Structure):
+    """rn_cell (include/rednoise.h): 32 bytes."""
+    _fields_ = [("position", C.c_float * 3), ("colour", C.c_float * 3), ("radius", C.c_float), ("normal", C.c_int8 * 3),
+                ("level", C.c_uint8)]
+
+
+CELL_DTYPE = np.dtype([("position", np.float32, 3), ("colour", np.float32, 3), ("radius", np.float32), ("normal", np.int8, 3),
+                       ("level", np.uint8)])
+
+
+def cell_count(depth: int) -> int:
+    return (4 ** depth - 1) // 3
+
+
 def params(seed=12345, depth=8, apply_volcano=1, **kw) -> Params:
     d = dict(seed=seed, depth=depth, amplitude=0.2, size=500.0, persistence=0.5, lacunarity=2, sideways_scale=0.5,
              radiosity_strength=0.5, feature_scale=80.0, amplitude_variation=0.5, bulgy_rocks=1,
@@ -76,6 +90,9 @@ class Oracle:
         L.rno_add_volcano.argtypes = [vp, vp, vp]
         L.rno_terrain2d.argtypes = [vp, vp, vp]
         L.rno_terrain2d_batch.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+        L.rno_cell_count.restype = C.c_uint64
+        L.rno_cell_count.argtypes = [C.c_int]
+        L.rno_terrain2d_cells.argtypes = [vp, vp, vp]
         L.rno_fnv64.restype = C.c_uint64
         L.rno_fnv64.argtypes = [vp, C.c_size_t]
 
@@ -105,6 +122,15 @@ class Oracle:
             raise RuntimeError(f"oracle status {st}")
         return out
 
+    def cells(self, p: Params, field: np.ndarray) -> np.ndarray:
+        """Terrain::generateRecursive restated: the Cell quadtree of the finished field (structured array, CELL_DTYPE)."""
+        field = np.ascontiguousarray(field, np.float32)
+        out = np.zeros(cell_count(p.depth), CELL_DTYPE)
+        st = self.L.rno_terrain2d_cells(C.byref(p), field.ctypes.data, out.ctypes.data)
+        if st != 0:
+            raise RuntimeError(f"oracle status {st}")
+        return out
+
     def fnv64(self, a: np.ndarray) -> str:
         a = np.ascontiguousarray(a)
         return "%016x" % self.L.rno_fnv64(a.ctypes.data, a.nbytes)
@@ -117,6 +143,8 @@ class Ref:
         L.ref_terrain_passes.argtypes = [C.c_int, C.c_float, C.c_float, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_lcg_draws.restype = None
         L.ref_lcg_draws.argtypes = [C.c_uint, C.c_int, C.c_void_p]
+        L.ref_terrain_cells.restype = C.c_longlong
+        L.ref_terrain_cells.argtypes = [C.c_int, C.c_float, C.c_float, C.c_uint, C.c_void_p, C.c_void_p]
         L.ref_random_from_state.restype = C.c_float
         L.ref_random_from_state.argtypes = [C.c_uint]
 
@@ -128,6 +156,16 @@ class Ref:
         if calls < 0:
             raise RuntimeError("reference harness rejected the arguments")
         return (out, calls, tuple(times)) if want_times else (out, calls)
+
+    def cells(self, depth, seed=12345, amplitude=0.2, size=500.0):
+        """The reference's own generateRecursive on its own field: (field, cells)."""
+        s = (1 << depth) + 1
+        field = np.empty((s, s, 4), np.float32)
+        out = np.zeros(cell_count(depth), CELL_DTYPE)
+        n = self.L.ref_terrain_cells(depth, amplitude, size, seed, field.ctypes.data, out.ctypes.data)
+        if n != cell_count(depth):
+            raise RuntimeError(f"reference harness returned {n}")
+        return field, out
 
     def lcg_draws(self, seed, n):
         out = np.empty(n, np.int32)

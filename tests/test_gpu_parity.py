@@ -149,6 +149,39 @@ def test_streamed_batch_and_slabs(ctx, rnlib, oracle):
         assert_bitwise(slab, want[i0:i0 + ni], f"slab {r} of {world}")
 
 
+@pytest.mark.parametrize("depth,seed", [(3, 12345), (4, 9), (5, 7), (8, 12345), (10, 777), (11, 2024)])
+def test_cell_quadtree_equals_oracle_bitwise(ctx, rnlib, oracle, depth, seed):
+    """rn_terrain2d_cells (Terrain::generateRecursive on the GPU) vs the oracle: every byte of every rn_cell."""
+    p = rnlib.default_params(seed=seed, depth=depth, apply_volcano=1)
+    po = oracle_lib.params(seed=seed, depth=depth, apply_volcano=1)
+    field = oracle.terrain2d(po)
+    want = oracle.cells(po, field)
+    got = ctx.cells_host(p, field)               # host field in, host cells out
+    assert got.tobytes() == want.tobytes()
+    got2 = ctx.cells_host(p)                     # field synthesized on the device first
+    assert got2.tobytes() == want.tobytes()
+
+
+def test_cell_quadtree_depth12_digest_and_device_path(ctx, rnlib, oracle):
+    import torch
+    gold = {e["depth"]: e for e in GOLD.get("cells", [])}
+    p = rnlib.default_params(seed=12345, depth=12, apply_volcano=1)
+    S = rnlib.side(12)
+    n = int(rnlib.lib().rn_terrain2d_cell_count(12))
+    fld = torch.empty((S, S, 4), device="cuda", dtype=torch.float32)
+    cells = torch.empty((n, 8), device="cuda", dtype=torch.float32)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx.terrain2d_ptr(p, fld.data_ptr(), dst_is_device=True, stream=stream)
+    ctx.cells_ptr(p, cells.data_ptr(), field_ptr=fld.data_ptr(), field_is_device=True, cells_is_device=True, stream=stream)
+    torch.cuda.synchronize()
+    po = oracle_lib.params(seed=12345, depth=12, apply_volcano=1)
+    want = oracle.cells(po, oracle.terrain2d(po))
+    assert cells.cpu().numpy().tobytes() == want.tobytes()
+    # the depth-10 reference digest through the GPU path as well
+    p10 = rnlib.default_params(seed=gold[10]["seed"], depth=10, apply_volcano=1)
+    assert oracle.fnv64(ctx.cells_host(p10).view(np.uint8)) == gold[10]["fnv64"]
+
+
 def test_bad_arguments(ctx, rnlib):
     L = rnlib.lib()
     buf = np.empty((9 * 9, 4), np.float32)

@@ -136,3 +136,13 @@ def test_batch_threads(oracle):
     b = oracle.terrain2d_batch(p, seeds, threads=3)
     for t, s in enumerate(seeds):
         assert np.array_equal(b[t], oracle.terrain2d(oracle_lib.params(seed=s, depth=6, apply_volcano=1)))
+
+
+@pytest.mark.parametrize("entry", GOLD.get("cells", []), ids=lambda e: f"d{e['depth']}-s{e['seed']}")
+def test_cell_quadtree_matches_reference_digests(oracle, entry):
+    """The Cell-quadtree restatement against digests produced by the reference's own generateRecursive."""
+    p = oracle_lib.params(seed=entry["seed"], depth=entry["depth"], apply_volcano=1)
+    cells = oracle.cells(p, oracle.terrain2d(p))
+    assert len(cells) == entry["count"] == oracle_lib.cell_count(entry["depth"])
+    assert oracle.fnv64(cells.view(np.uint8)) == entry["fnv64"]
+    assert cells[:5].view(np.uint32).reshape(-1).tolist() == entry["first"]

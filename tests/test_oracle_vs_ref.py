@@ -32,3 +32,15 @@ def test_reference_lcg(oracle, ref):
     for seed in (1, 12345, 0xFFFFFFFF):
         d = ref.lcg_draws(seed, 64)
         assert [oracle.L.rno_lcg_draw(seed, k) for k in range(64)] == d.tolist()
+
+
+@pytest.mark.parametrize("depth,seed", [(3, 12345), (4, 9), (5, 7), (6, 1), (8, 12345), (9, 31337), (10, 777)])
+def test_cell_quadtree_restatement_equals_reference(oracle, ref, depth, seed):
+    """Terrain::generateRecursive (Terrain.cpp:260-356) run by the reference itself vs rn_oracle_cells.c: positions,
+    colours, radii, quantised normals and the per-level visiting order, byte for byte."""
+    field, rc = ref.cells(depth, seed)
+    p = oracle_lib.params(seed=seed, depth=depth, apply_volcano=1)
+    f2 = oracle.terrain2d(p)
+    assert np.array_equal(field.view(np.uint32), f2.view(np.uint32))
+    oc = oracle.cells(p, f2)
+    assert rc.tobytes() == oc.tobytes()

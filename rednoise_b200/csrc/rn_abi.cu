@@ -31,7 +31,6 @@ struct rn_context {
   size_t slot_bytes[2] = {0, 0};
   cudaEvent_t coarse_done[2] = {nullptr, nullptr};  // coarse stages of the call using slot s have finished
   cudaEvent_t slot_free[2] = {nullptr, nullptr};    // the output stage that read slot s has finished
-  cudaEvent_t frame_done[2] = {nullptr, nullptr};   // the frame tiles of the output stage (side stream) have finished
   bool slot_used[2] = {false, false};
   uint64_t seq = 0;
   int overlap = 1;
@@ -144,7 +143,7 @@ int synth_window_fused(rn_context* ctx, const rn_params* p, const rn_window& w, 
   RN_CUDA(fused_generate(g, pitch, field_stride, p->depth, w.i0, w.j0, w.ni, w.nj, law, p->persistence, p->seed, dev_seeds, nfields,
                          p->apply_volcano != 0, p->amplitude, ctx->slot[sl], stream, &ctx->launches, ctx->profiling ? ctx->ev : nullptr,
                          ctx->profiling ? &ctx->ev_stages : nullptr, overlap ? ctx->coarse_stream : nullptr,
-                         overlap ? ctx->coarse_done[sl] : nullptr, overlap ? ctx->frame_done[sl] : nullptr));
+                         overlap ? ctx->coarse_done[sl] : nullptr));
   RN_CUDA(cudaEventRecord(ctx->slot_free[sl], stream));
   ctx->slot_used[sl] = true;
   return RN_OK;
@@ -265,7 +264,6 @@ int rn_create(int device, rn_context** out_ctx)
   for (int k = 0; k < 2 && e == cudaSuccess; k++) {
     e = cudaEventCreateWithFlags(&ctx->coarse_done[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slot_free[k], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->frame_done[k], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
     rn_destroy(ctx);
@@ -290,7 +288,6 @@ int rn_destroy(rn_context* ctx)
   for (int k = 0; k < 2; k++) {
     if (ctx->coarse_done[k]) cudaEventDestroy(ctx->coarse_done[k]);
     if (ctx->slot_free[k]) cudaEventDestroy(ctx->slot_free[k]);
-    if (ctx->frame_done[k]) cudaEventDestroy(ctx->frame_done[k]);
     cudaFree(ctx->slot[k]);
   }
   for (int k = 0; k < 17; k++)

@@ -27,11 +27,9 @@ template <int L, int T, int NT>
 __global__ void __launch_bounds__(NT, (TileGeo<L, T>::BYTES <= 113 * 1024) ? 2 : 1) k_stage(const __grid_constant__ StageParams sp)
 {
   extern __shared__ __align__(16) float sm[];
-  const int ti = sp.tile_i0 + (int)blockIdx.y, tj = sp.tile_j0 + (int)blockIdx.x;
-  if (ti >= sp.hole_i0 && ti < sp.hole_i1 && tj >= sp.hole_j0 && tj < sp.hole_j1) return;  // streamed interior (k_stream)
   TileCtx cx;
-  cx.I0 = ti * T;
-  cx.J0 = tj * T;
+  cx.I0 = (sp.tile_i0 + (int)blockIdx.y) * T;
+  cx.J0 = (sp.tile_j0 + (int)blockIdx.x) * T;
   const unsigned f = blockIdx.z;
   cx.seed = sp.seeds ? sp.seeds[f] : sp.seed;
   cx.gin = sp.gin ? sp.gin + (size_t)f * sp.gin_field_stride : nullptr;
@@ -125,7 +123,7 @@ size_t fused_scratch_bytes(int depth, int nfields) { return chain_scratch_bytes(
 cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int depth, int i0, int j0, int ni, int nj, const Law& law,
                            float persistence, uint32_t seed, const uint32_t* seeds, int nfields, int volcano, float amplitude,
                            void* scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events, int* nstages,
-                           cudaStream_t coarse_stream, cudaEvent_t coarse_done, cudaEvent_t frame_done)
+                           cudaStream_t coarse_stream, cudaEvent_t coarse_done)
 {
   StageLaunch chain[kMaxLaunches];
   const int nl = build_chain(chain, depth, i0, j0, ni, nj, reinterpret_cast<E4*>(dst), pitch, field_stride, scratch, nfields, law,
@@ -138,16 +136,11 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
   bool has_coarse = false;
   for (int k = 0; k < nl; k++) has_coarse = has_coarse || !chain[k].last;
   const bool split = coarse_stream && coarse_done && coarse_stream != stream && !events && has_coarse;
-  bool joined = false, frame_on_side = false;
+  bool joined = false;
   for (int k = 0; k < nl; k++) {
     const StageLaunch& sl = chain[k];
     const dim3 grid(sl.gx, sl.gy, (unsigned)nfields);
     cudaStream_t s = (split && !sl.last) ? coarse_stream : stream;
-    // frame tiles of a partly streamed output stage (not produced by the current planner) run on the side stream
-    if (split && sl.last && sl.kind == 0 && sl.sp.hole_i1 > sl.sp.hole_i0 && frame_done) {
-      s = coarse_stream;
-      frame_on_side = true;
-    }
     cudaError_t e;
     if (split && sl.last && !joined) {  // the output stage waits for the coarse stages
       e = cudaEventRecord(coarse_done, coarse_stream);
@@ -171,12 +164,6 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
       e = cudaEventRecord(events[k + 1], stream);
       if (e != cudaSuccess) return e;
     }
-  }
-  if (frame_on_side) {  // the call is complete when the frame is, too
-    cudaError_t e = cudaEventRecord(frame_done, coarse_stream);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamWaitEvent(stream, frame_done, 0);
-    if (e != cudaSuccess) return e;
   }
   if (launches) *launches += (uint64_t)nl;
   return cudaSuccess;

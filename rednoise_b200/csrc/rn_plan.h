@@ -206,7 +206,6 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
     sp.seeds = seeds;
     sp.law = law;
     fill_stage_levels(sp, persistence);
-    sp.hole_i0 = sp.hole_i1 = sp.hole_j0 = sp.hole_j1 = 0;
     // a streamed single-level stage: the whole needed rectangle goes through k_stream (no tile launch)
     if (streaming && plan[k].L == 1 && k >= ns - kStreamLevels) {
       const int nt = tiles_per_side(sp.dout);

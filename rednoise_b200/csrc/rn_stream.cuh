@@ -133,7 +133,6 @@ struct Stream {
   // threads with a cell; the lean instantiation lets the few surplus lanes compute on garbage (all in-bounds, never stored)
   static RN_HD bool active(const StreamCtx& cx, int c) { return !EDGE || c <= cx.CW + 1; }
   static RN_HD bool loader(const StreamCtx& cx, int c) { return c <= cx.CW + 2; }   // threads with a lattice column
-  static RN_HD int steps_last(const StreamCtx& cx) { return cx.a1e; }  // steps u = a0-1 .. a1e
 
   // lattice point (row r, thread column c) from the coarser grid; EDGE: only if it exists
   static RN_HD bool lattice_exists(const StreamParams& sp, const StreamCtx& cx, int r, int c)

@@ -79,7 +79,6 @@ struct StageParams {
   int din, dout;
   int win_i0, win_j0, win_ni, win_nj;  // the part of the output grid that is stored
   int tile_i0, tile_j0;                // tile index of blockIdx (y, x) = (0, 0)
-  int hole_i0, hole_i1, hole_j0, hole_j1;  // tiles [i0,i1) x [j0,j1) are produced by the streaming kernel: skipped here
   uint32_t seed;
   const uint32_t* seeds;               // batch: seed of field blockIdx.z (else nullptr)
   Law law;

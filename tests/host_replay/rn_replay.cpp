@@ -49,11 +49,9 @@ int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
     for (unsigned by = 0; by < sl.gy; by++)
       for (unsigned bx = 0; bx < sl.gx; bx++) {
         for (size_t i = 0; i < (size_t)G::WORDS + 2 * GUARD; i++) base[i] = poison ? nanv : 0.0f;
-        const int ti = sl.sp.tile_i0 + (int)by, tj = sl.sp.tile_j0 + (int)bx;
-        if (ti >= sl.sp.hole_i0 && ti < sl.sp.hole_i1 && tj >= sl.sp.hole_j0 && tj < sl.sp.hole_j1) continue;
         TileCtx cx;
-        cx.I0 = ti * kTile;
-        cx.J0 = tj * kTile;
+        cx.I0 = (sl.sp.tile_i0 + (int)by) * kTile;
+        cx.J0 = (sl.sp.tile_j0 + (int)bx) * kTile;
         cx.seed = seeds ? seeds[f] : sl.sp.seed;
         cx.gin = sl.sp.gin ? sl.sp.gin + (size_t)f * sl.sp.gin_field_stride : nullptr;
         cx.gout = sl.sp.gout + (size_t)f * sl.sp.gout_field_stride;

@@ -241,10 +241,10 @@ def test_batch_equals_singles(ctx, rnlib, oracle, algo):
 
 
 def test_algorithms_agree_at_full_size(ctx, rnlib, oracle):
-    """Depth 12 (4097^2) and depth 13: the fused tile path and the level-synchronous path are
-    independent implementations; bitwise equality at sizes the oracle is slow for."""
+    """Depth 12 (4097^2), 13 and 14 (16385^2, the deepest field the ABI accepts): the streamed/fused path and the
+    level-synchronous path are independent implementations; bitwise equality at sizes the oracle is slow for."""
     import torch
-    for depth, seed in ((12, 2), (13, 12345)):
+    for depth, seed in ((12, 2), (13, 12345), (14, 99)):
         S = (1 << depth) + 1
         p = rnlib.default_params(seed=seed, depth=depth, apply_volcano=1)
         a = torch.empty((S, S, 4), device="cuda", dtype=torch.float32)

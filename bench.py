@@ -42,6 +42,29 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", {}
 
 
+def alu_roofline(args, value_gs, kernel_ms, my_samples, sm_mhz):
+    """The instruction-issue ("ALU") bound of the output kernel: thread instructions per sample counted by ncu on the
+    committed capture (profiles/r01o_stream_kernel_ncu_metrics.json) against 148 SMs x 4 schedulers x 32 lanes x the SM clock
+    seen during this run.  The bit-exact contract forbids FMA contraction, so this bound sits below the HBM-write bound."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01o_stream_kernel_ncu_metrics.json")))
+        if args.workload != "field" or args.depth != 12:
+            return None
+        warp_inst = float(d["smsp__inst_executed.sum"][0])
+        lanes = float(d["smsp__thread_inst_executed_per_inst_executed.ratio"][0])
+        side = (1 << args.depth) + 1
+        inst_per_sample = warp_inst * lanes / (side * side)
+        mhz = float(sm_mhz or 1965.0)
+        peak = 148 * 4 * 32 * mhz * 1e6           # thread instructions / s
+        bound = peak / inst_per_sample / 1e9      # Gsamples/s of the output kernel at 100 % issue
+        achieved = my_samples / (kernel_ms * 1e-3) / 1e9
+        return {"bound": "issue", "thread_inst_per_sample": inst_per_sample, "peak_thread_inst_per_s": peak,
+                "gsamples_bound": bound, "achieved_gsamples_kernel": achieved, "frac": achieved / bound,
+                "source": "profiles/r01o_stream_kernel_ncu_metrics.json (ncu --set full, k_stream<128>)"}
+    except Exception:
+        return None
+
+
 def ncu_traffic(args):
     """dram__bytes_read.sum + dram__bytes_write.sum of the output-stage kernel per launch, from the committed
     `ncu --set full` capture of this command (profiles/roofline_traffic.json); None for other workloads."""
@@ -178,7 +201,7 @@ def run_reference_arm(args):
     depth = args.depth
     side = (1 << depth) + 1
     samples = side * side
-    procs = max(1, min(os.cpu_count() or 1, args.cpu_procs))
+    procs = max(1, min(os.cpu_count() or 1, args.cpu_procs or (os.cpu_count() or 1)))
     fps, kind, round_s, pass_s = cpu_fields_per_second(depth, procs, args.warmup + args.steps, budget_s=240.0)
     timed = round_s[args.warmup:] if len(round_s) > args.warmup else round_s
     ms = 1e3 * statistics.mean(timed)
@@ -398,6 +421,9 @@ def run_ours(args):
         }
         if stage_ms:
             line["stage_ms"] = stage_ms
+            alu = alu_roofline(args, value, k_ms, my_samples, (clocks or {}).get("sm_mhz"))
+            if alu:
+                line["roofline_alu"] = alu
         if world == 1 and not args.no_cpu:
             try:
                 procs = 1
@@ -428,7 +454,7 @@ def main():
     ap.add_argument("--gather", action="store_true", help="slab workload: assemble the field on every rank with one NCCL all-gather per step")
     ap.add_argument("--depth", type=int, default=None)
     ap.add_argument("--algo", type=int, default=0)
-    ap.add_argument("--cpu-procs", type=int, default=16, help="reference arm: concurrent single-threaded generators")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="reference arm: concurrent single-threaded generators (0 = all host cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-pipelining", action="store_true", help="run the coarse stages on the caller's stream (no overlap between calls)")
     args = ap.parse_args()

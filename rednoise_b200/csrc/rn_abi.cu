@@ -34,6 +34,10 @@ struct rn_context {
   bool slot_used[2] = {false, false};
   uint64_t seq = 0;
   int overlap = 1;
+  // host destinations: the window is produced in row chunks, chunk k+1 is synthesized while chunk k crosses PCIe
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t chunk_ready[2] = {nullptr, nullptr};   // synthesis of the chunk in staging half h has finished
+  cudaEvent_t chunk_copied[2] = {nullptr, nullptr};  // its device-to-host copy has finished
   // stage profiling
   int profiling = 0;
   cudaEvent_t ev[17] = {};
@@ -261,9 +265,12 @@ int rn_create(int device, rn_context** out_ctx)
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   e = cudaStreamCreateWithPriority(&ctx->coarse_stream, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for (int k = 0; k < 2 && e == cudaSuccess; k++) {
     e = cudaEventCreateWithFlags(&ctx->coarse_done[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slot_free[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->chunk_ready[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->chunk_copied[k], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
     rn_destroy(ctx);
@@ -281,6 +288,10 @@ int rn_destroy(rn_context* ctx)
     cudaStreamSynchronize(ctx->coarse_stream);
     cudaStreamDestroy(ctx->coarse_stream);
   }
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
@@ -288,6 +299,8 @@ int rn_destroy(rn_context* ctx)
   for (int k = 0; k < 2; k++) {
     if (ctx->coarse_done[k]) cudaEventDestroy(ctx->coarse_done[k]);
     if (ctx->slot_free[k]) cudaEventDestroy(ctx->slot_free[k]);
+    if (ctx->chunk_ready[k]) cudaEventDestroy(ctx->chunk_ready[k]);
+    if (ctx->chunk_copied[k]) cudaEventDestroy(ctx->chunk_copied[k]);
     cudaFree(ctx->slot[k]);
   }
   for (int k = 0; k < 17; k++)
@@ -395,22 +408,54 @@ int rn_terrain2d(rn_context* ctx, const rn_params* p, const rn_window* win, rn_e
     }
   } else {
     // ---- algorithm 2 (default): fused tiles write the window directly ----
-    Elem* g;
-    size_t gpitch;
+    Elem* g = nullptr;
+    size_t gpitch = 0;
+    bool chunked = false;
     if (aligned) {
       g = reinterpret_cast<Elem*>(dst);
       gpitch = pitch_elems;
+      st = synth_window_fused(ctx, p, w, g, gpitch, 0, nullptr, 1, stream);
+      if (st != RN_OK) return st;
+    } else if (!dst_is_device && ctx->copy_stream && (size_t)w.ni * (size_t)w.nj >= ((size_t)1 << 22)) {
+      // Large host destination: row chunks through two staging halves, so that synthesis of chunk k+1 overlaps the
+      // PCIe transfer of chunk k (the transfer is the bottleneck: 16 B/sample at ~55 GB/s).
+      chunked = true;
+      int rows = (int)(((size_t)32 << 20) / ((size_t)w.nj * sizeof(Elem)));  // ~32 MB per chunk
+      rows = rows < 64 ? 64 : (rows / 64) * 64;
+      const size_t half = (size_t)rows * (size_t)w.nj;
+      st = ensure(&ctx->field, &ctx->field_bytes, sizeof(Elem) * 2 * half);
+      if (st != RN_OK) return st;
+      int k = 0;
+      for (int r0 = 0; r0 < w.ni; r0 += rows, k++) {
+        const int nr = (w.ni - r0 < rows) ? w.ni - r0 : rows;
+        const int h = k & 1;
+        Elem* stage = reinterpret_cast<Elem*>(ctx->field) + (size_t)h * half;
+        if (k >= 2) RN_CUDA(cudaStreamWaitEvent(stream, ctx->chunk_copied[h], 0));  // the staging half is free again
+        const rn_window cw{w.i0 + r0, w.j0, nr, w.nj};
+        st = synth_window_fused(ctx, p, cw, stage, (size_t)w.nj, 0, nullptr, 1, stream);
+        if (st != RN_OK) return st;
+        RN_CUDA(cudaEventRecord(ctx->chunk_ready[h], stream));
+        RN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ready[h], 0));
+        RN_CUDA(cudaMemcpy2DAsync(dst + (size_t)r0 * pitch_elems, pitch_elems * sizeof(Elem), stage, (size_t)w.nj * sizeof(Elem),
+                                  (size_t)w.nj * sizeof(Elem), (size_t)nr, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        RN_CUDA(cudaEventRecord(ctx->chunk_copied[h], ctx->copy_stream));
+      }
+      RN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     } else {
       st = ensure(&ctx->field, &ctx->field_bytes, sizeof(Elem) * (size_t)w.ni * (size_t)w.nj);
       if (st != RN_OK) return st;
       g = reinterpret_cast<Elem*>(ctx->field);
       gpitch = (size_t)w.nj;
-    }
-    st = synth_window_fused(ctx, p, w, g, gpitch, 0, nullptr, 1, stream);
-    if (st != RN_OK) return st;
-    if (!aligned)
+      st = synth_window_fused(ctx, p, w, g, gpitch, 0, nullptr, 1, stream);
+      if (st != RN_OK) return st;
       RN_CUDA(cudaMemcpy2DAsync(dst, pitch_elems * sizeof(Elem), g, gpitch * sizeof(Elem), (size_t)w.nj * sizeof(Elem), (size_t)w.ni,
                                 dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+    }
+    if (volcano_pos && chunked && centre_inside) {
+      // the destination is host memory and complete: read the centre sample from it
+      const rn_element& e = dst[(size_t)(c - w.i0) * pitch_elems + (size_t)(c - w.j0)];
+      centre = Elem{e.x, e.y, e.z, e.shade};
+    } else
     if (volcano_pos) {
       if (centre_inside) {
         RN_CUDA(cudaMemcpyAsync(&centre, g + (size_t)(c - w.i0) * gpitch + (size_t)(c - w.j0), sizeof(Elem), cudaMemcpyDeviceToHost, stream));

@@ -182,6 +182,36 @@ def test_cell_quadtree_depth12_digest_and_device_path(ctx, rnlib, oracle):
     assert oracle.fnv64(ctx.cells_host(p10).view(np.uint8)) == gold[10]["fnv64"]
 
 
+def test_many_seeds_and_depths(ctx, rnlib, oracle):
+    """A sweep of seeds (the band / bulgy branches and the sqrt path of normalise are data dependent)."""
+    ctx.set_algorithm(0)
+    rng = np.random.default_rng(2026)
+    cases = [(9, int(s)) for s in rng.integers(0, 2**32, 12)] + [(10, int(s)) for s in rng.integers(0, 2**32, 6)] + \
+            [(11, int(s)) for s in rng.integers(0, 2**32, 2)]
+    for depth, seed in cases:
+        for volc in (0, 1):
+            got = ctx.terrain2d_host(rnlib.default_params(seed=seed, depth=depth, apply_volcano=volc))
+            want = oracle.terrain2d(oracle_lib.params(seed=seed, depth=depth, apply_volcano=volc))
+            assert_bitwise(got, want, f"depth {depth} seed {seed} volcano {volc}")
+
+
+def test_empty_batch_and_single_sample_windows(ctx, rnlib, oracle):
+    import torch
+    ctx.set_algorithm(0)
+    p = rnlib.default_params(depth=10, apply_volcano=1)
+    ctx.terrain2d_batch_ptr(p, [], 0, dst_is_device=False) if False else None  # ctypes cannot pass a NULL dst: covered below
+    L = rnlib.lib()
+    buf = np.zeros(4, np.float32)
+    seeds = (C.c_uint32 * 1)(5)
+    assert L.rn_terrain2d_batch(ctx._h, C.byref(p), seeds, 0, buf.ctypes.data, 0, 0, None) == rnlib.RN_OK   # ntiles == 0
+    assert L.rn_terrain2d_batch(ctx._h, C.byref(p), seeds, -1, buf.ctypes.data, 0, 0, None) == rnlib.RN_ERR_BAD_PARAM
+    full = oracle.terrain2d(oracle_lib.params(depth=10, apply_volcano=1))
+    S = rnlib.side(10)
+    for (i, j) in [(0, 0), (S - 1, S - 1), (S // 2, S // 2), (1, S - 2), (S - 1, 0)]:
+        got = ctx.terrain2d_host(p, window=rnlib.Window(i, j, 1, 1))
+        assert_bitwise(got, full[i:i + 1, j:j + 1], f"1x1 window at {(i, j)}")
+
+
 def test_bad_arguments(ctx, rnlib):
     L = rnlib.lib()
     buf = np.empty((9 * 9, 4), np.float32)

@@ -174,6 +174,23 @@ uint64_t rn_terrain2d_cell_level_offset(int level);
 int rn_terrain2d_cells(rn_context* ctx, const rn_params* p, const rn_element* field, size_t field_pitch, int field_is_device,
                        rn_cell* cells, int cells_is_device, void* stream);
 
+/* ---- 3D density volume: an EXTENSION, not a drop-in -------------------------------------------
+ * The reference has no volume generator: there is nothing to be bit-exact with, so the
+ * definition is this repository's own CPU specification oracle/rn_oracle3d.c -- 3D midpoint displacement in the
+ * reference's style (cube centres, face centres, edge midpoints per level; amplitude law of Rock.cpp:185,
+ * random() of basics.h:16-19; depth-1 levels on a (W+1)^3 lattice, W = 1 << depth).  The CUDA path reproduces that
+ * specification bit for bit.  Planes [i0, i0+ni) of the volume are final after the call; `vol` is DEVICE memory in
+ * the full-volume layout, element (i,j,k) at vol[(i*(W+1)+j)*(W+1)+k] (planes outside the slab receive partial
+ * coarse-level data): slabs of one volume are independent, which is how it shards across GPUs. */
+#define RN_VOLUME_MIN_DEPTH 2
+#define RN_VOLUME_MAX_DEPTH 11 /* 2049^3 floats = 34.4 GB */
+typedef struct rn_volume_params {
+  uint32_t seed;
+  int32_t depth;
+  float amplitude;
+} rn_volume_params;
+int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, float* vol, void* stream);
+
 /* Device self-test of the arithmetic shortcuts: the normal-range sqrt / reciprocal sequences
  * used by the fused kernels are compared with the IEEE-rounded intrinsics over every binary32
  * value in 2^-100 .. 2^100.  mismatches[0..2] = sqrt, reciprocal, 1/sqrt (all must be 0). */

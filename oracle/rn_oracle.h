@@ -48,6 +48,10 @@ int rno_terrain2d_batch(const rn_params* p, const uint32_t* seeds, int ntiles, r
 uint64_t rno_cell_count(int depth);
 int rno_terrain2d_cells(const rn_params* p, const rn_element* field, rn_cell* cells);
 
+/* 3D density-volume extension (rn_oracle3d.c): NO reference counterpart, parity unpinned by the reference. */
+uint32_t rno_volume_draw(uint32_t seed, uint64_t idx);
+int rno_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, float* volume);
+
 uint64_t rno_fnv64(const void* data, size_t nbytes);
 
 #ifdef __cplusplus

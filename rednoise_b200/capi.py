@@ -22,7 +22,7 @@ SYMBOLS = [
     "rn_version", "rn_last_error_string", "rn_status_string", "rn_params_default", "rn_terrain2d_side",
     "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
     "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_set_pipelining", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device", "rn_selftest_math",
-    "rn_terrain2d_cell_count", "rn_terrain2d_cell_level_offset", "rn_terrain2d_cells",
+    "rn_terrain2d_cell_count", "rn_terrain2d_cell_level_offset", "rn_terrain2d_cells", "rn_volume3d",
 ]
 
 
@@ -39,6 +39,11 @@ class Params(C.Structure):
 
 CELL_DTYPE = np.dtype([("position", np.float32, 3), ("colour", np.float32, 3), ("radius", np.float32), ("normal", np.int8, 3),
                        ("level", np.uint8)])  # rn_cell, 32 bytes
+
+
+class VolumeParams(C.Structure):
+    """rn_volume_params (3D extension)."""
+    _fields_ = [("seed", C.c_uint32), ("depth", C.c_int32), ("amplitude", C.c_float)]
 
 
 class Window(C.Structure):
@@ -94,6 +99,7 @@ def lib() -> C.CDLL:
     L.rn_terrain2d_cell_level_offset.restype = u64
     L.rn_terrain2d_cell_level_offset.argtypes = [i32]
     L.rn_terrain2d_cells.argtypes = [vp, C.POINTER(Params), vp, sz, i32, vp, i32, vp]
+    L.rn_volume3d.argtypes = [vp, C.POINTER(VolumeParams), i32, i32, vp, vp]
     _lib = L
     return L
 
@@ -208,6 +214,13 @@ class Context:
         self.cells_ptr(p, out.ctypes.data, field_ptr=field.ctypes.data if field is not None else 0, field_is_device=False,
                        cells_is_device=False)
         return out
+
+    def volume3d_ptr(self, seed: int, depth: int, amplitude: float, ptr: int, *, i0: int = 0, ni: int | None = None, stream: int = 0):
+        """3D extension: planes [i0, i0+ni) of the (W+1)^3 float volume at device pointer `ptr` (full-volume layout)."""
+        vp_ = VolumeParams(seed & 0xFFFFFFFF, depth, amplitude)
+        side = (1 << depth) + 1
+        _check(lib().rn_volume3d(self._h, C.byref(vp_), i0, side - i0 if ni is None else ni, C.c_void_p(ptr),
+                                 C.c_void_p(stream) if stream else None))
 
     def selftest_math(self):
         buf = (C.c_uint64 * 3)()

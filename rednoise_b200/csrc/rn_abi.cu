@@ -592,6 +592,21 @@ int rn_terrain2d_cells(rn_context* ctx, const rn_params* p, const rn_element* fi
   return RN_OK;
 }
 
+int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, float* vol, void* stream_v)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  if (!p || !vol) return fail(RN_ERR_BAD_PARAM, "params/vol is NULL");
+  if (p->depth < RN_VOLUME_MIN_DEPTH || p->depth > RN_VOLUME_MAX_DEPTH) return fail(RN_ERR_BAD_PARAM, "volume depth out of range [2,11]");
+  const int side = (1 << p->depth) + 1;
+  if (i0 < 0 || ni <= 0 || i0 > side - ni) return fail(RN_ERR_BAD_PARAM, "slab does not lie inside the volume");
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+  RN_CUDA(volume_generate(vol, p->depth, p->seed, p->amplitude, i0, ni, stream, &ctx->launches));
+  if (!stream_v) RN_CUDA(cudaStreamSynchronize(stream));
+  return RN_OK;
+}
+
 int rn_selftest_math(rn_context* ctx, uint64_t* mismatches3)
 {
   if (!ctx || !mismatches3) return fail(RN_ERR_BAD_PARAM, "ctx/mismatches3 is NULL");

@@ -22,6 +22,10 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
 cudaError_t cells_generate(void* cells, const Elem* field, size_t pitch, int depth, float feature_scale, float size, float amplitude,
                            cudaStream_t stream, uint64_t* launches);
 
+// 3D density-volume extension (rn_volume.cu; defined by the CPU specification of DESIGN.md section 5.8, no reference counterpart):
+// planes [i0, i0+ni) of the (W+1)^3 float volume d (full-volume layout).
+cudaError_t volume_generate(float* d, int depth, uint32_t seed, float amplitude, int i0, int ni, cudaStream_t stream, uint64_t* launches);
+
 // Epilogues / utilities (rn_util.cu).
 // addVolcano (Terrain.cpp:121-141) over the window [i0,i0+ni) x [j0,j0+nj) of a depth-`depth` field
 // stored at g with row pitch `pitch` (g points at window element (i0,j0)).

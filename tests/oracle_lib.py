@@ -93,6 +93,7 @@ class Oracle:
         L.rno_cell_count.restype = C.c_uint64
         L.rno_cell_count.argtypes = [C.c_int]
         L.rno_terrain2d_cells.argtypes = [vp, vp, vp]
+        L.rno_volume3d.argtypes = [C.c_uint32, C.c_int, C.c_float, C.c_int, C.c_int, vp]
         L.rno_fnv64.restype = C.c_uint64
         L.rno_fnv64.argtypes = [vp, C.c_size_t]
 
@@ -130,6 +131,15 @@ class Oracle:
         if st != 0:
             raise RuntimeError(f"oracle status {st}")
         return out
+
+    def volume3d(self, seed: int, depth: int, amplitude: float, i0: int = 0, ni=None, fill=np.nan) -> np.ndarray:
+        """3D extension (rn_oracle3d.c, no reference counterpart): planes [i0, i0+ni) final, the rest `fill` or partial."""
+        S = (1 << depth) + 1
+        v = np.full((S, S, S), fill, np.float32)
+        st = self.L.rno_volume3d(seed & 0xFFFFFFFF, depth, amplitude, i0, S - i0 if ni is None else ni, v.ctypes.data)
+        if st != 0:
+            raise RuntimeError(f"oracle status {st}")
+        return v
 
     def fnv64(self, a: np.ndarray) -> str:
         a = np.ascontiguousarray(a)

@@ -199,7 +199,6 @@ def test_empty_batch_and_single_sample_windows(ctx, rnlib, oracle):
     import torch
     ctx.set_algorithm(0)
     p = rnlib.default_params(depth=10, apply_volcano=1)
-    ctx.terrain2d_batch_ptr(p, [], 0, dst_is_device=False) if False else None  # ctypes cannot pass a NULL dst: covered below
     L = rnlib.lib()
     buf = np.zeros(4, np.float32)
     seeds = (C.c_uint32 * 1)(5)

@@ -200,6 +200,29 @@ def run_reference_arm(args):
         return 0
     depth = args.depth
     side = (1 << depth) + 1
+    if args.workload == "volume":
+        # the 3D volume is an extension without a reference implementation: the arm times its CPU specification
+        from tests import oracle_lib
+        o = oracle_lib.load_oracle()
+        d_cpu = min(depth, 7)
+        n_cpu = ((1 << d_cpu) + 1) ** 3
+        times = []
+        for _ in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            o.volume3d(BASE_SEED, d_cpu, 0.3)
+            times.append(time.perf_counter() - t0)
+        timed = times[args.warmup:] or times
+        ms = 1e3 * statistics.mean(timed)
+        value = n_cpu / (ms * 1e-3) / 1e9
+        print(json.dumps({
+            "impl": "reference", "metric": "red-noise field synthesis throughput", "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus,
+            "steps": len(timed), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": 1, "kind": "port",
+                             "sample": f"one {(1 << d_cpu) + 1}^3 volume per step by the CPU specification oracle/rn_oracle3d.c (no reference "
+                                       "implementation of a volume generator exists)", "host_cpus": os.cpu_count()},
+            "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return 0
     samples = side * side
     procs = max(1, min(os.cpu_count() or 1, args.cpu_procs or (os.cpu_count() or 1)))
     fps, kind, round_s, pass_s = cpu_fields_per_second(depth, procs, args.warmup + args.steps, budget_s=240.0)
@@ -230,19 +253,24 @@ def workload_config(args):
         "slab": f"row slabs of ONE {side}x{side} field (depth={args.depth}, seed {BASE_SEED}) sharded over the ranks"
                 + (", assembled on every rank by one NCCL all-gather" if getattr(args, "gather", False) else ""),
         "batch": f"batch of {getattr(args, 'tiles', 0)} independent {side}x{side} fields (depth={args.depth}, seeds {BASE_SEED}+k), round-robin over the ranks",
+        "volume": f"{side}^3 3D density volume ({args.depth - 1} displacement levels), seed {BASE_SEED}, amplitude 0.3, i-slabs over the ranks -- "
+                  "EXTENSION defined by oracle/rn_oracle3d.c, the reference has no volume generator",
     }[args.workload]
     par = {"field": f"dp{args.gpus}: one process per GPU, one independent field each, no collective",
            "slab": f"slab{args.gpus}: equal row slabs, dependency cone recomputed per rank, no data-path collective",
-           "batch": f"dp{args.gpus}: fields round-robin over the ranks, no collective"}[args.workload]
+           "batch": f"dp{args.gpus}: fields round-robin over the ranks, no collective",
+           "volume": f"slab{args.gpus}: i-slabs of one volume, dependency cone recomputed per rank, no collective"}[args.workload]
     return {
         "workload": what,
         "baseline_config": {"field": "configs[1]: 4096x4096 2D heightfield, 12 octaves, single B200",
                             "slab": "2D analogue of configs[3] (slab-sharded large field; the reference has no 3D generator)",
-                            "batch": "configs[4]: batch of independent 1024x1024 tiles with distinct seeds"}[args.workload]
-                           if args.depth in (10, 12, 14) else f"depth {args.depth}",
+                            "batch": "configs[4]: batch of independent 1024x1024 tiles with distinct seeds",
+                            "volume": {9: "configs[2]: 512^3 3D density volume, 8 octaves, single B200",
+                                       11: "configs[3]: 2048^3 3D volume, 10 octaves, slab-sharded"}.get(args.depth, f"3D depth {args.depth}")}[args.workload]
+                           if args.depth in (9, 10, 11, 12, 14) else f"depth {args.depth}",
         "fields_per_step_per_rank": 1 if args.workload != "batch" else None,
-        "samples_per_field": side * side,
-        "bytes_per_sample": ELEM_BYTES,
+        "samples_per_field": side * side if args.workload != "volume" else side ** 3,
+        "bytes_per_sample": ELEM_BYTES if args.workload != "volume" else 4,
         "cache_policy": "the output of a step (268 MB at depth 12) is larger than the 126 MB L2 and there is no input; no explicit L2 flush",
         "parallelism": par,
     }
@@ -301,6 +329,19 @@ def run_ours(args):
                 ctx.terrain2d_ptr(p, dst.data_ptr(), window=win, dst_is_device=True, stream=stream)
             if args.gather and world > 1:
                 sharding.all_gather_slabs(dst, side)
+    elif args.workload == "volume":  # 3D extension: i-slabs of ONE (W+1)^3 density volume, halo recomputed per rank
+        S3 = side
+        i0, _, ni, _ = sharding.slab_window(S3, rank, world)
+        my_samples = ni * S3 * S3
+        nj = S3
+        vol = torch.empty((S3, S3, S3), device="cuda", dtype=torch.float32)  # full-volume layout (the ABI's contract)
+        p = None
+        win = None
+        seeds = []
+
+        def step():
+            if ni:
+                ctx.volume3d_ptr(BASE_SEED, depth, 0.3, vol.data_ptr(), i0=i0, ni=ni, stream=stream)
     else:  # batch: args.tiles independent fields with distinct seeds, round-robin over the ranks
         p = capi.default_params(seed=BASE_SEED, depth=depth, apply_volcano=1)
         win = None
@@ -355,7 +396,19 @@ def run_ours(args):
 
     # ---- e2e: the same C-ABI call with a HOST destination (pinned), D2H inside the timed region ----
     e2e_steps = max(2, min(args.steps, 5))
-    if args.workload == "batch":
+    if args.workload == "volume":
+        # bounded pinned buffer (<= 1 GiB per rank): the e2e leg generates and ships a sub-slab of ni_e planes
+        ni_e = max(0, min(ni, (1 << 30) // (S3 * S3 * 4)))
+        host = torch.empty((max(ni_e, 1), S3, S3), dtype=torch.float32, pin_memory=True)
+        e2e_samples = ni_e * S3 * S3
+
+        def e2e_step():
+            if ni_e:
+                ctx.volume3d_ptr(BASE_SEED, depth, 0.3, vol.data_ptr(), i0=i0, ni=ni_e)  # blocking
+                host[:ni_e].copy_(vol[i0:i0 + ni_e])                                      # the slab's planes are contiguous
+                return float(host[ni_e // 2, S3 // 2, S3 // 2])
+            return 0.0
+    elif args.workload == "batch":
         e2e_tiles = min(len(seeds), 32)  # bounded pinned buffer; the metric is a rate
         host = torch.empty((max(e2e_tiles, 1), side, side, 4), dtype=torch.float32, pin_memory=True)
         e2e_samples = e2e_tiles * side * side
@@ -400,7 +453,8 @@ def run_ours(args):
             k_ms, k_name = stage_ms["final_ms"], stage_ms.get("final_name", "final stage")
         else:
             k_ms, k_name = statistics.mean(per_step), "whole step (all launches)"
-        achieved = my_samples * ELEM_BYTES / (k_ms * 1e-3) / 1e9
+        bytes_per_sample = 4 if args.workload == "volume" else ELEM_BYTES
+        achieved = my_samples * bytes_per_sample / (k_ms * 1e-3) / 1e9
         line = {
             "metric": "red-noise field synthesis throughput", "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -409,11 +463,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(args),
                          "kernel": k_name, "kernel_ms": k_ms, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": my_samples * ELEM_BYTES,
-                         "samples_per_s_bound_hbm": peak * 1e9 / ELEM_BYTES / 1e9},
+                         "algorithmic_bytes_per_launch": my_samples * bytes_per_sample,
+                         "samples_per_s_bound_hbm": peak * 1e9 / bytes_per_sample / 1e9},
             "e2e": {"value": all_e2e_samples / e2e_s / 1e9, "unit": "Gsamples/s",
                     "h2d_bytes_per_step": 48 + (4 * len(seeds[:32]) if args.workload == "batch" else 0),
-                    "d2h_bytes_per_step": e2e_samples * ELEM_BYTES, "ms_per_step": e2e_s * 1e3,
+                    "d2h_bytes_per_step": e2e_samples * (4 if args.workload == "volume" else ELEM_BYTES), "ms_per_step": e2e_s * 1e3,
                     "note": "rn_terrain2d()/rn_terrain2d_batch() with a pinned HOST destination: synthesis + D2H of the samples + host read; "
                             "the only inputs are the 48-byte rn_params (and the seeds of a batch)"},
             "gpu_launches": int(launches), "clocks": clocks, "algorithm": args.algo,
@@ -424,7 +478,22 @@ def run_ours(args):
             alu = alu_roofline(args, value, k_ms, my_samples, (clocks or {}).get("sm_mhz"))
             if alu:
                 line["roofline_alu"] = alu
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.workload == "volume":
+            try:
+                from tests import oracle_lib
+                o = oracle_lib.load_oracle()
+                d_cpu = min(depth, 7)
+                t0 = time.perf_counter()
+                o.volume3d(BASE_SEED, d_cpu, 0.3)
+                dt = time.perf_counter() - t0
+                n_cpu = ((1 << d_cpu) + 1) ** 3
+                line["cpu_baseline"] = {"value": n_cpu / dt / 1e9, "unit": "Gsamples/s", "cores": 1, "kind": "port",
+                                        "sample": f"one {(1 << d_cpu) + 1}^3 volume by the CPU specification (oracle/rn_oracle3d.c, the definition of this "
+                                                  f"extension; no reference implementation exists) on one host thread: {dt * 1e3:.0f} ms",
+                                        "host_cpus": os.cpu_count()}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "Gsamples/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        elif world == 1 and not args.no_cpu:
             try:
                 procs = 1
                 fps, kind, round_s, pass_s = cpu_fields_per_second(depth, procs, rounds=8, budget_s=20.0)
@@ -449,7 +518,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="field", choices=["field", "slab", "batch"])
+    ap.add_argument("--workload", default="field", choices=["field", "slab", "batch", "volume"])
     ap.add_argument("--tiles", type=int, default=1024, help="batch workload: independent fields per step (all ranks together)")
     ap.add_argument("--gather", action="store_true", help="slab workload: assemble the field on every rank with one NCCL all-gather per step")
     ap.add_argument("--depth", type=int, default=None)
@@ -459,7 +528,7 @@ def main():
     ap.add_argument("--no-pipelining", action="store_true", help="run the coarse stages on the caller's stream (no overlap between calls)")
     args = ap.parse_args()
     if args.depth is None:
-        args.depth = {"field": 12, "slab": 14, "batch": 10}[args.workload]
+        args.depth = {"field": 12, "slab": 14, "batch": 10, "volume": 9}[args.workload]
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)

@@ -48,7 +48,7 @@ def test_spec_digests(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("depth,seed", [(2, 1), (3, 12345), (4, 7), (5, 12345), (6, 99), (7, 2024)])
+@pytest.mark.parametrize("depth,seed", [(2, 1), (3, 12345), (4, 7), (5, 12345), (6, 99), (7, 2024), (8, 31337)])
 def test_gpu_volume_equals_spec_bitwise(ctx, rnlib, oracle, depth, seed):
     import torch
     S = (1 << depth) + 1
@@ -64,11 +64,11 @@ def test_gpu_volume_equals_spec_bitwise(ctx, rnlib, oracle, depth, seed):
 def test_gpu_volume_slabs_are_independent(ctx, rnlib, oracle):
     """What the 2048^3 multi-GPU workload relies on: a slab generated alone == the same planes of the whole volume."""
     import torch
-    depth = 7
+    depth = 8
     S = (1 << depth) + 1
     full = torch.empty((S, S, S), device="cuda", dtype=torch.float32)
     ctx.volume3d_ptr(5, depth, 0.3, full.data_ptr())
-    for world in (2, 8):
+    for world in (2, 8, 5):
         rows = (S + world - 1) // world
         for r in range(world):
             i0 = r * rows

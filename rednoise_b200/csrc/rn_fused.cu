@@ -40,32 +40,84 @@ __global__ void __launch_bounds__(NT, (TileGeo<L, T>::BYTES <= 113 * 1024) ? 2 :
 }
 
 // Streaming form of one level (rn_stream.cuh): blockIdx.x = column strip, blockIdx.y = row segment.
-template <int NT, bool EDGE>
-__device__ __forceinline__ void stream_march(const StreamParams& sp, const StreamCtx& cx, float* sm)
+template <int NT, bool EDGE, int PH>
+__device__ __forceinline__ void stream_step(const StreamParams& sp, const StreamCtx& cx, float* sm, StreamThread& th, int u, int c)
 {
   using S = Stream<NT, EDGE>;
+  S::template interval1<PH>(sp, cx, sm, th, u, c);
+  __syncthreads();
+  S::template interval2<PH>(sp, cx, sm, th, u, c);
+  __syncthreads();
+  S::template interval3<PH>(sp, cx, sm, th, u, c);
+  __syncthreads();
+}
+
+template <int NT>
+__device__ __forceinline__ void stream_march(const StreamParams& sp, const StreamCtx& cx, float* sm)
+{
+  using S = Stream<NT, true>;
   const int c = (int)threadIdx.x;
   StreamThread th;
   S::init(sp, cx, sm, th, c);
   __syncthreads();
-  for (int u = cx.a0 - 1; u <= cx.a1e; u++) {
-    S::interval1(sp, cx, sm, th, u, c);
-    __syncthreads();
-    S::interval2(sp, cx, sm, th, u, c);
-    __syncthreads();
-    S::interval3(sp, cx, sm, th, u, c);
-    __syncthreads();
+  // Every warp executes the same three barriers per step, in whichever instantiation its columns and the step's rows allow.
+  const bool warp_lean = stream_warp_is_lean(sp, cx, c) && cx.lean_lo <= cx.lean_hi;
+  const int last = cx.a1e;
+  int u = cx.a0 - 1;
+  while (u <= last) {
+    if (warp_lean && u == cx.lean_lo) {
+      const int hi = cx.lean_hi;
+#if RN_STREAM_UNROLL == 4
+      // four steps per trip: the ring slot of every rolling row is a compile-time constant (step_of(u) & 3 = PH)
+      for (;;) {
+        stream_step<NT, false, 0>(sp, cx, sm, th, u, c);
+        if (u == hi) break;
+        stream_step<NT, false, 1>(sp, cx, sm, th, u + 1, c);
+        if (u + 1 == hi) break;
+        stream_step<NT, false, 2>(sp, cx, sm, th, u + 2, c);
+        if (u + 2 == hi) break;
+        stream_step<NT, false, 3>(sp, cx, sm, th, u + 3, c);
+        if (u + 3 == hi) break;
+        u += 4;
+      }
+#else
+      for (; u <= hi; u++) stream_step<NT, false, -1>(sp, cx, sm, th, u, c);
+#endif
+      u = hi + 1;
+    } else {
+      stream_step<NT, true, -1>(sp, cx, sm, th, u, c);
+      u++;
+    }
   }
-  S::store_rows(sp, cx, sm, th, cx.a1e - 1);
+  S::store_rows(sp, cx, sm, th, cx.a1e - 1, S::mod(S::step_of(cx, cx.a1e - 1), 2));
 }
+
+#ifdef RN_STREAM_TRACE
+__device__ unsigned long long g_trace[4 * 8192];
+#endif
 
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_stream(const __grid_constant__ StreamParams sp)
 {
   extern __shared__ __align__(16) float sm[];
-  const StreamCtx cx = stream_ctx(sp, (int)blockIdx.x, (int)blockIdx.y, blockIdx.z);
-  if (stream_is_edge(sp, cx)) stream_march<NT, true>(sp, cx, sm);
-  else stream_march<NT, false>(sp, cx, sm);
+  const StreamCtx cx = stream_ctx(sp, (int)blockIdx.x, blockIdx.z);
+#ifdef RN_STREAM_TRACE
+  const unsigned bid = blockIdx.x;
+  if (threadIdx.x == 0 && bid < 8192) {
+    unsigned smid; unsigned long long t;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[4 * bid] = smid; g_trace[4 * bid + 1] = t; g_trace[4 * bid + 3] = !cx.col_lean;
+  }
+#endif
+  stream_march<NT>(sp, cx, sm);
+#ifdef RN_STREAM_TRACE
+  if (threadIdx.x == 0 && bid < 8192) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[4 * bid + 2] = t;
+  }
+#endif
 }
 
 template <int NT, int MINB>
@@ -109,6 +161,13 @@ cudaError_t launch_stage(const StageParams& sp, dim3 grid, cudaStream_t stream)
 }
 
 }  // namespace
+
+#ifdef RN_STREAM_TRACE
+extern "C" int rn_debug_trace(unsigned long long* host, int n)
+{
+  return (int)cudaMemcpyFromSymbol(host, g_trace, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 
 size_t fused_scratch_bytes(int depth, int nfields) { return chain_scratch_bytes(depth, nfields); }
 

@@ -26,6 +26,9 @@ constexpr int kMaxLaunches = 2 * kMaxStages;
 #endif
 constexpr int kStreamThreads = RN_STREAM_THREADS;      // threads (= cell columns incl. 3 halo / loader columns) of a streaming CTA
 constexpr int kStreamMinBlocks = RN_STREAM_MINBLOCKS;  // resident CTAs per SM the kernel is compiled for
+#ifndef RN_STREAM_UNROLL
+#define RN_STREAM_UNROLL 4   // steps per trip of the streaming march (4: ring slots are immediates; 1: rolled loop)
+#endif
 #ifndef RN_STREAM_LEVELS
 #define RN_STREAM_LEVELS 2
 #endif
@@ -33,6 +36,7 @@ constexpr int kStreamLevels = RN_STREAM_LEVELS;  // the last levels of a field a
 constexpr int kStreamMinDepth = 10;   // ... when the field is at least this deep
 constexpr int kStreamThreadsSmall = 64;   // narrower strips for small levels (more CTAs, fewer warm-up rows per sample)
 constexpr int kStreamMinBlocksSmall = 14;
+constexpr float kStreamEdgeCost = 1.28f;  // duration of a border-strip CTA relative to an interior one with the same rows
 constexpr int kStreamSmallCols = 1536;    // levels with fewer cell columns than this use the small configuration
 constexpr int kTile = 64;  // output tile edge of every stage
 
@@ -227,19 +231,36 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
       const int ctas_target = 148 * (cols < kStreamSmallCols ? kStreamMinBlocksSmall : kStreamMinBlocks);
       const int strips = (cols + (sl.nt - 3) - 1) / (sl.nt - 3);
       st.strip_cols = (cols + strips - 1) / strips;
-      // a segment costs 2 warm-up steps, but small levels are latency-bound: filling every CTA slot wins
-      // (measured: 1025 -> 2049 level 40 us with 8-row segments, 52 us with 24-row segments)
-      int nseg = ctas_target / (strips * (nfields > 0 ? nfields : 1));
-      if (nseg > rows / 8) nseg = rows / 8;
-      if (nseg < 1) nseg = 1;
-      st.seg_rows = (rows + nseg - 1) / nseg;
+      st.nstrips = (cols + st.strip_cols - 1) / st.strip_cols;
+      // strips on a column border (same rule as StreamCtx::col_lean)
+      st.edge_first = st.b_lo < 1 || (st.nstrips == 1 && (st.b_hi > n - 1 || st.close_j));
+      st.edge_last = st.nstrips > 1 && (st.b_hi > n - 1 || st.close_j);
+      const int ne = st.edge_first + st.edge_last, ni = st.nstrips - ne;
+      // One wave: about ctas_target CTAs of equal duration.  A segment costs 2 warm-up steps, but small levels are
+      // latency-bound: filling every CTA slot wins (measured: 1025 -> 2049 level 40 us with 8-row segments, 52 us
+      // with 24-row segments).  A border-strip CTA takes kStreamEdgeCost times as long per row (measured), so it
+      // gets that much fewer rows.
+      const int per_field = ctas_target / (nfields > 0 ? nfields : 1);
+      // smallest interior segment length r (>= 8 rows) whose CTA count fits; border strips get r / kStreamEdgeCost rows
+      int r = 8 < rows ? 8 : rows, re = r;
+      for (;; r++) {
+        const int cnt_i = ni * ((rows + r - 1) / r);
+        re = (int)((float)r / kStreamEdgeCost + 0.5f);
+        re = re < 8 ? (8 < rows ? 8 : rows) : re;
+        while (re < r && cnt_i + ne * ((rows + re - 1) / re) > per_field) re++;
+        if (r >= rows || cnt_i + ne * ((rows + re - 1) / re) <= per_field) break;
+      }
+      st.seg_rows = r;
+      st.nseg = (rows + r - 1) / r;
+      st.seg_rows_edge = re;
+      st.nseg_edge = (rows + re - 1) / re;
       st.seed = seed; st.seeds = seeds; st.law = law;
       st.lev = sp.lev[0];
       st.jn = jump_of((uint64_t)st.lev.n);
       st.jn1 = jump_of((uint64_t)st.lev.n + 1);
       st.volcano = sp.volcano; st.volcano_gain = sp.volcano_gain;
-      sl.gx = (unsigned)((cols + st.strip_cols - 1) / st.strip_cols);
-      sl.gy = (unsigned)((rows + st.seg_rows - 1) / st.seg_rows);
+      sl.gx = (unsigned)stream_grid_size(st);
+      sl.gy = 1;
       gin = sp.gout;
       gin_pitch = sp.gout_pitch;
       gin_stride = sp.gout_field_stride;

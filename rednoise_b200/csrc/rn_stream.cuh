@@ -40,8 +40,14 @@ struct StreamParams {
   int a_lo, a_hi;  // cell rows [a_lo, a_hi) of the streamed region (a_hi <= n); close_i: output row W as well
   int b_lo, b_hi;  // cell columns; close_j: output column W as well
   int close_i, close_j;
-  int seg_rows;    // cell rows per CTA (blockIdx.y)
-  int strip_cols;  // cell columns per CTA (blockIdx.x), <= NT-3
+  // Decomposition: blockIdx.x enumerates (strip, segment) pairs, the strips on a lattice column border first.  Those CTAs
+  // run the EDGE instantiation for every step, which is slower per step, so their strips are cut into more, shorter
+  // segments: all CTAs of the (single-wave) launch then take about the same time.
+  int strip_cols;     // cell columns per strip, <= NT-3
+  int nstrips;
+  int edge_first, edge_last;  // strip 0 / strip nstrips-1 touches a column border
+  int seg_rows, nseg;            // interior strips: cell rows per segment, segments
+  int seg_rows_edge, nseg_edge;  // border strips
   uint32_t seed;
   const uint32_t* seeds;
   Law law;
@@ -55,6 +61,8 @@ struct StreamParams {
 struct StreamThread {
   uint32_t sS, sD1, sD2;  // LCG states whose extraction is the draw of this column's next S / loop-1 / loop-2 call
   E4 pre;                 // prefetched lattice point of row u+2 in this thread's column
+  const E4* pre_src;      // where the next prefetch reads (advances one lattice row per step)
+  E4* out_dst;            // output row 2a, column out_j of the next cell row to be stored (advances two rows per store)
   float sg0, sg1;         // shade of corners K(u,c) / K(u-1,c) after generateSquare's scatter (carried from step to step)
   // copy-out: this thread stores the output columns out_j and out_j + NT (relative to 2*B0) of every finished row
   int out_j;
@@ -71,6 +79,11 @@ struct StreamCtx {
   const E4* gin;
   E4* gout;
   int far;      // every sample of this CTA lies outside the volcano's crater (d >= minRad)
+  // Steps [lean_lo, lean_hi] touch no lattice row border (every row they read or write exists), so warps whose columns
+  // touch no column border run them in the lean instantiation; all other (warp, step) pairs run the EDGE one.
+  int lean_lo, lean_hi;
+  int col_lean;  // no thread column of the CTA touches a column border
+  int ubase;     // ring rows are indexed by u - ubase (the first lean step has ring phase 0)
 };
 
 // crater test for a CTA: index distance of the nearest sample of its box from the volcano
@@ -82,27 +95,56 @@ RN_HD int stream_box_is_far(int i_lo, int i_hi, int j_lo, int j_hi, int W)
   return dmin > 0.0205f;
 }
 
-RN_HD StreamCtx stream_ctx(const StreamParams& sp, int bx, int by, unsigned f)
+RN_HD int stream_grid_size(const StreamParams& sp)
+{
+  const int ne = sp.edge_first + sp.edge_last;
+  return ne * sp.nseg_edge + (sp.nstrips - ne) * sp.nseg;
+}
+
+// id: blockIdx.x in [0, stream_grid_size)
+RN_HD StreamCtx stream_ctx(const StreamParams& sp, int id, unsigned f)
 {
   StreamCtx cx;
-  cx.B0 = sp.b_lo + bx * sp.strip_cols;
+  const int ne = sp.edge_first + sp.edge_last;
+  int strip, seg, rows;
+  if (id < ne * sp.nseg_edge) {  // border strips: consecutive ids alternate between the two
+    seg = ne == 2 ? id >> 1 : id;
+    strip = (ne == 2 ? (id & 1) : sp.edge_last) ? sp.nstrips - 1 : 0;
+    if (ne == 1 && sp.edge_first) strip = 0;
+    rows = sp.seg_rows_edge;
+  } else {
+    const int k = id - ne * sp.nseg_edge, ni = sp.nstrips - ne;
+    seg = k / ni;
+    strip = sp.edge_first + (k - seg * ni);
+    rows = sp.seg_rows;
+  }
+  cx.B0 = sp.b_lo + strip * sp.strip_cols;
   cx.CW = imin_(sp.strip_cols, sp.b_hi - cx.B0);
   cx.CWe = cx.CW + ((sp.close_j && cx.B0 + cx.CW == sp.b_hi) ? 1 : 0);
-  cx.a0 = sp.a_lo + by * sp.seg_rows;
-  cx.a1 = imin_(cx.a0 + sp.seg_rows, sp.a_hi);
+  cx.a0 = sp.a_lo + seg * rows;
+  cx.a1 = imin_(cx.a0 + rows, sp.a_hi);
   cx.a1e = cx.a1 + ((sp.close_i && cx.a1 == sp.a_hi) ? 1 : 0);
   cx.seed = sp.seeds ? sp.seeds[f] : sp.seed;
   cx.gin = sp.gin + (size_t)f * sp.gin_field_stride;
   cx.gout = sp.gout + (size_t)f * sp.gout_field_stride;
   cx.far = stream_box_is_far(2 * cx.a0, 2 * cx.a1e - 1, 2 * cx.B0, 2 * (cx.B0 + cx.CWe) - 1, 1 << sp.dout);
+  const int n = sp.lev.n;
+  cx.col_lean = !(cx.B0 < 1 || cx.B0 + cx.CW > n - 1 || cx.CWe != cx.CW);
+  // step u reads lattice rows u-1 .. u+2 (the last step of a CTA does not prefetch) and cell rows u-2 .. u
+  cx.lean_lo = imax_(cx.a0 - 1, 1);
+  cx.lean_hi = cx.a1e <= n - 1 ? cx.a1e : n - 2;
+  cx.ubase = cx.lean_lo <= cx.lean_hi ? cx.lean_lo : cx.a0 - 1;
   return cx;
 }
-// A CTA whose cells, their neighbours and lattice points all exist can run the lean instantiation.
-RN_HD bool stream_is_edge(const StreamParams& sp, const StreamCtx& cx)
+// A warp all of whose thread columns have existing cells, neighbours and lattice points can run the lean instantiation
+// (c: any thread of the warp).
+RN_HD bool stream_warp_is_lean(const StreamParams& sp, const StreamCtx& cx, int c)
 {
-  const int n = sp.lev.n;
-  return cx.B0 < 1 || cx.B0 + cx.CW > n - 1 || cx.a0 < 2 || cx.a1 > n - 1 || cx.CWe != cx.CW || cx.a1e != cx.a1;
+  // (a per-warp rule -- lean warps beside the border warp of an edge strip -- was measured slower: 107 vs 97 us per CTA)
+  (void)sp; (void)c;
+  return cx.col_lean;
 }
+RN_HD bool stream_step_is_lean(const StreamCtx& cx, int u) { return u >= cx.lean_lo && u <= cx.lean_hi; }
 
 template <int NT>
 struct StreamGeo {
@@ -128,7 +170,13 @@ struct Stream {
   using G = StreamGeo<NT>;
   static RN_HD E4* e4(float* sm, int row_off, int c) { return reinterpret_cast<E4*>(sm) + row_off + (c + 1); }
   static RN_HD float* f32(float* sm, int row_off, int c) { return sm + row_off + (c + 1); }
-  static RN_HD int mod(int u, int m) { return u & (m - 1); }  // ring sizes are powers of two
+  // Ring rows are indexed by the step number t relative to the CTA's first step (ring sizes are powers of two).  The
+  // unrolled march passes PH = t & 3 as a template argument, which turns every ring offset into an immediate;
+  // PH < 0 computes it from t at run time.
+  static RN_HD int mod(int t, int m) { return t & (m - 1); }
+  template <int PH>
+  static RN_HD int ring(int t, int k, int m) { return (PH >= 0 ? PH + k : t + k) & (m - 1); }
+  static RN_HD int step_of(const StreamCtx& cx, int u) { return u - cx.ubase; }
 
   // threads with a cell; the lean instantiation lets the few surplus lanes compute on garbage (all in-bounds, never stored)
   static RN_HD bool active(const StreamCtx& cx, int c) { return !EDGE || c <= cx.CW + 1; }
@@ -146,7 +194,7 @@ struct Stream {
   }
   static RN_HD void load_row_now(const StreamParams& sp, const StreamCtx& cx, float* sm, int r, int c)
   {
-    if (lattice_exists(sp, cx, r, c)) *e4(sm, G::KROW + mod(r, 4) * G::P, c) = lattice(sp, cx, r, c);
+    if (lattice_exists(sp, cx, r, c)) *e4(sm, G::KROW + mod(step_of(cx, r), 4) * G::P, c) = lattice(sp, cx, r, c);
   }
 
   // ------------------------------------------------------------------ start-up ----
@@ -175,6 +223,9 @@ struct Stream {
         th.out_fy2[pass] = fy * fy;
       }
     }
+    // (both pointers may start outside their grids; they are only dereferenced where the row / column exists)
+    th.pre_src = cx.gin + ((ptrdiff_t)(u0 + 2) * (ptrdiff_t)sp.gin_pitch + (ptrdiff_t)(cx.B0 - 1 + c));
+    th.out_dst = cx.gout + ((ptrdiff_t)(2 * cx.a0 - sp.win_i0) * (ptrdiff_t)sp.gout_pitch + (ptrdiff_t)(2 * cx.B0 - sp.win_j0 + th.out_j));
     if (loader(cx, c)) {
       load_row_now(sp, cx, sm, u0, c);
       load_row_now(sp, cx, sm, u0 + 1, c);
@@ -183,7 +234,7 @@ struct Stream {
 
   // ------------------------------------------------------------------ interval 1 ----
   template <bool VOLCANO, bool FAR>
-  static RN_HD void store_rows_t(const StreamParams& sp, const StreamCtx& cx, float* sm, const StreamThread& th, int a)
+  static RN_HD void store_rows_t(const StreamParams& sp, const StreamCtx& cx, float* sm, StreamThread& th, int a, int m1slot)
   {
     // output rows 2a (corners K(a,.) / mids M1(a,.)) and 2a+1 (mids M2(a,.) / centres C(a,.))
     const int Wout = 1 << sp.dout;
@@ -192,40 +243,43 @@ struct Stream {
     const E4* smE = reinterpret_cast<const E4*>(sm);
     const bool odd = th.out_j & 1;
     const int cc0 = (th.out_j >> 1) + 2, cc1 = cc0 + NT / 2;  // slot of the owning cell inside a class row (its c + 1)
-    const uint32_t wj0 = (uint32_t)(2 * cx.B0 - sp.win_j0 + th.out_j), wj1 = wj0 + NT;
     const bool ok0 = th.out_ok & 1, ok1 = th.out_ok & 2;
-    const uint32_t pitch = (uint32_t)sp.gout_pitch;
+    E4* dst = th.out_dst;
+    th.out_dst = dst + 2 * sp.gout_pitch;
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       const int gi = 2 * a + r;
       const int wi = gi - sp.win_i0;
       if ((unsigned)wi < (unsigned)sp.win_ni && gi <= Wout) {  // uniform
-        const uint32_t rowoff = (uint32_t)wi * pitch;
+        E4* row = r == 0 ? dst : dst + sp.gout_pitch;
         const float fx = (float)(gi - Wout / 2);
         const float fx2 = fx * fx;
-        const int src = r == 0 ? (odd ? G::M1ROW + (a & 1) * G::P : G::OUTK) : (odd ? G::OUTC : G::M2ROW);
+        const int src = r == 0 ? (odd ? G::M1ROW + m1slot * G::P : G::OUTK) : (odd ? G::OUTC : G::M2ROW);
         if (ok0) {
           E4 e = smE[src + cc0];
           if (VOLCANO) e.y = e.y + volcano_height_r2<FAR>(fx2 + th.out_fy2[0], inv_w, sp.volcano_gain, gain_w);
-          cx.gout[rowoff + wj0] = e;
+          row[0] = e;
         }
         if (ok1) {
           E4 e = smE[src + cc1];
           if (VOLCANO) e.y = e.y + volcano_height_r2<FAR>(fx2 + th.out_fy2[1], inv_w, sp.volcano_gain, gain_w);
-          cx.gout[rowoff + wj1] = e;
+          row[NT] = e;
         }
       }
     }
   }
-  static RN_HD void store_rows(const StreamParams& sp, const StreamCtx& cx, float* sm, const StreamThread& th, int a)
+  // m1slot: ring slot of the M1 row of cell row a
+  static RN_HD void store_rows(const StreamParams& sp, const StreamCtx& cx, float* sm, StreamThread& th, int a, int m1slot)
   {
-    if (!sp.volcano) store_rows_t<false, true>(sp, cx, sm, th, a);
-    else if (cx.far) store_rows_t<true, true>(sp, cx, sm, th, a);
-    else store_rows_t<true, false>(sp, cx, sm, th, a);
+    if (!sp.volcano) store_rows_t<false, true>(sp, cx, sm, th, a, m1slot);
+    else if (cx.far) store_rows_t<true, true>(sp, cx, sm, th, a, m1slot);
+    else store_rows_t<true, false>(sp, cx, sm, th, a, m1slot);
   }
 
+  template <int PH = -1>
   static RN_HD void interval1(const StreamParams& sp, const StreamCtx& cx, float* sm, StreamThread& th, int u, int c)
   {
+    const int t = step_of(cx, u);
     if (active(cx, c)) {
       const int n = sp.lev.n;
       const int bg = cx.B0 - 1 + c;
@@ -235,25 +289,28 @@ struct Stream {
       th.sS = jump_apply(sp.jn, th.sS);
       if (ex) {
         // S(u): averageSquare (Terrain.cpp:216-222) + generateSquare (:224-258)
-        const int r0 = G::KROW + mod(u, 4) * G::P, r1 = G::KROW + mod(u + 1, 4) * G::P;
+        const int r0 = G::KROW + ring<PH>(t, 0, 4) * G::P, r1 = G::KROW + ring<PH>(t, 1, 4) * G::P;
         const E4 k00 = *e4(sm, r0, c), k01 = *e4(sm, r0, c + 1), k10 = *e4(sm, r1, c), k11 = *e4(sm, r1, c + 1);
         const V3 avg = vmul(vadd(vadd(vadd(pos4(k00), pos4(k10)), pos4(k01)), pos4(k11)), 0.25f);
         const float sh = (k00.w + k10.w + k01.w + k11.w) * 0.25f;
         const Displaced dp = displace<true>(sp.law, avg, vsub(pos4(k11), pos4(k00)), vsub(pos4(k10), pos4(k01)), sp.lev.blahS, draw);
-        *e4(sm, G::CROW + mod(u, 2) * G::P, c) = e4_of(dp.pos, sh + shade_gain(sp.law, dp.offset));
+        *e4(sm, G::CROW + ring<PH>(t, 0, 2) * G::P, c) = e4_of(dp.pos, sh + shade_gain(sp.law, dp.offset));
         loss = shade_loss(sp.law, dp.offset);
       }
-      *f32(sm, G::TS + mod(u, 4) * G::P, c) = loss;
+      *f32(sm, G::TS + ring<PH>(t, 0, 4) * G::P, c) = loss;
     }
     // the rows G(u-1) finished: cell row u-2
-    if (u - 2 >= cx.a0 && u - 2 < cx.a1e) store_rows(sp, cx, sm, th, u - 2);
+    if (u - 2 >= cx.a0 && u - 2 < cx.a1e) store_rows(sp, cx, sm, th, u - 2, ring<PH>(t, -2, 2));
   }
 
   // ------------------------------------------------------------------ interval 2 ----
+  template <int PH = -1>
   static RN_HD void interval2(const StreamParams& sp, const StreamCtx& cx, float* sm, StreamThread& th, int u, int c)
   {
+    const int t = step_of(cx, u);
     // prefetch lattice row u+2 (needed by S(u+1) and D(u+2)); it lands in shared memory in interval 3
-    if (loader(cx, c) && u + 1 <= cx.a1e && lattice_exists(sp, cx, u + 2, c)) th.pre = lattice(sp, cx, u + 2, c);
+    if (loader(cx, c) && u + 1 <= cx.a1e && lattice_exists(sp, cx, u + 2, c)) th.pre = *th.pre_src;
+    th.pre_src += sp.gin_pitch;
     if (!active(cx, c)) return;
     const int n = sp.lev.n;
     const int bg = cx.B0 - 1 + c;
@@ -268,16 +325,16 @@ struct Stream {
     float loss1 = 0.0f, loss2 = 0.0f;
     // corner shades as generateSquare left them (Terrain.cpp:252-255): minus the scatter of the 4 surrounding
     // centres.  sg(u,c) is computed here once and carried to the next step (as sg(u-1,c)) and to interval 3.
-    const int ts1 = G::TS + mod(u - 1, 4) * G::P, ts0 = G::TS + mod(u, 4) * G::P;
-    const int kr = G::KROW + mod(u, 4) * G::P;
+    const int ts1 = G::TS + ring<PH>(t, -1, 4) * G::P, ts0 = G::TS + ring<PH>(t, 0, 4) * G::P;
+    const int kr = G::KROW + ring<PH>(t, 0, 4) * G::P;
     const float t10 = *f32(sm, ts1, c), t00 = *f32(sm, ts0, c);
     E4 k00 = *e4(sm, kr, c);  // K(u, c)
     k00.w = (((k00.w - *f32(sm, ts1, c - 1)) - t10) - *f32(sm, ts0, c - 1)) - t00;
     th.sg1 = th.sg0;   // sg(u-1, c)
     th.sg0 = k00.w;    // sg(u, c)
     if (v1 || v2) {
-      const int krm = G::KROW + mod(u - 1, 4) * G::P;
-      const int cr = G::CROW + mod(u, 2) * G::P, crm = G::CROW + mod(u - 1, 2) * G::P;
+      const int krm = G::KROW + ring<PH>(t, -1, 4) * G::P;
+      const int cr = G::CROW + ring<PH>(t, 0, 2) * G::P, crm = G::CROW + ring<PH>(t, -1, 2) * G::P;
       if (v1) {  // loop 1: M1(u, c) at output (2u, 2c'+1): x neighbours C(u-1,c), C(u,c); y neighbours K(u,c), K(u,c+1)
         E4 k01 = *e4(sm, kr, c + 1);
         k01.w = (((k01.w - t10) - *f32(sm, ts1, c + 1)) - t00) - *f32(sm, ts0, c + 1);
@@ -289,37 +346,37 @@ struct Stream {
         } else {
           m = mid_interior(sp.law, *e4(sm, crm, c), *e4(sm, cr, c), k00, k01, sp.lev.blahD, draw1, &loss1);
         }
-        *e4(sm, G::M1ROW + mod(u, 2) * G::P, c) = m;
+        *e4(sm, G::M1ROW + ring<PH>(t, 0, 2) * G::P, c) = m;
       }
       if (v2) {  // loop 2: M2(u-1, c) at output (2u-1, 2c'): x neighbours K(u-1,c), K(u,c); y neighbours C(u-1,c-1), C(u-1,c)
         E4 km = *e4(sm, krm, c);  // K(u-1, c)
         km.w = th.sg1;
         E4 m;
-        if (EDGE && (bg == 0 || bg == n)) {
-          const E4 dummy = k00;
-          m = mid_border(sp.law, km, k00, bg == 0 ? dummy : *e4(sm, crm, c - 1), bg == n ? dummy : *e4(sm, crm, c), false, false, bg == 0, bg == n,
-                         sp.lev.blahD, draw2, &loss2);
+        if (EDGE) {  // column borders by selects: no divergence inside the border warp
+          m = mid_select_y(sp.law, km, k00, *e4(sm, crm, c - 1), *e4(sm, crm, c), bg == 0, bg == n, sp.lev.blahD, draw2, &loss2);
         } else {
           m = mid_interior(sp.law, km, k00, *e4(sm, crm, c - 1), *e4(sm, crm, c), sp.lev.blahD, draw2, &loss2);
         }
         *e4(sm, G::M2ROW, c) = m;
       }
     }
-    *f32(sm, G::TD1 + mod(u, 2) * G::P, c) = loss1;
-    *f32(sm, G::TD2 + mod(u - 1, 2) * G::P, c) = loss2;
+    *f32(sm, G::TD1 + ring<PH>(t, 0, 2) * G::P, c) = loss1;
+    *f32(sm, G::TD2 + ring<PH>(t, -1, 2) * G::P, c) = loss2;
   }
 
   // ------------------------------------------------------------------ interval 3 ----
+  template <int PH = -1>
   static RN_HD void interval3(const StreamParams& sp, const StreamCtx& cx, float* sm, StreamThread& th, int u, int c)
   {
+    const int t = step_of(cx, u);
     if (active(cx, c)) {
       const int n = sp.lev.n;
       const int bg = cx.B0 - 1 + c;
-      const int td1m = G::TD1 + mod(u - 1, 2) * G::P, td10 = G::TD1 + mod(u, 2) * G::P;
-      const int td2mm = G::TD2 + mod(u - 2, 2) * G::P, td2m = G::TD2 + mod(u - 1, 2) * G::P;
+      const int td1m = G::TD1 + ring<PH>(t, -1, 2) * G::P, td10 = G::TD1 + ring<PH>(t, 0, 2) * G::P;
+      const int td2mm = G::TD2 + ring<PH>(t, -2, 2) * G::P, td2m = G::TD2 + ring<PH>(t, -1, 2) * G::P;
       if (!EDGE || (u - 1 >= 0 && u - 1 <= n && bg >= 0 && bg <= n)) {
         // corner K(u-1, c): generateSquare's scatter (carried sg), then loop 1 (same row), loop 2 (same column)
-        E4 k = *e4(sm, G::KROW + mod(u - 1, 4) * G::P, c);
+        E4 k = *e4(sm, G::KROW + ring<PH>(t, -1, 4) * G::P, c);
         float sh = th.sg1;
         sh -= *f32(sm, td1m, c - 1);
         sh -= *f32(sm, td1m, c);
@@ -330,7 +387,7 @@ struct Stream {
       }
       if (!EDGE || (u - 1 >= 0 && u - 1 < n && bg >= 0 && bg < n)) {
         // centre C(u-1, c): loop-1 mids above and below, loop-2 mids left and right
-        E4 ce = *e4(sm, G::CROW + mod(u - 1, 2) * G::P, c);
+        E4 ce = *e4(sm, G::CROW + ring<PH>(t, -1, 2) * G::P, c);
         float shc = ce.w;
         shc -= *f32(sm, td1m, c);
         shc -= *f32(sm, td10, c);
@@ -341,7 +398,7 @@ struct Stream {
       }
     }
     // the row prefetched in interval 2
-    if (loader(cx, c) && u + 1 <= cx.a1e && lattice_exists(sp, cx, u + 2, c)) *e4(sm, G::KROW + mod(u + 2, 4) * G::P, c) = th.pre;
+    if (loader(cx, c) && u + 1 <= cx.a1e && lattice_exists(sp, cx, u + 2, c)) *e4(sm, G::KROW + ring<PH>(t, 2, 4) * G::P, c) = th.pre;
   }
 };
 

@@ -278,6 +278,28 @@ RN_HD E4 mid_border(const Law& law, E4 ex0, E4 ex1, E4 ey0, E4 ey1, bool sx0, bo
   return e4_of(dp.pos, sh);
 }
 
+// mid_interior, or mid_border for a missing y neighbour (sy0 / sy1), chosen by selects instead of a branch: the one
+// thread of a warp that sits on a lattice column border then shares its warp's instruction stream.
+RN_HD E4 mid_select_y(const Law& law, const E4& ex0, const E4& ex1, E4 ey0, E4 ey1, bool sy0, bool sy1, float blah, uint32_t draw,
+                      float* loss_out)
+{
+  const bool yb = sy0 || sy1;
+  if (sy0) ey0.w = 1.0f;
+  if (sy1) ey1.w = 1.0f;
+  const V3 sx = vadd(pos4(ex0), pos4(ex1));
+  const V3 avg_i = vmul(vadd(vadd(sx, pos4(ey0)), pos4(ey1)), 0.25f);
+  const V3 avg_b = vmul(sx, 0.5f);
+  const V3 avg = yb ? avg_b : avg_i;
+  float sh = (ex0.w + ex1.w + ey0.w + ey1.w) * 0.25f;
+  const V3 py0 = sy0 ? avg : pos4(ey0), py1 = sy1 ? avg : pos4(ey1);
+  const Displaced dp = displace<true>(law, avg, vsub(pos4(ex0), pos4(ex1)), vsub(py1, py0), blah, draw);
+  const float loss = shade_loss(law, dp.offset);
+  sh += shade_gain(law, dp.offset);
+  if (yb) sh -= loss;  // the scatter onto the clamped index lands on the midpoint itself
+  *loss_out = loss;
+  return e4_of(dp.pos, sh);
+}
+
 RN_HD E4 mid_interior(const Law& law, const E4& ex0, const E4& ex1, const E4& ey0, const E4& ey1, float blah, uint32_t draw,
                              float* loss_out)
 {

@@ -69,18 +69,51 @@ int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
   return bad;
 }
 
-template <int SNT, bool EDGE>
-void stream_march_host(const StreamParams& sp, const StreamCtx& cx, float* sm, std::vector<StreamThread>& th)
+// One barrier interval for every thread, each in the instantiation the kernel's warp would run at this step.
+template <int SNT, int K, int PH>
+void stream_interval_thread(const StreamParams& sp, const StreamCtx& cx, float* sm, StreamThread& th, int u, int c, bool lean)
 {
-  using S = Stream<SNT, EDGE>;
+  if (lean) {
+    using S = Stream<SNT, false>;
+    if (K == 1) S::template interval1<PH>(sp, cx, sm, th, u, c);
+    if (K == 2) S::template interval2<PH>(sp, cx, sm, th, u, c);
+    if (K == 3) S::template interval3<PH>(sp, cx, sm, th, u, c);
+  } else {
+    using S = Stream<SNT, true>;
+    if (K == 1) S::template interval1<-1>(sp, cx, sm, th, u, c);
+    if (K == 2) S::template interval2<-1>(sp, cx, sm, th, u, c);
+    if (K == 3) S::template interval3<-1>(sp, cx, sm, th, u, c);
+  }
+}
+
+template <int SNT, int K>
+void stream_interval_host(const StreamParams& sp, const StreamCtx& cx, float* sm, std::vector<StreamThread>& th, int u, bool force_edge)
+{
+  const int ph = (u - cx.ubase) & 3;
+  for (int q = 0; q < SNT; q++) {
+    const int c = g_reverse ? SNT - 1 - q : q;
+    const bool lean = !force_edge && stream_warp_is_lean(sp, cx, c) && stream_step_is_lean(cx, u);
+    switch (ph) {  // the lean instantiation is replayed in its unrolled form (ring slots as template constants), like the kernel
+      case 0: stream_interval_thread<SNT, K, 0>(sp, cx, sm, th[c], u, c, lean); break;
+      case 1: stream_interval_thread<SNT, K, 1>(sp, cx, sm, th[c], u, c, lean); break;
+      case 2: stream_interval_thread<SNT, K, 2>(sp, cx, sm, th[c], u, c, lean); break;
+      default: stream_interval_thread<SNT, K, 3>(sp, cx, sm, th[c], u, c, lean); break;
+    }
+  }
+}
+
+template <int SNT>
+void stream_march_host(const StreamParams& sp, const StreamCtx& cx, float* sm, std::vector<StreamThread>& th, bool force_edge)
+{
+  using S = Stream<SNT, true>;
 #define RN_ALL_THREADS(call) for (int q = 0; q < SNT; q++) { const int c = g_reverse ? SNT - 1 - q : q; call; }
   RN_ALL_THREADS(S::init(sp, cx, sm, th[c], c))
   for (int u = cx.a0 - 1; u <= cx.a1e; u++) {
-    RN_ALL_THREADS(S::interval1(sp, cx, sm, th[c], u, c))
-    RN_ALL_THREADS(S::interval2(sp, cx, sm, th[c], u, c))
-    RN_ALL_THREADS(S::interval3(sp, cx, sm, th[c], u, c))
+    stream_interval_host<SNT, 1>(sp, cx, sm, th, u, force_edge);
+    stream_interval_host<SNT, 2>(sp, cx, sm, th, u, force_edge);
+    stream_interval_host<SNT, 3>(sp, cx, sm, th, u, force_edge);
   }
-  RN_ALL_THREADS(S::store_rows(sp, cx, sm, th[c], cx.a1e - 1))
+  RN_ALL_THREADS(S::store_rows(sp, cx, sm, th[c], cx.a1e - 1, S::mod(S::step_of(cx, cx.a1e - 1), 2)))
 #undef RN_ALL_THREADS
 }
 
@@ -104,10 +137,9 @@ int run_stream_t(const StageLaunch& sl, int nfields, const uint32_t* seeds, int 
         for (size_t i = 0; i < (size_t)G::WORDS + 2 * GUARD; i++) base[i] = poison ? nanv : 0.0f;
         StreamParams sp = sp0;
         if (seeds) { sp.seeds = nullptr; sp.seed = seeds[f]; }
-        const StreamCtx cx = stream_ctx(sp, (int)bx, (int)by, (unsigned)f);
+        const StreamCtx cx = stream_ctx(sp, (int)bx, (unsigned)f);
         memset(th.data(), poison ? 0xff : 0, sizeof(StreamThread) * th.size());
-        if (force_edge || stream_is_edge(sp, cx)) stream_march_host<SNT, true>(sp, cx, sm, th);
-        else stream_march_host<SNT, false>(sp, cx, sm, th);
+        stream_march_host<SNT>(sp, cx, sm, th, force_edge != 0);
         if (poison) {
           for (int i = 0; i < GUARD; i++) {
             uint32_t a, b;

@@ -86,6 +86,7 @@ Law law_of(const rn_params* p)
   l.band_hi = 3.0f / p->feature_scale;  // Terrain.cpp:191,235
   l.band_lo = 0.5f / p->feature_scale;
   l.bulgy = p->bulgy_rocks != 0;
+  l.one = 1.0f;
   return l;
 }
 

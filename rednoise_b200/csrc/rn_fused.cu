@@ -80,6 +80,15 @@ __device__ __forceinline__ void stream_march(const StreamParams& sp, const Strea
         if (u + 3 == hi) break;
         u += 4;
       }
+#elif RN_STREAM_UNROLL == 2
+      // two steps per trip: half the code of the four-step form (it no longer fits the 32 KB instruction cache)
+      for (;;) {
+        stream_step<NT, false, 4>(sp, cx, sm, th, u, c);
+        if (u == hi) break;
+        stream_step<NT, false, 5>(sp, cx, sm, th, u + 1, c);
+        if (u + 1 == hi) break;
+        u += 2;
+      }
 #else
       for (; u <= hi; u++) stream_step<NT, false, -1>(sp, cx, sm, th, u, c);
 #endif

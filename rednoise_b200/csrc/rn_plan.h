@@ -22,12 +22,13 @@ constexpr int kMaxLaunches = 2 * kMaxStages;
 #define RN_STREAM_THREADS 128
 #endif
 #ifndef RN_STREAM_MINBLOCKS
-#define RN_STREAM_MINBLOCKS 7
+#define RN_STREAM_MINBLOCKS 8
 #endif
 constexpr int kStreamThreads = RN_STREAM_THREADS;      // threads (= cell columns incl. 3 halo / loader columns) of a streaming CTA
 constexpr int kStreamMinBlocks = RN_STREAM_MINBLOCKS;  // resident CTAs per SM the kernel is compiled for
 #ifndef RN_STREAM_UNROLL
-#define RN_STREAM_UNROLL 4   // steps per trip of the streaming march (4: ring slots are immediates; 1: rolled loop)
+#define RN_STREAM_UNROLL 2   // steps per trip of the streaming march: 2 = rings of two are immediates (measured best: the
+                             // 4-step form, all ring slots immediate, outgrows the instruction cache), 1 = rolled loop
 #endif
 #ifndef RN_STREAM_LEVELS
 #define RN_STREAM_LEVELS 2

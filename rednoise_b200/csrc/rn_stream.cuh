@@ -174,8 +174,14 @@ struct Stream {
   // unrolled march passes PH = t & 3 as a template argument, which turns every ring offset into an immediate;
   // PH < 0 computes it from t at run time.
   static RN_HD int mod(int t, int m) { return t & (m - 1); }
+  // PH = 0..3: t & 3 is known; PH = 4, 5: only the parity t & 1 = PH - 4 is known (two steps per trip: the rings of
+  // two are immediates, the rings of four are computed); PH < 0: nothing is known.
   template <int PH>
-  static RN_HD int ring(int t, int k, int m) { return (PH >= 0 ? PH + k : t + k) & (m - 1); }
+  static RN_HD int ring(int t, int k, int m)
+  {
+    if (PH >= 4) return m == 2 ? ((PH + k) & 1) : ((t + k) & (m - 1));
+    return (PH >= 0 ? PH + k : t + k) & (m - 1);
+  }
   static RN_HD int step_of(const StreamCtx& cx, int u) { return u - cx.ubase; }
 
   // threads with a cell; the lean instantiation lets the few surplus lanes compute on garbage (all in-bounds, never stored)
@@ -255,14 +261,23 @@ struct Stream {
         const float fx = (float)(gi - Wout / 2);
         const float fx2 = fx * fx;
         const int src = r == 0 ? (odd ? G::M1ROW + m1slot * G::P : G::OUTK) : (odd ? G::OUTC : G::M2ROW);
+        float h0 = 0.0f, h1 = 0.0f;
+        if (VOLCANO && FAR) {  // both columns of the thread at once (packed pair)
+          const F2 h = f2mul(rcp_rn_normal2(sqrt_rn_normal2(f2add(f2s(fx2), f2(th.out_fy2[0], th.out_fy2[1])))), f2s(gain_w));
+          h0 = f2lo(h);
+          h1 = f2hi(h);
+        } else if (VOLCANO) {
+          h0 = volcano_height_r2<false>(fx2 + th.out_fy2[0], inv_w, sp.volcano_gain, gain_w);
+          h1 = volcano_height_r2<false>(fx2 + th.out_fy2[1], inv_w, sp.volcano_gain, gain_w);
+        }
         if (ok0) {
           E4 e = smE[src + cc0];
-          if (VOLCANO) e.y = e.y + volcano_height_r2<FAR>(fx2 + th.out_fy2[0], inv_w, sp.volcano_gain, gain_w);
+          if (VOLCANO) e.y = e.y + h0;
           row[0] = e;
         }
         if (ok1) {
           E4 e = smE[src + cc1];
-          if (VOLCANO) e.y = e.y + volcano_height_r2<FAR>(fx2 + th.out_fy2[1], inv_w, sp.volcano_gain, gain_w);
+          if (VOLCANO) e.y = e.y + h1;
           row[NT] = e;
         }
       }
@@ -291,8 +306,9 @@ struct Stream {
         // S(u): averageSquare (Terrain.cpp:216-222) + generateSquare (:224-258)
         const int r0 = G::KROW + ring<PH>(t, 0, 4) * G::P, r1 = G::KROW + ring<PH>(t, 1, 4) * G::P;
         const E4 k00 = *e4(sm, r0, c), k01 = *e4(sm, r0, c + 1), k10 = *e4(sm, r1, c), k11 = *e4(sm, r1, c + 1);
-        const V3 avg = vmul(vadd(vadd(vadd(pos4(k00), pos4(k10)), pos4(k01)), pos4(k11)), 0.25f);
-        const float sh = (k00.w + k10.w + k01.w + k11.w) * 0.25f;
+        const E4 a4 = avg4_packed(k00, k10, k01, k11);
+        const V3 avg = pos4(a4);
+        const float sh = a4.w;
         const Displaced dp = displace<true>(sp.law, avg, vsub(pos4(k11), pos4(k00)), vsub(pos4(k10), pos4(k01)), sp.lev.blahS, draw);
         *e4(sm, G::CROW + ring<PH>(t, 0, 2) * G::P, c) = e4_of(dp.pos, sh + shade_gain(sp.law, dp.offset));
         loss = shade_loss(sp.law, dp.offset);
@@ -332,7 +348,20 @@ struct Stream {
     k00.w = (((k00.w - *f32(sm, ts1, c - 1)) - t10) - *f32(sm, ts0, c - 1)) - t00;
     th.sg1 = th.sg0;   // sg(u-1, c)
     th.sg0 = k00.w;    // sg(u, c)
-    if (v1 || v2) {
+    if (!EDGE) {
+      // both midpoints exist and have all four neighbours: one packed evaluation (rn_tile.cuh mid_interior2)
+      const int krm = G::KROW + ring<PH>(t, -1, 4) * G::P;
+      const int cr = G::CROW + ring<PH>(t, 0, 2) * G::P, crm = G::CROW + ring<PH>(t, -1, 2) * G::P;
+      E4 k01 = *e4(sm, kr, c + 1);
+      k01.w = (((k01.w - t10) - *f32(sm, ts1, c + 1)) - t00) - *f32(sm, ts0, c + 1);
+      E4 km = *e4(sm, krm, c);  // K(u-1, c)
+      km.w = th.sg1;
+      const E4 cm = *e4(sm, crm, c);  // C(u-1, c): x neighbour of M1, y neighbour of M2
+      E4 m1, m2;
+      mid_interior2(sp.law, cm, *e4(sm, cr, c), k00, k01, km, k00, *e4(sm, crm, c - 1), cm, sp.lev.blahD, draw1, draw2, &m1, &m2, &loss1, &loss2);
+      *e4(sm, G::M1ROW + ring<PH>(t, 0, 2) * G::P, c) = m1;
+      *e4(sm, G::M2ROW, c) = m2;
+    } else if (v1 || v2) {
       const int krm = G::KROW + ring<PH>(t, -1, 4) * G::P;
       const int cr = G::CROW + ring<PH>(t, 0, 2) * G::P, crm = G::CROW + ring<PH>(t, -1, 2) * G::P;
       if (v1) {  // loop 1: M1(u, c) at output (2u, 2c'+1): x neighbours C(u-1,c), C(u,c); y neighbours K(u,c), K(u,c+1)

@@ -310,6 +310,40 @@ RN_HD E4 mid_interior(const Law& law, const E4& ex0, const E4& ex1, const E4& ey
   return e4_of(dp.pos, sh + shade_gain(law, dp.offset));
 }
 
+// Two interior midpoints at once (mid_interior twice, bit for bit): the component-wise averages run as packed pairs
+// inside each float4, everything from the cross product on as packed pairs across the two samples.
+RN_HD F2 e4_xy(const E4& e) { return f2(e.x, e.y); }
+RN_HD F2 e4_zw(const E4& e) { return f2(e.z, e.w); }
+// ((a + b) + c) + d) * 0.25 on all four components (positions and shade are averaged in the same order)
+RN_HD E4 avg4_packed(const E4& a, const E4& b, const E4& c, const E4& d)
+{
+  const F2 q = f2s(0.25f);
+  const F2 xy = f2mul(f2add(f2add(f2add(e4_xy(a), e4_xy(b)), e4_xy(c)), e4_xy(d)), q);
+  const F2 zw = f2mul(f2add(f2add(f2add(e4_zw(a), e4_zw(b)), e4_zw(c)), e4_zw(d)), q);
+  return E4{f2lo(xy), f2hi(xy), f2lo(zw), f2hi(zw)};
+}
+RN_HD void mid_interior2(const Law& law, const E4& ax0, const E4& ax1, const E4& ay0, const E4& ay1, const E4& bx0, const E4& bx1,
+                         const E4& by0, const E4& by1, float blah, uint32_t draw_a, uint32_t draw_b, E4* out_a, E4* out_b, float* loss_a,
+                         float* loss_b)
+{
+  const F2 q = f2s(0.25f);
+  // (x, y, z, shade) averages: ((x0 + x1) + y0) + y1) * 0.25 per component
+  const F2 a_xy = f2mul(f2add(f2add(f2add(e4_xy(ax0), e4_xy(ax1)), e4_xy(ay0)), e4_xy(ay1)), q);
+  const F2 a_zw = f2mul(f2add(f2add(f2add(e4_zw(ax0), e4_zw(ax1)), e4_zw(ay0)), e4_zw(ay1)), q);
+  const F2 b_xy = f2mul(f2add(f2add(f2add(e4_xy(bx0), e4_xy(bx1)), e4_xy(by0)), e4_xy(by1)), q);
+  const F2 b_zw = f2mul(f2add(f2add(f2add(e4_zw(bx0), e4_zw(bx1)), e4_zw(by0)), e4_zw(by1)), q);
+  const V3P dir1 = v3p(vsub(pos4(ax0), pos4(ax1)), vsub(pos4(bx0), pos4(bx1)));
+  const V3P dir2 = v3p(vsub(pos4(ay1), pos4(ay0)), vsub(pos4(by1), pos4(by0)));
+  const Displaced2 dp = displace2(law, f2lo(a_xy), f2hi(a_xy), f2lo(b_xy), f2hi(b_xy), dir1, dir2, blah, draw_a, draw_b);
+  const F2 rs = f2s(law.radiosity_strength);
+  const F2 gain = f2mul(dp.offset, rs);
+  const F2 loss = f2mul(f2mul(f2s(0.25f), dp.offset), rs);
+  *loss_a = f2lo(loss);
+  *loss_b = f2hi(loss);
+  *out_a = E4{f2lo(a_xy) + f2lo(dp.shift.x), f2hi(a_xy) + f2lo(dp.shift.y), f2lo(a_zw) + f2lo(dp.shift.z), f2hi(a_zw) + f2lo(gain)};
+  *out_b = E4{f2lo(b_xy) + f2hi(dp.shift.x), f2hi(b_xy) + f2hi(dp.shift.y), f2lo(b_zw) + f2hi(dp.shift.z), f2hi(b_zw) + f2hi(gain)};
+}
+
 
 struct TileCtx {
   int I0, J0;        // output-grid coordinates of the tile origin

@@ -93,11 +93,18 @@ void stream_interval_host(const StreamParams& sp, const StreamCtx& cx, float* sm
   for (int q = 0; q < SNT; q++) {
     const int c = g_reverse ? SNT - 1 - q : q;
     const bool lean = !force_edge && stream_warp_is_lean(sp, cx, c) && stream_step_is_lean(cx, u);
-    switch (ph) {  // the lean instantiation is replayed in its unrolled form (ring slots as template constants), like the kernel
+    // the lean instantiation is replayed in the kernel's unrolled form (ring slots as template constants): the form
+    // RN_STREAM_UNROLL selects, and the other two on alternating cells so that every form stays covered
+    const int form = ((u + c) % 3 == 0) ? RN_STREAM_UNROLL : ((u + c) % 3 == 1 ? 4 : 1);
+    const int sel = form == 4 ? ph : (form == 2 ? 4 + (ph & 1) : -1);
+    switch (sel) {
       case 0: stream_interval_thread<SNT, K, 0>(sp, cx, sm, th[c], u, c, lean); break;
       case 1: stream_interval_thread<SNT, K, 1>(sp, cx, sm, th[c], u, c, lean); break;
       case 2: stream_interval_thread<SNT, K, 2>(sp, cx, sm, th[c], u, c, lean); break;
-      default: stream_interval_thread<SNT, K, 3>(sp, cx, sm, th[c], u, c, lean); break;
+      case 3: stream_interval_thread<SNT, K, 3>(sp, cx, sm, th[c], u, c, lean); break;
+      case 4: stream_interval_thread<SNT, K, 4>(sp, cx, sm, th[c], u, c, lean); break;
+      case 5: stream_interval_thread<SNT, K, 5>(sp, cx, sm, th[c], u, c, lean); break;
+      default: stream_interval_thread<SNT, K, -1>(sp, cx, sm, th[c], u, c, lean); break;
     }
   }
 }
@@ -203,6 +210,7 @@ int replay_terrain2d(const rn_params* p, const rn_window* win, rn_element* dst, 
   law.band_hi = 3.0f / p->feature_scale;
   law.band_lo = 0.5f / p->feature_scale;
   law.bulgy = p->bulgy_rocks != 0;
+  law.one = 1.0f;
   const size_t sbytes = chain_scratch_bytes(p->depth, 1);
   void* scratch = nullptr;
   if (sbytes && posix_memalign(&scratch, 256, sbytes) != 0) return RN_ERR_OOM;

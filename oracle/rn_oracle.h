@@ -48,6 +48,12 @@ int rno_terrain2d_batch(const rn_params* p, const uint32_t* seeds, int ntiles, r
 uint64_t rno_cell_count(int depth);
 int rno_terrain2d_cells(const rn_params* p, const rn_element* field, rn_cell* cells);
 
+/* Rock generator (rn_oracle_rock.c): Rock::generateBaseRecursive on the six cube faces + Rock::generateRecursive. */
+uint64_t rno_rock_draw_count(int depth);
+long long rno_rock(uint32_t state_in, int depth, float amplitude, float size, float* faces, rn_cell* cells, uint32_t* state_out);
+/* index-addressed, breadth-first restatement (the CUDA formulation); -3 if a displaced height is exactly 0.0f */
+long long rno_rock_indexed(uint32_t state_in, int depth, float amplitude, float* faces, uint32_t* state_out);
+
 /* 3D density-volume extension (rn_oracle3d.c): NO reference counterpart, parity unpinned by the reference. */
 uint32_t rno_volume_draw(uint32_t seed, uint64_t idx);
 int rno_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, float* volume);

@@ -94,6 +94,12 @@ class Oracle:
         L.rno_cell_count.argtypes = [C.c_int]
         L.rno_terrain2d_cells.argtypes = [vp, vp, vp]
         L.rno_volume3d.argtypes = [C.c_uint32, C.c_int, C.c_float, C.c_int, C.c_int, vp]
+        L.rno_rock_draw_count.restype = C.c_uint64
+        L.rno_rock_draw_count.argtypes = [C.c_int]
+        L.rno_rock.restype = C.c_longlong
+        L.rno_rock.argtypes = [C.c_uint32, C.c_int, C.c_float, C.c_float, vp, vp, vp]
+        L.rno_rock_indexed.restype = C.c_longlong
+        L.rno_rock_indexed.argtypes = [C.c_uint32, C.c_int, C.c_float, vp, vp]
         L.rno_fnv64.restype = C.c_uint64
         L.rno_fnv64.argtypes = [vp, C.c_size_t]
 
@@ -141,6 +147,25 @@ class Oracle:
             raise RuntimeError(f"oracle status {st}")
         return v
 
+    def rock(self, state: int, depth: int, amplitude: float = 0.3, want_cells: bool = True):
+        """Rock.cpp restated: (faces[6, W+1, W+1, 2] = {height, shade} through Rock::element, cells[6, count], draws, state_after)."""
+        S = (1 << depth) + 1
+        faces = np.empty((6, S, S, 2), np.float32)
+        cells = np.zeros((6, cell_count(depth)), CELL_DTYPE) if want_cells else None
+        st = C.c_uint32(0)
+        n = self.L.rno_rock(state & 0xFFFFFFFF, depth, amplitude, 1.0, faces.ctypes.data, cells.ctypes.data if want_cells else None, C.byref(st))
+        if n < 0:
+            raise RuntimeError(f"oracle status {n}")
+        return faces, cells, int(n), int(st.value)
+
+    def rock_indexed(self, state: int, depth: int, amplitude: float = 0.3):
+        """Closed-form call indices + breadth-first levels (the CUDA formulation): (faces, status, state_after)."""
+        S = (1 << depth) + 1
+        faces = np.empty((6, S, S, 2), np.float32)
+        st = C.c_uint32(0)
+        n = self.L.rno_rock_indexed(state & 0xFFFFFFFF, depth, amplitude, faces.ctypes.data, C.byref(st))
+        return faces, int(n), int(st.value)
+
     def fnv64(self, a: np.ndarray) -> str:
         a = np.ascontiguousarray(a)
         return "%016x" % self.L.rno_fnv64(a.ctypes.data, a.nbytes)
@@ -157,6 +182,9 @@ class Ref:
         L.ref_terrain_cells.argtypes = [C.c_int, C.c_float, C.c_float, C.c_uint, C.c_void_p, C.c_void_p]
         L.ref_random_from_state.restype = C.c_float
         L.ref_random_from_state.argtypes = [C.c_uint]
+        if hasattr(L, "ref_rock"):
+            L.ref_rock.restype = C.c_longlong
+            L.ref_rock.argtypes = [C.c_uint, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
 
     def terrain2d(self, depth, seed=12345, amplitude=0.2, size=500.0, volcano=1, want_times=False):
         s = (1 << depth) + 1
@@ -176,6 +204,17 @@ class Ref:
         if n != cell_count(depth):
             raise RuntimeError(f"reference harness returned {n}")
         return field, out
+
+    def rock(self, state, depth, amplitude=0.3):
+        """The reference's own Rock::generateBaseRecursive / generateRecursive: (faces, cells, draws, state_after)."""
+        S = (1 << depth) + 1
+        faces = np.empty((6, S, S, 2), np.float32)
+        cells = np.zeros((6, cell_count(depth)), CELL_DTYPE)
+        st = C.c_uint(0)
+        n = self.L.ref_rock(state & 0xFFFFFFFF, depth, amplitude, faces.ctypes.data, cells.ctypes.data, C.byref(st))
+        if n < 0:
+            raise RuntimeError(f"reference harness returned {n}")
+        return faces, cells, int(n), int(st.value)
 
     def lcg_draws(self, seed, n):
         out = np.empty(n, np.int32)

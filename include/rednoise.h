@@ -174,6 +174,37 @@ uint64_t rn_terrain2d_cell_level_offset(int level);
 int rn_terrain2d_cells(rn_context* ctx, const rn_params* p, const rn_element* field, size_t field_pitch, int field_is_device,
                        rn_cell* cells, int cells_is_device, void* stream);
 
+/* ---- Rock generator ---------------------------------------------
+ * Replaces the field synthesis and the per-node arithmetic of Rock::Rock (renderEngine/source/Rock.cpp:14-99):
+ * generateBaseRecursive on the six cube faces (:64-67,173-218) and generateRecursive (:70-79,228-271).  The
+ * reference does not seed for rocks (Rock.cpp:63 is commented out): they continue the CRT rand() stream, so the
+ * caller passes the generator state at entry (srand(x): state x; after k calls: rn_lcg_state_after(x, k)) and gets
+ * the state afterwards back (rn_rock_draw_count(depth) = 4 W^2 - 4 calls later).
+ *   faces  6 x (W+1) x (W+1) x {height, shade}, W = 1 << depth: face f is the reference's currentFace, element
+ *          (x, y) at faces[(f*(W+1) + x)*(W+1) + y] is what Rock::element(x, y) refers to (Rock.cpp:127-170; a sample
+ *          on a cube edge appears on both faces that share it).  May be NULL.
+ *   cells  6 x rn_terrain2d_cell_count(depth) rn_cell: per face the nodes level by level, inside a level in the
+ *          recursion's visiting order (children 4e..4e+3 of node e), with position relative to the parent, colour,
+ *          quantised normal and radius of Rock.cpp:236-262.  The root PhysicalCell (:69,82-89) is scene graph and
+ *          stays with the caller.  May be NULL.
+ * The reference decides with `height == 0.0f` whether an edge midpoint still has to be displaced (:181-212); a
+ * displaced height that is exactly 0.0f would be drawn again there.  This implementation addresses every rand()
+ * call by index instead; it detects that case and returns RN_ERR_UNSUPPORTED rather than different samples.  The call
+ * synchronises `stream` (the status needs the device's answer). */
+#define RN_ROCK_MIN_DEPTH 1
+#define RN_ROCK_MAX_DEPTH 12
+typedef struct rn_rock_params {
+  uint32_t lcg_state; /* CRT generator state when Rock::Rock is entered */
+  int32_t depth;      /* Rock.h:10: detail; Core.cpp:76 uses 2..7 */
+  float amplitude;    /* Core.cpp:76: 0.3f */
+} rn_rock_params;
+typedef struct rn_rock_element {
+  float height, shade; /* Rock.h:21-24 */
+} rn_rock_element;
+uint64_t rn_rock_draw_count(int depth);
+int rn_rock(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, rn_cell* cells, int dst_is_device, void* stream,
+            uint32_t* lcg_state_after);
+
 /* ---- 3D density volume: an EXTENSION, not a drop-in -------------------------------------------
  * The reference has no volume generator: there is nothing to be bit-exact with, so the
  * definition is this repository's own CPU specification oracle/rn_oracle3d.c -- 3D midpoint displacement in the

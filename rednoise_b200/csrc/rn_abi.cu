@@ -608,6 +608,53 @@ int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, floa
   return RN_OK;
 }
 
+uint64_t rn_rock_draw_count(int depth)
+{
+  if (depth < RN_ROCK_MIN_DEPTH || depth > RN_ROCK_MAX_DEPTH) return 0;
+  return rock_draw_count(depth);
+}
+
+int rn_rock(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, rn_cell* cells, int dst_is_device, void* stream_v,
+            uint32_t* lcg_state_after)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  if (!p) return fail(RN_ERR_BAD_PARAM, "params is NULL");
+  if (p->depth < RN_ROCK_MIN_DEPTH || p->depth > RN_ROCK_MAX_DEPTH) return fail(RN_ERR_BAD_PARAM, "rock depth out of range [1,12]");
+  if (!faces && !cells) return fail(RN_ERR_BAD_PARAM, "faces and cells are both NULL");
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+  const size_t side = ((size_t)1 << p->depth) + 1;
+  const size_t face_bytes = 6 * side * side * sizeof(rn_rock_element);
+  const size_t ncells = 6 * (size_t)rn_terrain2d_cell_count(p->depth);
+  int st = ensure(&ctx->small, &ctx->small_bytes, 256);
+  if (st != RN_OK) return st;
+  void* dfaces = faces;
+  if (!faces || !dst_is_device || reinterpret_cast<uintptr_t>(faces) % 8 != 0) {
+    st = ensure(&ctx->field, &ctx->field_bytes, face_bytes);
+    if (st != RN_OK) return st;
+    dfaces = ctx->field;
+  }
+  void* dcells = cells;
+  if (cells && (!dst_is_device || reinterpret_cast<uintptr_t>(cells) % 16 != 0)) {
+    st = ensure(&ctx->cells, &ctx->cells_bytes, ncells * sizeof(rn_cell));
+    if (st != RN_OK) return st;
+    dcells = ctx->cells;
+  }
+  RN_CUDA(rock_generate(dfaces, dcells, (int*)ctx->small, p->depth, p->lcg_state, p->amplitude, stream, &ctx->launches));
+  if (faces && dfaces != faces)
+    RN_CUDA(cudaMemcpyAsync(faces, dfaces, face_bytes, dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+  if (cells && dcells != cells)
+    RN_CUDA(cudaMemcpyAsync(cells, dcells, ncells * sizeof(rn_cell), dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+  int collision = 0;
+  RN_CUDA(cudaMemcpyAsync(&collision, ctx->small, sizeof collision, cudaMemcpyDeviceToHost, stream));
+  RN_CUDA(cudaStreamSynchronize(stream));
+  if (collision)
+    return fail(RN_ERR_UNSUPPORTED, "a displaced rock height is exactly 0.0f: the reference's `height == 0.0f` test (Rock.cpp:181) would draw again");
+  if (lcg_state_after) *lcg_state_after = rn_lcg_state_after(p->lcg_state, rock_draw_count(p->depth));
+  return RN_OK;
+}
+
 int rn_selftest_math(rn_context* ctx, uint64_t* mismatches3)
 {
   if (!ctx || !mismatches3) return fail(RN_ERR_BAD_PARAM, "ctx/mismatches3 is NULL");

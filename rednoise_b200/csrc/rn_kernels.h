@@ -22,6 +22,12 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
 cudaError_t cells_generate(void* cells, const Elem* field, size_t pitch, int depth, float feature_scale, float size, float amplitude,
                            cudaStream_t stream, uint64_t* launches);
 
+// Rock generator (rn_rock.cu; Rock.cpp:64-67,173-271): faces = 6 x (W+1)^2 float2 {height, shade}, cells = 6 x (4^depth-1)/3 rn_cell or
+// nullptr, flag = device int set when a displaced height is exactly 0.0f (the reference's "unset" sentinel).
+uint64_t rock_draw_count(int depth);
+cudaError_t rock_generate(void* faces, void* cells, int* flag, int depth, uint32_t state, float amplitude, cudaStream_t stream,
+                          uint64_t* launches);
+
 // 3D density-volume extension (rn_volume.cu; defined by the CPU specification of DESIGN.md section 5.8, no reference counterpart):
 // planes [i0, i0+ni) of the (W+1)^3 float volume d (full-volume layout).
 cudaError_t volume_generate(float* d, int depth, uint32_t seed, float amplitude, int i0, int ni, cudaStream_t stream, uint64_t* launches);

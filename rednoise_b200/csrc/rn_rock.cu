@@ -1,0 +1,289 @@
+// rn_rock.cu -- the Rock generator: Rock::generateBaseRecursive on the six faces of a
+// cube that share their edges (Rock.cpp:64-67,127-218) and the Cell attributes of Rock::generateRecursive (:220-271).
+//
+// The reference recurses depth-first and lets a `height == 0.0f` test decide whether an edge midpoint still has to be
+// displaced, so the rand() call that displaces a sample is defined by the visiting order.  Here every call is
+// addressed by a closed-form index instead:
+//   * faces are visited 0..5; inside a face the quadtree in pre-order, children in Morton order (x = low bit); a node
+//     draws for its left, right, bottom, top midpoint if that sample is still unset (Rock.cpp:181-212);
+//   * nodes of one level are visited in Morton order, which is monotone in x and in y: the left and bottom midpoints
+//     of a node have been set by its neighbours, unless the node lies on the face border, where the midpoint is set
+//     iff a lower-numbered face shares that cube edge;
+//   * hence a subtree of width 2^k draws E(k) - (2^k - 1) * (sides already set) times, E(k) = (2^k+1)^2 - 4 - (4^k-1)/3,
+//     and the index of a node's slot is a sum of such terms along the path from the root.
+// With the index known, the LCG state is reached by skip-ahead and the levels are evaluated breadth-first, one launch
+// per level, each face on its own: a sample on a cube edge is computed by both faces that see it, from the same call
+// index, so the faces never exchange data.  A displaced height of exactly 0.0f would make the reference draw again
+// (value-dependent); the kernels flag it and the call fails loudly instead of returning different samples.
+#include "rn_kernels.h"
+#include "rn_tile.cuh"
+
+namespace rn {
+
+namespace {
+
+struct RockTopo {
+  int pre[6][4];       // side (L, R, B, T) of face f belongs to a lower-numbered face
+  uint32_t base[6];    // call index of the face's first draw (mod 2^32: only the LCG state is derived from it)
+};
+
+struct RockParams {
+  float2* faces;       // 6 x (W+1) x (W+1) {height, shade}: face f = the reference's currentFace, (x, y) as Rock::element sees it
+  int depth;
+  uint32_t state;      // generator state when the rock is entered
+  float amplitude;
+  RockTopo topo;
+  int* collision;      // set if a displaced height is exactly 0.0f
+};
+
+// Rock::element (Rock.cpp:127-151): face-local (x, y) -> cube coordinates
+__host__ __device__ inline void cube_of(int W, int f, int x, int y, int& X, int& Y, int& Z)
+{
+  const int a = f >> 1, fixed = (f & 1) ? 0 : W;
+  if (a == 0) { X = fixed; Y = x; Z = y; }
+  else if (a == 1) { X = x; Y = fixed; Z = y; }
+  else { X = x; Y = y; Z = fixed; }
+}
+__host__ __device__ inline bool face_local(int W, int g, int X, int Y, int Z, int& x, int& y)
+{
+  const int a = g >> 1, fixed = (g & 1) ? 0 : W;
+  if (a == 0) { if (X != fixed) return false; x = Y; y = Z; }
+  else if (a == 1) { if (Y != fixed) return false; x = X; y = Z; }
+  else { if (Z != fixed) return false; x = X; y = Y; }
+  return true;
+}
+__host__ __device__ inline uint32_t rock_E(int k)  // edge midpoints in the closed square of a node of width 2^k (mod 2^32)
+{
+  const uint32_t w = 1u << k;
+  return (w + 1u) * (w + 1u) - 4u - (uint32_t)((((uint64_t)1 << (2 * k)) - 1u) / 3u);
+}
+__host__ __device__ inline uint32_t node_draws(const int* pre, int j, int qx, int qy, int upto)
+{
+  const int n = 1 << j;
+  uint32_t d = 0;
+  if (upto > 0 && qx == 0 && !pre[0]) d++;
+  if (upto > 1 && !(qx == n - 1 && pre[1])) d++;
+  if (upto > 2 && qy == 0 && !pre[2]) d++;
+  if (upto > 3 && !(qy == n - 1 && pre[3])) d++;
+  return d;
+}
+__host__ __device__ inline uint32_t subtree_draws(const int* pre, int depth, int j, int qx, int qy)
+{
+  const int n = 1 << j, k = depth - j;
+  const int preset = ((qx > 0) || pre[0]) + ((qx == n - 1) && pre[1]) + ((qy > 0) || pre[2]) + ((qy == n - 1) && pre[3]);
+  return rock_E(k) - ((1u << k) - 1u) * (uint32_t)preset;
+}
+// call index of slot `slot` of node (level l, qx, qy) of face f
+__device__ inline uint32_t rock_call_index(const RockTopo& t, int depth, int f, int l, int qx, int qy, int slot)
+{
+  const int* pre = t.pre[f];
+  uint32_t idx = t.base[f];
+  for (int j = 0; j < l; j++) {
+    const int ax = qx >> (l - j), ay = qy >> (l - j);
+    idx += node_draws(pre, j, ax, ay, 4);
+    const int cx = qx >> (l - j - 1), cy = qy >> (l - j - 1);
+    const int ci = ((cy & 1) << 1) | (cx & 1);
+    for (int s = 0; s < ci; s++) idx += subtree_draws(pre, depth, j + 1, (ax << 1) | (s & 1), (ay << 1) | (s >> 1));
+  }
+  return idx + node_draws(pre, l, qx, qy, slot);
+}
+// call index of the edge midpoint (x, y) of face f at level l, resolved on the face that draws it
+__device__ inline uint32_t rock_point_call_index(const RockTopo& t, int depth, int f, int l, int x, int y)
+{
+  const int W = 1 << depth, sh = depth - l;  // node width w = 1 << sh
+  int X, Y, Z;
+  cube_of(W, f, x, y, X, Y, Z);
+  for (int g = 0; g < 6; g++) {
+    int gx, gy;
+    if (!face_local(W, g, X, Y, Z, gx, gy)) continue;
+    if ((gx & ((1 << sh) - 1)) == 0) {  // on a vertical node side: right slot of the node on its left, left slot in column 0
+      const int qy = gy >> sh;
+      if (gx == 0) return rock_call_index(t, depth, g, l, 0, qy, 0);
+      return rock_call_index(t, depth, g, l, (gx >> sh) - 1, qy, 1);
+    }
+    const int qx = gx >> sh;
+    if (gy == 0) return rock_call_index(t, depth, g, l, qx, 0, 2);
+    return rock_call_index(t, depth, g, l, qx, (gy >> sh) - 1, 3);
+  }
+  return 0;
+}
+
+// One level: the centres (Rock.cpp:179) and edge midpoints (:181-212) of all nodes of width W >> l, on the
+// half-step lattice of that level ((2n+1)^2 points per face; those with two even coordinates are older).
+__global__ void k_rock_level(const __grid_constant__ RockParams rp, int l)
+{
+  const int depth = rp.depth, W = 1 << depth, P = W + 1;
+  const int n2 = (2 << l) + 1;  // points per side of the half-step lattice
+  const int f = blockIdx.z;
+  const int px = blockIdx.y * blockDim.y + threadIdx.y, py = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= n2 || py >= n2) return;
+  const int ox = px & 1, oy = py & 1;
+  if (!ox && !oy) return;
+  const int hsh = depth - l - 1, h = 1 << hsh;  // half step
+  const int x = px << hsh, y = py << hsh;
+  float2* g = rp.faces + (size_t)f * P * P;
+  float2 e;
+  if (ox && oy) {
+    const float2 a = g[(size_t)(x - h) * P + (y - h)], b = g[(size_t)(x + h) * P + (y - h)], c = g[(size_t)(x - h) * P + (y + h)],
+                 d = g[(size_t)(x + h) * P + (y + h)];
+    e.x = (a.x + b.x + c.x + d.x) * 0.25f;  // Rock.h:25-29
+    e.y = (a.y + b.y + c.y + d.y) * 0.25f;
+  } else {
+    const float2 a = ox ? g[(size_t)(x - h) * P + y] : g[(size_t)x * P + (y - h)], b = ox ? g[(size_t)(x + h) * P + y] : g[(size_t)x * P + (y + h)];
+    const uint32_t k = rock_point_call_index(rp.topo, depth, f, l, x, y);
+    const float r = random_from_draw(lcg_draw_from_state(lcg_skip(rp.state, k + 1u)));
+    const float offset = rp.amplitude * r * (float)(2 * h) / (float)W;  // Rock.cpp:185: amplitude * random() * extent / maxWidth
+    e.x = (a.x + b.x) * 0.5f + offset;                                   // Rock.h:30-34, Rock.cpp:186
+    e.y = (a.y + b.y) * 0.5f + offset * 1.5f;                            // radiosityStrength, Rock.cpp:171,187
+    if (e.x == 0.0f) atomicExch(rp.collision, 1);
+  }
+  g[(size_t)x * P + y] = e;
+}
+
+__global__ void k_rock_init(float2* faces, size_t n)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) faces[i] = make_float2(0.0f, 1.0f);  // Rock.cpp:57-60
+}
+
+// ---- Cell attributes: Rock::generateRecursive (Rock.cpp:228-271) ----
+__device__ inline V3 rock_box_pos(int W, int f, int x, int y)  // Rock.cpp:100-124
+{
+  const float fw = (float)W;
+  const int a = f >> 1;
+  const float fixed = (f & 1) ? 0.f : 1.f;
+  const float u = __fdiv_rn((float)x, fw), v = __fdiv_rn((float)y, fw);
+  float X, Y, Z;
+  if (a == 0) { X = fixed; Y = u; Z = v; }
+  else if (a == 1) { X = u; Y = fixed; Z = v; }
+  else { X = u; Y = v; Z = fixed; }
+  return V3{X - 0.5f, Y - 0.5f, Z - 0.5f};
+}
+__device__ inline V3 rock_normalise(V3 v)  // member normalise(), Vector3.h:109-120
+{
+  const float f = __fsqrt_rn(v.x * v.x + v.y * v.y + v.z * v.z);
+  if (f < 1e-10f) return V3{0.0f, 0.0f, 1.0f};
+  const float d = __frcp_rn(f);
+  return V3{v.x * d, v.y * d, v.z * d};
+}
+__device__ inline V3 rock_get_pos(const float2* g, int P, int W, int f, int x, int y)  // Rock.cpp:220-227
+{
+  const V3 r = rock_normalise(rock_box_pos(W, f, x, y));
+  const float s = 1.0f + g[(size_t)x * P + y].x;
+  return V3{r.x * s, r.y * s, r.z * s};
+}
+__device__ inline float clampedf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }  // basics.h:12-15
+
+struct RockCell {  // rn_cell (include/rednoise.h)
+  float position[3];
+  float colour[3];
+  float radius;
+  int8_t normal[3];
+  uint8_t level;
+};
+
+__global__ void k_rock_cells(RockCell* __restrict__ out, const float2* __restrict__ faces, int depth, uint32_t count, float radius0)
+{
+  const uint32_t e_all = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e_all >= count) return;
+  const int f = blockIdx.y;
+  const int W = 1 << depth, P = W + 1;
+  const float2* g = faces + (size_t)f * P * P;
+  // level-major index -> (level, entry); entry = Morton code of the node, x in the low bit (children order of :266-269)
+  int l = 0;
+  uint32_t off = 0;
+  while (off + (1u << (2 * l)) <= e_all) { off += 1u << (2 * l); l++; }
+  const uint32_t m = e_all - off;
+  int qx = 0, qy = 0;
+  for (int b = 0; b < l; b++) { qx |= ((m >> (2 * b)) & 1u) << b; qy |= ((m >> (2 * b + 1)) & 1u) << b; }
+  const int w = W >> l;
+  const int minX = qx * w, minY = qy * w, maxX = minX + w, maxY = minY + w, midX = minX + w / 2, midY = minY + w / 2;
+  V3 centre = rock_get_pos(g, P, W, f, midX, midY);
+  centre = vmul(centre, 1.0f);  // `* size` with the constructor's size argument 1.0f (Rock.cpp:77,236)
+  V3 position = centre;
+  {  // cell->position -= parentPosWorldSpace: the parent's centre, (0,0,0) for the root PhysicalCell
+    V3 parent{0.0f, 0.0f, 0.0f};
+    if (l > 0) {
+      const int pw = w * 2, pX = (qx >> 1) * pw + pw / 2, pY = (qy >> 1) * pw + pw / 2;
+      parent = vmul(rock_get_pos(g, P, W, f, pX, pY), 1.0f);
+    }
+    position = vsub(position, parent);
+  }
+  const float shade = g[(size_t)midX * P + midY].y;
+  RockCell c;
+  c.colour[0] = clampedf(0.6f * shade, 0.0f, 1.0f);
+  c.colour[1] = clampedf(0.54f * shade, 0.0f, 1.0f);
+  c.colour[2] = clampedf(0.48f * shade, 0.0f, 1.0f);
+  c.position[0] = position.x; c.position[1] = position.y; c.position[2] = position.z;
+  const V3 xc = vsub(rock_get_pos(g, P, W, f, minX, minY), rock_get_pos(g, P, W, f, maxX, maxY));
+  const V3 yc = vsub(rock_get_pos(g, P, W, f, maxX, minY), rock_get_pos(g, P, W, f, minX, maxY));
+  V3 normal = vcross(xc, yc);
+  if (normal.x * centre.x + normal.y * centre.y + normal.z * centre.z < 0.0f) normal = V3{-normal.x, -normal.y, -normal.z};
+  normal = rock_normalise(normal);
+  c.normal[0] = (int8_t)(int)(normal.x * 127.0f);
+  c.normal[1] = (int8_t)(int)(normal.y * 127.0f);
+  c.normal[2] = (int8_t)(int)(normal.z * 127.0f);
+  float radius = radius0;
+  for (int b = 0; b < l; b++) radius = __fdiv_rn(radius, 2.0f);  // radius /= 2.0f per level (:264)
+  c.radius = radius;
+  c.level = (uint8_t)l;
+  const float4* src = reinterpret_cast<const float4*>(&c);
+  float4* dst = reinterpret_cast<float4*>(out + (size_t)f * count + e_all);
+  dst[0] = src[0];
+  dst[1] = src[1];
+}
+
+}  // namespace
+
+uint64_t rock_draw_count(int depth)
+{
+  const uint64_t W = (uint64_t)1 << depth;
+  return 4 * W * W - 4;
+}
+
+// faces: device, 6 x (W+1)^2 float2; cells: device or nullptr, 6 x (4^depth - 1)/3 rn_cell; flag: device int (collision)
+cudaError_t rock_generate(void* faces_v, void* cells_v, int* flag, int depth, uint32_t state, float amplitude, cudaStream_t stream,
+                          uint64_t* launches)
+{
+  float2* faces = static_cast<float2*>(faces_v);
+  const int W = 1 << depth;
+  const size_t P = (size_t)W + 1, nall = 6 * P * P;
+  RockParams rp;
+  rp.faces = faces; rp.depth = depth; rp.state = state; rp.amplitude = amplitude; rp.collision = flag;
+  {  // which sides of a face were drawn by an earlier face (cube topology of Rock::element), and the faces' first call
+    const int sx[4] = {0, W, W / 2, W / 2}, sy[4] = {W / 2, W / 2, 0, W};
+    uint32_t acc = 0;
+    for (int f = 0; f < 6; f++) {
+      for (int s = 0; s < 4; s++) {
+        int X, Y, Z, x, y;
+        cube_of(W, f, sx[s], sy[s], X, Y, Z);
+        rp.topo.pre[f][s] = 0;
+        for (int g = 0; g < f; g++)
+          if (face_local(W, g, X, Y, Z, x, y)) rp.topo.pre[f][s] = 1;
+      }
+      rp.topo.base[f] = acc;
+      acc += rock_E(depth) - (uint32_t)(W - 1) * (uint32_t)(rp.topo.pre[f][0] + rp.topo.pre[f][1] + rp.topo.pre[f][2] + rp.topo.pre[f][3]);
+    }
+  }
+  cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  k_rock_init<<<(unsigned)((nall + 255) / 256), 256, 0, stream>>>(faces, nall);
+  uint64_t nl = 1;
+  for (int l = 0; l < depth; l++) {
+    const int n2 = (2 << l) + 1;
+    const dim3 block(32, 8), grid((n2 + 31) / 32, (n2 + 7) / 8, 6);
+    k_rock_level<<<grid, block, 0, stream>>>(rp, l);
+    nl++;
+  }
+  if (cells_v) {
+    uint32_t count = 0;
+    for (int l = 0; l < depth; l++) count += 1u << (2 * l);
+    const float radius0 = 1.4f * sqrtf((1.0f + 0.5f * amplitude) * 0.5f);  // Rock.cpp:76
+    k_rock_cells<<<dim3((count + 127) / 128, 6), 128, 0, stream>>>(static_cast<RockCell*>(cells_v), faces, depth, count, radius0);
+    nl++;
+  }
+  if (launches) *launches += nl;
+  return cudaGetLastError();
+}
+
+}  // namespace rn

@@ -1,0 +1,73 @@
+"""GPU: the Rock generator (rn_rock, rednoise_b200/csrc/rn_rock.cu) against the oracle restatement of Rock.cpp and against the
+golden digests produced by the reference's own functions -- bit for bit: faces {height, shade}, Cell attributes, generator state."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "terrain2d_golden.json")))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from rednoise_b200 import capi
+    return capi.Context(0)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("state", [12345, 1, 0xDEADBEEF])
+def test_rock_equals_oracle(ctx, oracle, depth, state):
+    fo, co, draws, so = oracle.rock(state, depth, 0.3)
+    fg, cg, sg = ctx.rock_host(state, depth, 0.3)
+    assert sg == so
+    assert np.array_equal(fo.view(np.uint32), fg.view(np.uint32))
+    assert co.tobytes() == cg.tobytes()
+
+
+@pytest.mark.parametrize("entry", GOLD.get("rocks", []), ids=lambda e: f"d{e['depth']}-s{e['state']}")
+def test_rock_golden(ctx, oracle, entry):
+    """digests recorded from the reference's own Rock::generateBaseRecursive / generateRecursive"""
+    faces, cells, after = ctx.rock_host(entry["state"], entry["depth"], entry["amplitude"])
+    assert after == entry["state_after"]
+    assert oracle.fnv64(faces) == entry["fnv64_faces"]
+    assert oracle.fnv64(cells.view(np.uint8)) == entry["fnv64_cells"]
+
+
+def test_rock_amplitude_and_faces_only(ctx, oracle):
+    fo, _, _, so = oracle.rock(42, 6, 0.45, want_cells=False)
+    fg, cg, sg = ctx.rock_host(42, 6, 0.45, want_cells=False)
+    assert cg is None and sg == so and np.array_equal(fo.view(np.uint32), fg.view(np.uint32))
+
+
+def test_rock_device_destination_and_stream_continuity(ctx, oracle):
+    """20 rocks continuing one rand() stream, as Core.cpp:69-79 builds them (the draws Core.cpp:72 takes in between are
+    the caller's: here the stream simply runs on), into device memory."""
+    import torch
+    from rednoise_b200 import capi
+    state = 777
+    for k in range(6):
+        depth = 2 + (k % 6)
+        side = (1 << depth) + 1
+        n = int(capi.lib().rn_terrain2d_cell_count(depth))
+        faces = torch.empty((6, side, side, 2), device="cuda", dtype=torch.float32)
+        cells = torch.empty((6, n, 8), device="cuda", dtype=torch.float32)
+        after = ctx.rock_ptr(state, depth, 0.3, faces.data_ptr(), cells.data_ptr(), dst_is_device=True)
+        fo, co, draws, so = oracle.rock(state, depth, 0.3)
+        assert after == so == capi.lib().rn_lcg_state_after(state, capi.lib().rn_rock_draw_count(depth))
+        assert np.array_equal(fo.view(np.uint32), faces.cpu().numpy().view(np.uint32))
+        assert co.tobytes() == cells.cpu().numpy().tobytes()
+        state = after
+
+
+def test_rock_rejects_bad_arguments(ctx):
+    from rednoise_b200 import capi
+    with pytest.raises(Exception):
+        ctx.rock_host(1, 0)
+    with pytest.raises(Exception):
+        ctx.rock_host(1, 13)
+    with pytest.raises(Exception):
+        ctx.rock_ptr(1, 4, 0.3, 0, 0)

@@ -205,6 +205,18 @@ uint64_t rn_rock_draw_count(int depth);
 int rn_rock(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, rn_cell* cells, int dst_is_device, void* stream,
             uint32_t* lcg_state_after);
 
+/* ---- Cloud generator --------------------------------------------
+ * Cloud::Cloud (renderEngine/source/Cloud.cpp:14-105; the app never instantiates one, Core.cpp:80-82): the two-face
+ * variant of Rock.  Same calling convention as rn_rock with 2 faces instead of 6: faces[(f*(W+1) + x)*(W+1) + y] is what
+ * Cloud::element(x, y) refers to for currentFace f (the two sheets share their border, Cloud.cpp:116-121), cells =
+ * 2 x rn_terrain2d_cell_count(depth) in the recursion's visiting order -- note that Cloud stores the child POINTERS in
+ * decreasing slots (children[3 - k] = node 4e + k, Cloud.cpp:217-220).  depth >= 2 (the preset control heights of
+ * :64-73 sit at maxWidth/4).  rn_cloud_draw_count(depth) rand() calls are consumed. */
+#define RN_CLOUD_MIN_DEPTH 2
+uint64_t rn_cloud_draw_count(int depth);
+int rn_cloud(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, rn_cell* cells, int dst_is_device, void* stream,
+             uint32_t* lcg_state_after);
+
 /* ---- 3D density volume: an EXTENSION, not a drop-in -------------------------------------------
  * The reference has no volume generator: there is nothing to be bit-exact with, so the
  * definition is this repository's own CPU specification oracle/rn_oracle3d.c -- 3D midpoint displacement in the

@@ -19,6 +19,7 @@
 #define private public
 #include "Terrain.h"
 #include "Rock.h"
+#include "Cloud.h"
 #undef private
 #include "Cell.h"
 #include "OrientableCell.h"
@@ -344,6 +345,118 @@ long long ref_rock(unsigned int state_in, int depth, float amplitude, float* fac
     free(parent);
   }
   for (int face = 0; face < 6; face++)
+  {
+    for (int i = 0; i < maxWidth + 1; i++) delete[] r->baseArray[face][i];
+    delete[] r->baseArray[face];
+  }
+  delete[] r->baseArray;
+  delete[] r->levels;
+  delete[] r->numEntries;
+  free(r);
+  return draws;
+}
+
+// The reference's own Cloud::generateBaseRecursive (Cloud.cpp:124-171) on its two sheets and Cloud::generateRecursive
+// (:174-222), members set up as Cloud::Cloud does (:14-73, :78-88); the constructor itself is not run.
+long long ref_cloud(unsigned int state_in, int depth, float amplitude, float* faces_out, void* cells_out, unsigned int* state_out)
+{
+  if (depth < 2 || depth > 12) return -1;
+  Cloud* r = (Cloud*)calloc(1, sizeof(Cloud));
+  r->size = 1.0f;
+  r->m_depth = depth;
+  r->maxWidth = 1 << depth;
+  r->m_amplitude = amplitude;
+  r->levels = new int[depth];
+  r->numEntries = new int[depth];
+  int count = 0, width = 0;
+  for (int i = 0; i < depth; i++)
+  {
+    r->numEntries[i] = 0;
+    width = 1 << i;
+    r->levels[i] = count;
+    count += width * width;
+  }
+  const int maxWidth = r->maxWidth;
+  r->baseArray = new Cloud::CloudElement**[2];
+  for (int face = 0; face < 2; face++)
+  {
+    r->baseArray[face] = new Cloud::CloudElement*[maxWidth + 1];
+    for (int i = 0; i < maxWidth + 1; i++)
+    {
+      r->baseArray[face][i] = new Cloud::CloudElement[maxWidth + 1];
+      for (int j = 0; j < maxWidth + 1; j++)
+      {
+        r->baseArray[face][i][j].height = 0.0f;
+        r->baseArray[face][i][j].shade = 1.0f;
+      }
+    }
+  }
+  r->baseArray[0][maxWidth / 2][maxWidth / 2].height = -0.5f; // Cloud.cpp:64-73
+  r->baseArray[0][maxWidth / 4][maxWidth / 4].height = -0.5f;
+  r->baseArray[0][3 * maxWidth / 4][maxWidth / 4].height = -0.5f;
+  r->baseArray[0][maxWidth / 4][3 * maxWidth / 4].height = -0.5f;
+  r->baseArray[0][3 * maxWidth / 4][3 * maxWidth / 4].height = -0.5f;
+  r->baseArray[1][maxWidth / 2][maxWidth / 2].height = 0.5f;
+  r->baseArray[1][maxWidth / 4][maxWidth / 4].height = 0.5f;
+  r->baseArray[1][3 * maxWidth / 4][maxWidth / 4].height = 0.5f;
+  r->baseArray[1][maxWidth / 4][3 * maxWidth / 4].height = 0.5f;
+  r->baseArray[1][3 * maxWidth / 4][3 * maxWidth / 4].height = 0.5f;
+  g_seed_forced = 0;
+  rn_msvc_srand(state_in);
+  const unsigned long long calls0 = g_calls;
+  for (r->currentFace = 0; r->currentFace < 2; r->currentFace++) r->generateBaseRecursive(0, 0, maxWidth, maxWidth);
+  const long long draws = (long long)(g_calls - calls0);
+  if (state_out) *state_out = g_state;
+  if (faces_out)
+    for (r->currentFace = 0; r->currentFace < 2; r->currentFace++)
+      for (int x = 0; x <= maxWidth; x++)
+        for (int y = 0; y <= maxWidth; y++)
+        {
+          Cloud::CloudElement& e = r->element(x, y);
+          float* o = faces_out + (((size_t)r->currentFace * (maxWidth + 1) + x) * (maxWidth + 1) + y) * 2;
+          o[0] = e.height; o[1] = e.shade;
+        }
+  if (cells_out)
+  {
+    RnRefRockPoolElem* contiguous = (RnRefRockPoolElem*)malloc(sizeof(RnRefRockPoolElem) * (size_t)count * 2);
+    r->cells = new Cell*[count * 2];
+    for (int face = 0; face < 2; face++)
+      for (int i = 0; i < count; i++)
+      {
+        RnRefRockPoolElem* e = contiguous + (size_t)face * count + i;
+        if (i >= count - (width * width)) r->cells[i + face * count] = new (&(e->cell)) Cell(NULL, 0);
+        else r->cells[i + face * count] = new (&(e->cell)) Cell(NULL, 4, (char*)&(e->children));
+      }
+    Cell* parent = (Cell*)malloc(sizeof(Cell));
+    struct Out { float pos[3], col[3], radius; signed char n[3]; unsigned char level; };
+    Out* out = (Out*)cells_out;
+    long long k = 0;
+    for (r->currentFace = 0; r->currentFace < 2; r->currentFace++)
+    {
+      for (int i = 0; i < depth; i++) r->numEntries[i] = 0;
+      float radius = 1.8f * sqrtf((1.0f + 0.5f * r->m_amplitude) * 0.5f); // Cloud.cpp:84
+      r->generateRecursive(r->cells + count * r->currentFace, parent, Vector3(0, 0, 0), 0, 0, maxWidth, maxWidth, 0, 1.0f, radius);
+      for (int l = 0; l < depth; l++)
+      {
+        const int n = 1 << (2 * l);
+        if (r->numEntries[l] != n) return -2;
+        for (int e = 0; e < n; e++)
+        {
+          const Cell* c = r->cells[count * r->currentFace + r->levels[l] + e];
+          Out& o = out[k++];
+          o.pos[0] = c->position.x; o.pos[1] = c->position.y; o.pos[2] = c->position.z;
+          o.col[0] = c->colour.x; o.col[1] = c->colour.y; o.col[2] = c->colour.z;
+          o.radius = c->radius;
+          o.n[0] = c->normal[0]; o.n[1] = c->normal[1]; o.n[2] = c->normal[2];
+          o.level = (unsigned char)l;
+        }
+      }
+    }
+    delete[] r->cells;
+    free(contiguous);
+    free(parent);
+  }
+  for (int face = 0; face < 2; face++)
   {
     for (int i = 0; i < maxWidth + 1; i++) delete[] r->baseArray[face][i];
     delete[] r->baseArray[face];

@@ -54,6 +54,9 @@ long long rno_rock(uint32_t state_in, int depth, float amplitude, float size, fl
 /* index-addressed, breadth-first restatement (the CUDA formulation); -3 if a displaced height is exactly 0.0f */
 long long rno_rock_indexed(uint32_t state_in, int depth, float amplitude, float* faces, uint32_t* state_out);
 
+/* Cloud generator (rn_oracle_cloud.c): the two-face variant of Rock (Cloud.cpp). */
+long long rno_cloud(uint32_t state_in, int depth, float amplitude, float* faces, rn_cell* cells, uint32_t* state_out);
+
 /* 3D density-volume extension (rn_oracle3d.c): NO reference counterpart, parity unpinned by the reference. */
 uint32_t rno_volume_draw(uint32_t seed, uint64_t idx);
 int rno_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, float* volume);

@@ -23,7 +23,7 @@ SYMBOLS = [
     "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
     "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_set_pipelining", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device", "rn_selftest_math",
     "rn_terrain2d_cell_count", "rn_terrain2d_cell_level_offset", "rn_terrain2d_cells", "rn_volume3d",
-    "rn_rock_draw_count", "rn_rock",
+    "rn_rock_draw_count", "rn_rock", "rn_cloud_draw_count", "rn_cloud",
 ]
 
 
@@ -113,6 +113,10 @@ def lib() -> C.CDLL:
     L.rn_rock_draw_count.argtypes = [i32]
     L.rn_rock.restype = i32
     L.rn_rock.argtypes = [vp, C.POINTER(RockParams), vp, vp, i32, vp, C.POINTER(C.c_uint32)]
+    L.rn_cloud_draw_count.restype = C.c_uint64
+    L.rn_cloud_draw_count.argtypes = [i32]
+    L.rn_cloud.restype = i32
+    L.rn_cloud.argtypes = [vp, C.POINTER(RockParams), vp, vp, i32, vp, C.POINTER(C.c_uint32)]
     _lib = L
     return L
 
@@ -235,20 +239,24 @@ class Context:
         _check(lib().rn_volume3d(self._h, C.byref(vp_), i0, side - i0 if ni is None else ni, C.c_void_p(ptr),
                                  C.c_void_p(stream) if stream else None))
 
-    def rock_ptr(self, state: int, depth: int, amplitude: float, faces_ptr: int, cells_ptr: int, *, dst_is_device: bool = True, stream: int = 0) -> int:
-        """Rock generator (Rock.cpp): faces / cells at the given pointers (0 = not wanted); returns the generator state afterwards."""
+    def rock_ptr(self, state: int, depth: int, amplitude: float, faces_ptr: int, cells_ptr: int, *, dst_is_device: bool = True, stream: int = 0,
+                 cloud: bool = False) -> int:
+        """Rock generator (Rock.cpp; cloud=True: Cloud.cpp): faces / cells at the given pointers (0 = not wanted); returns the generator
+        state afterwards."""
         rp = RockParams(state & 0xFFFFFFFF, depth, amplitude)
         after = C.c_uint32(0)
-        _check(lib().rn_rock(self._h, C.byref(rp), C.c_void_p(faces_ptr) if faces_ptr else None, C.c_void_p(cells_ptr) if cells_ptr else None,
+        fn = lib().rn_cloud if cloud else lib().rn_rock
+        _check(fn(self._h, C.byref(rp), C.c_void_p(faces_ptr) if faces_ptr else None, C.c_void_p(cells_ptr) if cells_ptr else None,
                              1 if dst_is_device else 0, C.c_void_p(stream) if stream else None, C.byref(after)))
         return int(after.value)
 
-    def rock_host(self, state: int, depth: int, amplitude: float = 0.3, want_cells: bool = True):
-        """(faces[6, W+1, W+1, 2] float32, cells[6, count] CELL_DTYPE or None, state_after) in host memory."""
+    def rock_host(self, state: int, depth: int, amplitude: float = 0.3, want_cells: bool = True, cloud: bool = False):
+        """(faces[6 or 2, W+1, W+1, 2] float32, cells[6 or 2, count] CELL_DTYPE or None, state_after) in host memory."""
         side = (1 << depth) + 1
-        faces = np.empty((6, side, side, 2), np.float32)
-        cells = np.zeros((6, int(lib().rn_terrain2d_cell_count(depth))), CELL_DTYPE) if want_cells else None
-        after = self.rock_ptr(state, depth, amplitude, faces.ctypes.data, cells.ctypes.data if want_cells else 0, dst_is_device=False)
+        nf = 2 if cloud else 6
+        faces = np.empty((nf, side, side, 2), np.float32)
+        cells = np.zeros((nf, int(lib().rn_terrain2d_cell_count(depth))), CELL_DTYPE) if want_cells else None
+        after = self.rock_ptr(state, depth, amplitude, faces.ctypes.data, cells.ctypes.data if want_cells else 0, dst_is_device=False, cloud=cloud)
         return faces, cells, after
 
     def selftest_math(self):

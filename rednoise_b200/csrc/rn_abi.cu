@@ -614,19 +614,21 @@ uint64_t rn_rock_draw_count(int depth)
   return rock_draw_count(depth);
 }
 
-int rn_rock(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, rn_cell* cells, int dst_is_device, void* stream_v,
-            uint32_t* lcg_state_after)
+namespace {
+int rock_or_cloud(rn_context* ctx, int kind, const rn_rock_params* p, rn_rock_element* faces, rn_cell* cells, int dst_is_device, void* stream_v,
+                  uint32_t* lcg_state_after)
 {
   if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
   if (!p) return fail(RN_ERR_BAD_PARAM, "params is NULL");
-  if (p->depth < RN_ROCK_MIN_DEPTH || p->depth > RN_ROCK_MAX_DEPTH) return fail(RN_ERR_BAD_PARAM, "rock depth out of range [1,12]");
+  const int nfaces = kind ? 2 : 6, min_depth = kind ? RN_CLOUD_MIN_DEPTH : RN_ROCK_MIN_DEPTH;
+  if (p->depth < min_depth || p->depth > RN_ROCK_MAX_DEPTH) return fail(RN_ERR_BAD_PARAM, kind ? "cloud depth out of range [2,12]" : "rock depth out of range [1,12]");
   if (!faces && !cells) return fail(RN_ERR_BAD_PARAM, "faces and cells are both NULL");
   DeviceGuard guard(ctx->device);
   if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
   const size_t side = ((size_t)1 << p->depth) + 1;
-  const size_t face_bytes = 6 * side * side * sizeof(rn_rock_element);
-  const size_t ncells = 6 * (size_t)rn_terrain2d_cell_count(p->depth);
+  const size_t face_bytes = (size_t)nfaces * side * side * sizeof(rn_rock_element);
+  const size_t ncells = (size_t)nfaces * (size_t)rn_terrain2d_cell_count(p->depth);
   int st = ensure(&ctx->small, &ctx->small_bytes, 256);
   if (st != RN_OK) return st;
   void* dfaces = faces;
@@ -641,7 +643,7 @@ int rn_rock(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, rn
     if (st != RN_OK) return st;
     dcells = ctx->cells;
   }
-  RN_CUDA(rock_generate(dfaces, dcells, (int*)ctx->small, p->depth, p->lcg_state, p->amplitude, stream, &ctx->launches));
+  RN_CUDA(rock_generate(dfaces, dcells, (int*)ctx->small, kind, p->depth, p->lcg_state, p->amplitude, stream, &ctx->launches));
   if (faces && dfaces != faces)
     RN_CUDA(cudaMemcpyAsync(faces, dfaces, face_bytes, dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
   if (cells && dcells != cells)
@@ -650,9 +652,28 @@ int rn_rock(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, rn
   RN_CUDA(cudaMemcpyAsync(&collision, ctx->small, sizeof collision, cudaMemcpyDeviceToHost, stream));
   RN_CUDA(cudaStreamSynchronize(stream));
   if (collision)
-    return fail(RN_ERR_UNSUPPORTED, "a displaced rock height is exactly 0.0f: the reference's `height == 0.0f` test (Rock.cpp:181) would draw again");
-  if (lcg_state_after) *lcg_state_after = rn_lcg_state_after(p->lcg_state, rock_draw_count(p->depth));
+    return fail(RN_ERR_UNSUPPORTED, "a displaced height is exactly 0.0f: the reference's `height == 0.0f` test (Rock.cpp:181, Cloud.cpp:134) would draw again");
+  if (lcg_state_after) *lcg_state_after = rn_lcg_state_after(p->lcg_state, kind ? cloud_draw_count(p->depth) : rock_draw_count(p->depth));
   return RN_OK;
+}
+}  // namespace
+
+int rn_rock(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, rn_cell* cells, int dst_is_device, void* stream_v,
+            uint32_t* lcg_state_after)
+{
+  return rock_or_cloud(ctx, 0, p, faces, cells, dst_is_device, stream_v, lcg_state_after);
+}
+
+uint64_t rn_cloud_draw_count(int depth)
+{
+  if (depth < RN_CLOUD_MIN_DEPTH || depth > RN_ROCK_MAX_DEPTH) return 0;
+  return cloud_draw_count(depth);
+}
+
+int rn_cloud(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, rn_cell* cells, int dst_is_device, void* stream_v,
+             uint32_t* lcg_state_after)
+{
+  return rock_or_cloud(ctx, 1, p, faces, cells, dst_is_device, stream_v, lcg_state_after);
 }
 
 int rn_selftest_math(rn_context* ctx, uint64_t* mismatches3)

@@ -24,8 +24,10 @@ cudaError_t cells_generate(void* cells, const Elem* field, size_t pitch, int dep
 
 // Rock generator (rn_rock.cu; Rock.cpp:64-67,173-271): faces = 6 x (W+1)^2 float2 {height, shade}, cells = 6 x (4^depth-1)/3 rn_cell or
 // nullptr, flag = device int set when a displaced height is exactly 0.0f (the reference's "unset" sentinel).
+// kind 0 = Rock (6 faces), 1 = Cloud (Cloud.cpp: 2 sheets sharing their border, preset control heights).
 uint64_t rock_draw_count(int depth);
-cudaError_t rock_generate(void* faces, void* cells, int* flag, int depth, uint32_t state, float amplitude, cudaStream_t stream,
+uint64_t cloud_draw_count(int depth);
+cudaError_t rock_generate(void* faces, void* cells, int* flag, int kind, int depth, uint32_t state, float amplitude, cudaStream_t stream,
                           uint64_t* launches);
 
 // 3D density-volume extension (rn_volume.cu; defined by the CPU specification of DESIGN.md section 5.8, no reference counterpart):

@@ -15,6 +15,11 @@
 // per level, each face on its own: a sample on a cube edge is computed by both faces that see it, from the same call
 // index, so the faces never exchange data.  A displaced height of exactly 0.0f would make the reference draw again
 // (value-dependent); the kernels flag it and the call fails loudly instead of returning different samples.
+//
+// KIND 1 is the Cloud generator (Cloud.cpp), the two-face variant: a lower and an upper sheet that share their whole border
+// (Cloud::element, Cloud.cpp:116-121: face 1 finds all four sides set by face 0), ten preset control heights (:64-73) that the
+// `height == 0.0f` test on centres (:131-132) preserves, flat boxPos/getPos (:106-113,167-173), grey colour, normal flipped on
+// the upper sheet (:199-200).
 #include "rn_kernels.h"
 #include "rn_tile.cuh"
 
@@ -27,8 +32,10 @@ struct RockTopo {
   uint32_t base[6];    // call index of the face's first draw (mod 2^32: only the LCG state is derived from it)
 };
 
+constexpr int kRock = 0, kCloud = 1;
+
 struct RockParams {
-  float2* faces;       // 6 x (W+1) x (W+1) {height, shade}: face f = the reference's currentFace, (x, y) as Rock::element sees it
+  float2* faces;       // nfaces x (W+1) x (W+1) {height, shade}: face f = the reference's currentFace, (x, y) as element() sees it
   int depth;
   uint32_t state;      // generator state when the rock is entered
   float amplitude;
@@ -88,14 +95,21 @@ __device__ inline uint32_t rock_call_index(const RockTopo& t, int depth, int f, 
   return idx + node_draws(pre, l, qx, qy, slot);
 }
 // call index of the edge midpoint (x, y) of face f at level l, resolved on the face that draws it
+template <int KIND>
 __device__ inline uint32_t rock_point_call_index(const RockTopo& t, int depth, int f, int l, int x, int y)
 {
   const int W = 1 << depth, sh = depth - l;  // node width w = 1 << sh
-  int X, Y, Z;
-  cube_of(W, f, x, y, X, Y, Z);
-  for (int g = 0; g < 6; g++) {
+  int X = 0, Y = 0, Z = 0;
+  if (KIND == kRock) cube_of(W, f, x, y, X, Y, Z);
+  for (int g = 0; g < (KIND == kRock ? 6 : 2); g++) {
     int gx, gy;
-    if (!face_local(W, g, X, Y, Z, gx, gy)) continue;
+    if (KIND == kRock) {
+      if (!face_local(W, g, X, Y, Z, gx, gy)) continue;
+    } else {  // Cloud::element: the border of the upper sheet IS the border of the lower one
+      const bool border = x == 0 || y == 0 || x == W || y == W;
+      if (g != (border ? 0 : f)) continue;
+      gx = x; gy = y;
+    }
     if ((gx & ((1 << sh) - 1)) == 0) {  // on a vertical node side: right slot of the node on its left, left slot in column 0
       const int qy = gy >> sh;
       if (gx == 0) return rock_call_index(t, depth, g, l, 0, qy, 0);
@@ -110,6 +124,7 @@ __device__ inline uint32_t rock_point_call_index(const RockTopo& t, int depth, i
 
 // One level: the centres (Rock.cpp:179) and edge midpoints (:181-212) of all nodes of width W >> l, on the
 // half-step lattice of that level ((2n+1)^2 points per face; those with two even coordinates are older).
+template <int KIND>
 __global__ void k_rock_level(const __grid_constant__ RockParams rp, int l)
 {
   const int depth = rp.depth, W = 1 << depth, P = W + 1;
@@ -124,13 +139,14 @@ __global__ void k_rock_level(const __grid_constant__ RockParams rp, int l)
   float2* g = rp.faces + (size_t)f * P * P;
   float2 e;
   if (ox && oy) {
+    if (KIND == kCloud && g[(size_t)x * P + y].x != 0.0f) return;  // a preset control height (Cloud.cpp:64-73,131)
     const float2 a = g[(size_t)(x - h) * P + (y - h)], b = g[(size_t)(x + h) * P + (y - h)], c = g[(size_t)(x - h) * P + (y + h)],
                  d = g[(size_t)(x + h) * P + (y + h)];
     e.x = (a.x + b.x + c.x + d.x) * 0.25f;  // Rock.h:25-29
     e.y = (a.y + b.y + c.y + d.y) * 0.25f;
   } else {
     const float2 a = ox ? g[(size_t)(x - h) * P + y] : g[(size_t)x * P + (y - h)], b = ox ? g[(size_t)(x + h) * P + y] : g[(size_t)x * P + (y + h)];
-    const uint32_t k = rock_point_call_index(rp.topo, depth, f, l, x, y);
+    const uint32_t k = rock_point_call_index<KIND>(rp.topo, depth, f, l, x, y);
     const float r = random_from_draw(lcg_draw_from_state(lcg_skip(rp.state, k + 1u)));
     const float offset = rp.amplitude * r * (float)(2 * h) / (float)W;  // Rock.cpp:185: amplitude * random() * extent / maxWidth
     e.x = (a.x + b.x) * 0.5f + offset;                                   // Rock.h:30-34, Rock.cpp:186
@@ -140,10 +156,18 @@ __global__ void k_rock_level(const __grid_constant__ RockParams rp, int l)
   g[(size_t)x * P + y] = e;
 }
 
-__global__ void k_rock_init(float2* faces, size_t n)
+__global__ void k_rock_init(float2* faces, size_t n, int cloud_W)
 {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) faces[i] = make_float2(0.0f, 1.0f);  // Rock.cpp:57-60
+  if (i >= n) return;
+  float2 v = make_float2(0.0f, 1.0f);  // Rock.cpp:57-60, Cloud.cpp:59-60
+  if (cloud_W) {                       // Cloud.cpp:64-73: centre and quarter points of both sheets
+    const size_t P = (size_t)cloud_W + 1, per = P * P;
+    const int f = (int)(i / per), x = (int)((i % per) / P), y = (int)(i % P), q = cloud_W / 4;
+    const bool preset = (x == 2 * q && y == 2 * q) || ((x == q || x == 3 * q) && (y == q || y == 3 * q));
+    if (preset) v.x = f ? 0.5f : -0.5f;
+  }
+  faces[i] = v;
 }
 
 // ---- Cell attributes: Rock::generateRecursive (Rock.cpp:228-271) ----
@@ -166,9 +190,14 @@ __device__ inline V3 rock_normalise(V3 v)  // member normalise(), Vector3.h:109-
   const float d = __frcp_rn(f);
   return V3{v.x * d, v.y * d, v.z * d};
 }
-__device__ inline V3 rock_get_pos(const float2* g, int P, int W, int f, int x, int y)  // Rock.cpp:220-227
+template <int KIND>
+__device__ inline V3 rock_get_pos(const float2* g, int P, int W, int f, int x, int y)
 {
-  const V3 r = rock_normalise(rock_box_pos(W, f, x, y));
+  if (KIND == kCloud) {  // Cloud.cpp:106-113,167-173
+    const float fw = (float)W;
+    return V3{-1.f + __fdiv_rn(2.0f * (float)x, fw), 0.0f + g[(size_t)x * P + y].x, -1.f + __fdiv_rn(2.0f * (float)y, fw)};
+  }
+  const V3 r = rock_normalise(rock_box_pos(W, f, x, y));  // Rock.cpp:220-227
   const float s = 1.0f + g[(size_t)x * P + y].x;
   return V3{r.x * s, r.y * s, r.z * s};
 }
@@ -182,6 +211,7 @@ struct RockCell {  // rn_cell (include/rednoise.h)
   uint8_t level;
 };
 
+template <int KIND>
 __global__ void k_rock_cells(RockCell* __restrict__ out, const float2* __restrict__ faces, int depth, uint32_t count, float radius0)
 {
   const uint32_t e_all = blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,27 +228,28 @@ __global__ void k_rock_cells(RockCell* __restrict__ out, const float2* __restric
   for (int b = 0; b < l; b++) { qx |= ((m >> (2 * b)) & 1u) << b; qy |= ((m >> (2 * b + 1)) & 1u) << b; }
   const int w = W >> l;
   const int minX = qx * w, minY = qy * w, maxX = minX + w, maxY = minY + w, midX = minX + w / 2, midY = minY + w / 2;
-  V3 centre = rock_get_pos(g, P, W, f, midX, midY);
+  V3 centre = rock_get_pos<KIND>(g, P, W, f, midX, midY);
   centre = vmul(centre, 1.0f);  // `* size` with the constructor's size argument 1.0f (Rock.cpp:77,236)
   V3 position = centre;
   {  // cell->position -= parentPosWorldSpace: the parent's centre, (0,0,0) for the root PhysicalCell
     V3 parent{0.0f, 0.0f, 0.0f};
     if (l > 0) {
       const int pw = w * 2, pX = (qx >> 1) * pw + pw / 2, pY = (qy >> 1) * pw + pw / 2;
-      parent = vmul(rock_get_pos(g, P, W, f, pX, pY), 1.0f);
+      parent = vmul(rock_get_pos<KIND>(g, P, W, f, pX, pY), 1.0f);
     }
     position = vsub(position, parent);
   }
   const float shade = g[(size_t)midX * P + midY].y;
   RockCell c;
-  c.colour[0] = clampedf(0.6f * shade, 0.0f, 1.0f);
-  c.colour[1] = clampedf(0.54f * shade, 0.0f, 1.0f);
-  c.colour[2] = clampedf(0.48f * shade, 0.0f, 1.0f);
+  c.colour[0] = clampedf((KIND == kCloud ? 0.5f : 0.6f) * shade, 0.0f, 1.0f);   // Rock.cpp:240-242, Cloud.cpp:186-188
+  c.colour[1] = clampedf((KIND == kCloud ? 0.5f : 0.54f) * shade, 0.0f, 1.0f);
+  c.colour[2] = clampedf((KIND == kCloud ? 0.5f : 0.48f) * shade, 0.0f, 1.0f);
   c.position[0] = position.x; c.position[1] = position.y; c.position[2] = position.z;
-  const V3 xc = vsub(rock_get_pos(g, P, W, f, minX, minY), rock_get_pos(g, P, W, f, maxX, maxY));
-  const V3 yc = vsub(rock_get_pos(g, P, W, f, maxX, minY), rock_get_pos(g, P, W, f, minX, maxY));
+  const V3 xc = vsub(rock_get_pos<KIND>(g, P, W, f, minX, minY), rock_get_pos<KIND>(g, P, W, f, maxX, maxY));
+  const V3 yc = vsub(rock_get_pos<KIND>(g, P, W, f, maxX, minY), rock_get_pos<KIND>(g, P, W, f, minX, maxY));
   V3 normal = vcross(xc, yc);
-  if (normal.x * centre.x + normal.y * centre.y + normal.z * centre.z < 0.0f) normal = V3{-normal.x, -normal.y, -normal.z};
+  const bool flip = KIND == kCloud ? f == 1 : normal.x * centre.x + normal.y * centre.y + normal.z * centre.z < 0.0f;  // Cloud.cpp:199, Rock.cpp:250
+  if (flip) normal = V3{-normal.x, -normal.y, -normal.z};
   normal = rock_normalise(normal);
   c.normal[0] = (int8_t)(int)(normal.x * 127.0f);
   c.normal[1] = (int8_t)(int)(normal.y * 127.0f);
@@ -241,23 +272,26 @@ uint64_t rock_draw_count(int depth)
   return 4 * W * W - 4;
 }
 
-// faces: device, 6 x (W+1)^2 float2; cells: device or nullptr, 6 x (4^depth - 1)/3 rn_cell; flag: device int (collision)
-cudaError_t rock_generate(void* faces_v, void* cells_v, int* flag, int depth, uint32_t state, float amplitude, cudaStream_t stream,
+// faces: device, nfaces x (W+1)^2 float2 (6 for a rock, 2 for a cloud); cells: device or nullptr, nfaces x (4^depth - 1)/3 rn_cell;
+// flag: device int (collision)
+cudaError_t rock_generate(void* faces_v, void* cells_v, int* flag, int kind, int depth, uint32_t state, float amplitude, cudaStream_t stream,
                           uint64_t* launches)
 {
   float2* faces = static_cast<float2*>(faces_v);
-  const int W = 1 << depth;
-  const size_t P = (size_t)W + 1, nall = 6 * P * P;
+  const int W = 1 << depth, nfaces = kind == kCloud ? 2 : 6;
+  const size_t P = (size_t)W + 1, nall = (size_t)nfaces * P * P;
   RockParams rp;
   rp.faces = faces; rp.depth = depth; rp.state = state; rp.amplitude = amplitude; rp.collision = flag;
-  {  // which sides of a face were drawn by an earlier face (cube topology of Rock::element), and the faces' first call
+  {  // which sides of a face were drawn by an earlier face (cube topology of Rock::element / shared border of Cloud::element),
+     // and the faces' first call
     const int sx[4] = {0, W, W / 2, W / 2}, sy[4] = {W / 2, W / 2, 0, W};
     uint32_t acc = 0;
     for (int f = 0; f < 6; f++) {
       for (int s = 0; s < 4; s++) {
+        rp.topo.pre[f][s] = 0;
+        if (kind == kCloud) { rp.topo.pre[f][s] = f == 1; continue; }
         int X, Y, Z, x, y;
         cube_of(W, f, sx[s], sy[s], X, Y, Z);
-        rp.topo.pre[f][s] = 0;
         for (int g = 0; g < f; g++)
           if (face_local(W, g, X, Y, Z, x, y)) rp.topo.pre[f][s] = 1;
       }
@@ -267,23 +301,33 @@ cudaError_t rock_generate(void* faces_v, void* cells_v, int* flag, int depth, ui
   }
   cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), stream);
   if (e != cudaSuccess) return e;
-  k_rock_init<<<(unsigned)((nall + 255) / 256), 256, 0, stream>>>(faces, nall);
+  k_rock_init<<<(unsigned)((nall + 255) / 256), 256, 0, stream>>>(faces, nall, kind == kCloud ? W : 0);
   uint64_t nl = 1;
   for (int l = 0; l < depth; l++) {
     const int n2 = (2 << l) + 1;
-    const dim3 block(32, 8), grid((n2 + 31) / 32, (n2 + 7) / 8, 6);
-    k_rock_level<<<grid, block, 0, stream>>>(rp, l);
+    const dim3 block(32, 8), grid((n2 + 31) / 32, (n2 + 7) / 8, nfaces);
+    if (kind == kCloud) k_rock_level<kCloud><<<grid, block, 0, stream>>>(rp, l);
+    else k_rock_level<kRock><<<grid, block, 0, stream>>>(rp, l);
     nl++;
   }
   if (cells_v) {
     uint32_t count = 0;
     for (int l = 0; l < depth; l++) count += 1u << (2 * l);
-    const float radius0 = 1.4f * sqrtf((1.0f + 0.5f * amplitude) * 0.5f);  // Rock.cpp:76
-    k_rock_cells<<<dim3((count + 127) / 128, 6), 128, 0, stream>>>(static_cast<RockCell*>(cells_v), faces, depth, count, radius0);
+    const float radius0 = (kind == kCloud ? 1.8f : 1.4f) * sqrtf((1.0f + 0.5f * amplitude) * 0.5f);  // Rock.cpp:76, Cloud.cpp:84
+    const dim3 grid((count + 127) / 128, nfaces);
+    if (kind == kCloud) k_rock_cells<kCloud><<<grid, 128, 0, stream>>>(static_cast<RockCell*>(cells_v), faces, depth, count, radius0);
+    else k_rock_cells<kRock><<<grid, 128, 0, stream>>>(static_cast<RockCell*>(cells_v), faces, depth, count, radius0);
     nl++;
   }
   if (launches) *launches += nl;
   return cudaGetLastError();
+}
+
+uint64_t cloud_draw_count(int depth)  // the lower sheet draws every edge midpoint of its closed square, the upper one all but the border
+{
+  const uint64_t W = (uint64_t)1 << depth;
+  const uint64_t E = (W + 1) * (W + 1) - 4 - ((((uint64_t)1 << (2 * depth)) - 1) / 3);
+  return 2 * E - 4 * (W - 1);
 }
 
 }  // namespace rn

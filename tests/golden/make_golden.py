@@ -68,6 +68,16 @@ def main():
             e["faces_bits"] = faces.view(np.uint32).reshape(-1).tolist()
             e["cells_bits"] = cells.view(np.uint32).reshape(-1).tolist()
         out["rocks"].append(e)
+    # Cloud (Cloud::generateBaseRecursive on two sheets + Cloud::generateRecursive, run by the reference itself)
+    out["clouds"] = []
+    for depth, state in [(2, 12345), (3, 7), (4, 12345), (5, 99), (7, 12345), (7, 0xDEADBEEF), (8, 4242), (10, 12345)]:
+        faces, cells, draws, state_after = ref.cloud(state, depth, 0.3)
+        e = {"depth": depth, "state": state, "amplitude": 0.3, "rand_calls": draws, "state_after": state_after,
+             "fnv64_faces": fnv64(faces), "fnv64_cells": fnv64(cells.view(np.uint8))}
+        if depth <= 2:
+            e["faces_bits"] = faces.view(np.uint32).reshape(-1).tolist()
+            e["cells_bits"] = cells.view(np.uint32).reshape(-1).tolist()
+        out["clouds"].append(e)
     for seed in (1, 12345, 0, 0xFFFFFFFF):
         out["lcg_kat"][str(seed)] = ref.lcg_draws(seed, 16).tolist()
     path = os.path.join(HERE, "terrain2d_golden.json")

@@ -98,6 +98,8 @@ class Oracle:
         L.rno_rock_draw_count.argtypes = [C.c_int]
         L.rno_rock.restype = C.c_longlong
         L.rno_rock.argtypes = [C.c_uint32, C.c_int, C.c_float, C.c_float, vp, vp, vp]
+        L.rno_cloud.restype = C.c_longlong
+        L.rno_cloud.argtypes = [C.c_uint32, C.c_int, C.c_float, vp, vp, vp]
         L.rno_rock_indexed.restype = C.c_longlong
         L.rno_rock_indexed.argtypes = [C.c_uint32, C.c_int, C.c_float, vp, vp]
         L.rno_fnv64.restype = C.c_uint64
@@ -158,6 +160,17 @@ class Oracle:
             raise RuntimeError(f"oracle status {n}")
         return faces, cells, int(n), int(st.value)
 
+    def cloud(self, state: int, depth: int, amplitude: float = 0.3, want_cells: bool = True):
+        """Cloud.cpp restated: (faces[2, W+1, W+1, 2], cells[2, count], draws, state_after)."""
+        S = (1 << depth) + 1
+        faces = np.empty((2, S, S, 2), np.float32)
+        cells = np.zeros((2, cell_count(depth)), CELL_DTYPE) if want_cells else None
+        st = C.c_uint32(0)
+        n = self.L.rno_cloud(state & 0xFFFFFFFF, depth, amplitude, faces.ctypes.data, cells.ctypes.data if want_cells else None, C.byref(st))
+        if n < 0:
+            raise RuntimeError(f"oracle status {n}")
+        return faces, cells, int(n), int(st.value)
+
     def rock_indexed(self, state: int, depth: int, amplitude: float = 0.3):
         """Closed-form call indices + breadth-first levels (the CUDA formulation): (faces, status, state_after)."""
         S = (1 << depth) + 1
@@ -182,6 +195,9 @@ class Ref:
         L.ref_terrain_cells.argtypes = [C.c_int, C.c_float, C.c_float, C.c_uint, C.c_void_p, C.c_void_p]
         L.ref_random_from_state.restype = C.c_float
         L.ref_random_from_state.argtypes = [C.c_uint]
+        if hasattr(L, "ref_cloud"):
+            L.ref_cloud.restype = C.c_longlong
+            L.ref_cloud.argtypes = [C.c_uint, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         if hasattr(L, "ref_rock"):
             L.ref_rock.restype = C.c_longlong
             L.ref_rock.argtypes = [C.c_uint, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -212,6 +228,16 @@ class Ref:
         cells = np.zeros((6, cell_count(depth)), CELL_DTYPE)
         st = C.c_uint(0)
         n = self.L.ref_rock(state & 0xFFFFFFFF, depth, amplitude, faces.ctypes.data, cells.ctypes.data, C.byref(st))
+        if n < 0:
+            raise RuntimeError(f"reference harness returned {n}")
+        return faces, cells, int(n), int(st.value)
+
+    def cloud(self, state, depth, amplitude=0.3):
+        S = (1 << depth) + 1
+        faces = np.empty((2, S, S, 2), np.float32)
+        cells = np.zeros((2, cell_count(depth)), CELL_DTYPE)
+        st = C.c_uint(0)
+        n = self.L.ref_cloud(state & 0xFFFFFFFF, depth, amplitude, faces.ctypes.data, cells.ctypes.data, C.byref(st))
         if n < 0:
             raise RuntimeError(f"reference harness returned {n}")
         return faces, cells, int(n), int(st.value)

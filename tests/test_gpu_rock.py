@@ -71,3 +71,29 @@ def test_rock_rejects_bad_arguments(ctx):
         ctx.rock_host(1, 13)
     with pytest.raises(Exception):
         ctx.rock_ptr(1, 4, 0.3, 0, 0)
+
+
+# ---- Cloud (rn_cloud), the two-face variant ----
+@pytest.mark.parametrize("depth", [2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("state", [12345, 1, 0xDEADBEEF])
+def test_cloud_equals_oracle(ctx, oracle, depth, state):
+    fo, co, draws, so = oracle.cloud(state, depth, 0.3)
+    fg, cg, sg = ctx.rock_host(state, depth, 0.3, cloud=True)
+    from rednoise_b200 import capi
+    assert draws == capi.lib().rn_cloud_draw_count(depth)
+    assert sg == so
+    assert np.array_equal(fo.view(np.uint32), fg.view(np.uint32))
+    assert co.tobytes() == cg.tobytes()
+
+
+@pytest.mark.parametrize("entry", GOLD.get("clouds", []), ids=lambda e: f"d{e['depth']}-s{e['state']}")
+def test_cloud_golden(ctx, oracle, entry):
+    faces, cells, after = ctx.rock_host(entry["state"], entry["depth"], entry["amplitude"], cloud=True)
+    assert after == entry["state_after"]
+    assert oracle.fnv64(faces) == entry["fnv64_faces"]
+    assert oracle.fnv64(cells.view(np.uint8)) == entry["fnv64_cells"]
+
+
+def test_cloud_rejects_depth_1(ctx):
+    with pytest.raises(Exception):
+        ctx.rock_host(1, 1, cloud=True)

@@ -59,3 +59,36 @@ def test_rock_shared_edges_agree(oracle):
     for f in range(6):
         for x, y in ((0, 0), (0, W), (W, 0), (W, W)):
             assert faces[f, x, y, 0] == 0.0 and faces[f, x, y, 1] == 1.0
+
+
+# ---- Cloud (Cloud.cpp), the two-face variant ----
+@pytest.mark.parametrize("depth,state", [(2, 1), (3, 12345), (4, 5), (5, 12345), (6, 31337), (7, 12345), (8, 777), (9, 2)])
+def test_cloud_restatement_equals_reference(oracle, ref, depth, state):
+    fr, cr, nr, sr = ref.cloud(state, depth, 0.3)
+    fo, co, no, so = oracle.cloud(state, depth, 0.3)
+    assert (no, so) == (nr, sr)
+    assert np.array_equal(fr.view(np.uint32), fo.view(np.uint32))
+    assert cr.tobytes() == co.tobytes()
+
+
+@pytest.mark.parametrize("entry", GOLD.get("clouds", []), ids=lambda e: f"d{e['depth']}-s{e['state']}")
+def test_cloud_golden(oracle, entry):
+    faces, cells, draws, state_after = oracle.cloud(entry["state"], entry["depth"], entry["amplitude"])
+    assert draws == entry["rand_calls"] and state_after == entry["state_after"]
+    assert oracle.fnv64(faces) == entry["fnv64_faces"]
+    assert oracle.fnv64(cells.view(np.uint8)) == entry["fnv64_cells"]
+    if "faces_bits" in entry:
+        assert faces.view(np.uint32).reshape(-1).tolist() == entry["faces_bits"]
+        assert cells.view(np.uint32).reshape(-1).tolist() == entry["cells_bits"]
+
+
+def test_cloud_presets_and_shared_border(oracle):
+    faces, _, draws, _ = oracle.cloud(12345, 5, 0.3, want_cells=False)
+    W = 32
+    for f, v in ((0, -0.5), (1, 0.5)):
+        for x, y in ((W // 2, W // 2), (W // 4, W // 4), (3 * W // 4, W // 4), (W // 4, 3 * W // 4), (3 * W // 4, 3 * W // 4)):
+            assert faces[f, x, y, 0] == v and faces[f, x, y, 1] == 1.0
+    for sl in ((0, slice(None)), (W, slice(None)), (slice(None), 0), (slice(None), W)):
+        assert np.array_equal(faces[0][sl].view(np.uint32), faces[1][sl].view(np.uint32))
+    E = (W + 1) ** 2 - 4 - (4 ** 5 - 1) // 3
+    assert draws == 2 * E - 4 * (W - 1)

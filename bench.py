@@ -47,7 +47,7 @@ def alu_roofline(args, value_gs, kernel_ms, my_samples, sm_mhz):
     committed capture (profiles/r01x_stream_kernel_ncu_metrics.json) against 148 SMs x 4 schedulers x 32 lanes x the SM clock
     seen during this run.  The bit-exact contract forbids FMA contraction, so this bound sits below the HBM-write bound."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01o_stream_kernel_ncu_metrics.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01x_stream_kernel_ncu_metrics.json")))
         if args.workload != "field" or args.depth != 12:
             return None
         warp_inst = float(d["smsp__inst_executed.sum"][0])

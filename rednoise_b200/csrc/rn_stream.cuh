@@ -28,6 +28,10 @@
 #pragma once
 #include "rn_tile.cuh"
 
+#ifndef RN_STREAM_CARRY
+#define RN_STREAM_CARRY 6   // (6 measured best: bit 0 costs spills at 64 registers) bit 0: K(u+1,c) from the prefetch register, bit 1: K(u,c), C(u,c) interval 1 -> 2, bit 2: K(u-1,c), C(u-1,c) interval 2 -> 3
+#endif
+
 namespace rn {
 
 struct StreamParams {
@@ -60,7 +64,11 @@ struct StreamParams {
 // registers of one thread that live across barrier intervals
 struct StreamThread {
   uint32_t sS, sD1, sD2;  // LCG states whose extraction is the draw of this column's next S / loop-1 / loop-2 call
-  E4 pre;                 // prefetched lattice point of row u+2 in this thread's column
+  E4 pre;                 // prefetched lattice point of row u+2 in this thread's column (kept until it is K(u+1, c) of the next step)
+  // lean instantiation: values of the thread's own column that the next interval would otherwise re-read from shared memory
+  // (the kernel is bound by the shared-memory pipe)
+  E4 own_k, own_c;        // K(u, c) and C(u, c) from interval 1 for interval 2
+  E4 own_km, own_cm;      // K(u-1, c) and C(u-1, c) from interval 2 for interval 3
   const E4* pre_src;      // where the next prefetch reads (advances one lattice row per step)
   E4* out_dst;            // output row 2a, column out_j of the next cell row to be stored (advances two rows per store)
   float sg0, sg1;         // shade of corners K(u,c) / K(u-1,c) after generateSquare's scatter (carried from step to step)
@@ -235,6 +243,7 @@ struct Stream {
     if (loader(cx, c)) {
       load_row_now(sp, cx, sm, u0, c);
       load_row_now(sp, cx, sm, u0 + 1, c);
+      if (lattice_exists(sp, cx, u0 + 1, c)) th.pre = lattice(sp, cx, u0 + 1, c);  // K(u0+1, c): interval 1 of the first step reads it from here
     }
   }
 
@@ -305,12 +314,14 @@ struct Stream {
       if (ex) {
         // S(u): averageSquare (Terrain.cpp:216-222) + generateSquare (:224-258)
         const int r0 = G::KROW + ring<PH>(t, 0, 4) * G::P, r1 = G::KROW + ring<PH>(t, 1, 4) * G::P;
-        const E4 k00 = *e4(sm, r0, c), k01 = *e4(sm, r0, c + 1), k10 = *e4(sm, r1, c), k11 = *e4(sm, r1, c + 1);
+        const E4 k00 = *e4(sm, r0, c), k01 = *e4(sm, r0, c + 1), k10 = (EDGE || !(RN_STREAM_CARRY & 1)) ? *e4(sm, r1, c) : th.pre, k11 = *e4(sm, r1, c + 1);
         const E4 a4 = avg4_packed(k00, k10, k01, k11);
         const V3 avg = pos4(a4);
         const float sh = a4.w;
         const Displaced dp = displace<true>(sp.law, avg, vsub(pos4(k11), pos4(k00)), vsub(pos4(k10), pos4(k01)), sp.lev.blahS, draw);
-        *e4(sm, G::CROW + ring<PH>(t, 0, 2) * G::P, c) = e4_of(dp.pos, sh + shade_gain(sp.law, dp.offset));
+        const E4 cnew = e4_of(dp.pos, sh + shade_gain(sp.law, dp.offset));
+        *e4(sm, G::CROW + ring<PH>(t, 0, 2) * G::P, c) = cnew;
+        if (!EDGE && (RN_STREAM_CARRY & 2)) { th.own_k = k00; th.own_c = cnew; }
         loss = shade_loss(sp.law, dp.offset);
       }
       *f32(sm, G::TS + ring<PH>(t, 0, 4) * G::P, c) = loss;
@@ -344,21 +355,22 @@ struct Stream {
     const int ts1 = G::TS + ring<PH>(t, -1, 4) * G::P, ts0 = G::TS + ring<PH>(t, 0, 4) * G::P;
     const int kr = G::KROW + ring<PH>(t, 0, 4) * G::P;
     const float t10 = *f32(sm, ts1, c), t00 = *f32(sm, ts0, c);
-    E4 k00 = *e4(sm, kr, c);  // K(u, c)
+    E4 k00 = (EDGE || !(RN_STREAM_CARRY & 2)) ? *e4(sm, kr, c) : th.own_k;  // K(u, c)
     k00.w = (((k00.w - *f32(sm, ts1, c - 1)) - t10) - *f32(sm, ts0, c - 1)) - t00;
     th.sg1 = th.sg0;   // sg(u-1, c)
     th.sg0 = k00.w;    // sg(u, c)
     if (!EDGE) {
       // both midpoints exist and have all four neighbours: one packed evaluation (rn_tile.cuh mid_interior2)
       const int krm = G::KROW + ring<PH>(t, -1, 4) * G::P;
-      const int cr = G::CROW + ring<PH>(t, 0, 2) * G::P, crm = G::CROW + ring<PH>(t, -1, 2) * G::P;
+      const int crm = G::CROW + ring<PH>(t, -1, 2) * G::P;
       E4 k01 = *e4(sm, kr, c + 1);
       k01.w = (((k01.w - t10) - *f32(sm, ts1, c + 1)) - t00) - *f32(sm, ts0, c + 1);
       E4 km = *e4(sm, krm, c);  // K(u-1, c)
       km.w = th.sg1;
       const E4 cm = *e4(sm, crm, c);  // C(u-1, c): x neighbour of M1, y neighbour of M2
       E4 m1, m2;
-      mid_interior2(sp.law, cm, *e4(sm, cr, c), k00, k01, km, k00, *e4(sm, crm, c - 1), cm, sp.lev.blahD, draw1, draw2, &m1, &m2, &loss1, &loss2);
+      if (RN_STREAM_CARRY & 4) { th.own_km = km; th.own_cm = cm; }
+      mid_interior2(sp.law, cm, (RN_STREAM_CARRY & 2) ? th.own_c : *e4(sm, G::CROW + ring<PH>(t, 0, 2) * G::P, c), k00, k01, km, k00, *e4(sm, crm, c - 1), cm, sp.lev.blahD, draw1, draw2, &m1, &m2, &loss1, &loss2);
       *e4(sm, G::M1ROW + ring<PH>(t, 0, 2) * G::P, c) = m1;
       *e4(sm, G::M2ROW, c) = m2;
     } else if (v1 || v2) {
@@ -405,7 +417,7 @@ struct Stream {
       const int td2mm = G::TD2 + ring<PH>(t, -2, 2) * G::P, td2m = G::TD2 + ring<PH>(t, -1, 2) * G::P;
       if (!EDGE || (u - 1 >= 0 && u - 1 <= n && bg >= 0 && bg <= n)) {
         // corner K(u-1, c): generateSquare's scatter (carried sg), then loop 1 (same row), loop 2 (same column)
-        E4 k = *e4(sm, G::KROW + ring<PH>(t, -1, 4) * G::P, c);
+        E4 k = (EDGE || !(RN_STREAM_CARRY & 4)) ? *e4(sm, G::KROW + ring<PH>(t, -1, 4) * G::P, c) : th.own_km;
         float sh = th.sg1;
         sh -= *f32(sm, td1m, c - 1);
         sh -= *f32(sm, td1m, c);
@@ -416,7 +428,7 @@ struct Stream {
       }
       if (!EDGE || (u - 1 >= 0 && u - 1 < n && bg >= 0 && bg < n)) {
         // centre C(u-1, c): loop-1 mids above and below, loop-2 mids left and right
-        E4 ce = *e4(sm, G::CROW + ring<PH>(t, -1, 2) * G::P, c);
+        E4 ce = (EDGE || !(RN_STREAM_CARRY & 4)) ? *e4(sm, G::CROW + ring<PH>(t, -1, 2) * G::P, c) : th.own_cm;
         float shc = ce.w;
         shc -= *f32(sm, td1m, c);
         shc -= *f32(sm, td10, c);

@@ -38,7 +38,10 @@ constexpr int kStreamMinDepth = 10;   // ... when the field is at least this dee
 constexpr int kStreamThreadsSmall = 64;   // narrower strips for small levels (more CTAs, fewer warm-up rows per sample)
 constexpr int kStreamMinBlocksSmall = 14;
 constexpr float kStreamEdgeCost = 1.28f;  // duration of a border-strip CTA relative to an interior one with the same rows
-constexpr int kStreamSmallCols = 1536;    // levels with fewer cell columns than this use the small configuration
+#ifndef RN_STREAM_SMALL_COLS
+#define RN_STREAM_SMALL_COLS 1024
+#endif
+constexpr int kStreamSmallCols = RN_STREAM_SMALL_COLS;    // levels with fewer cell columns than this use the small configuration
 constexpr int kTile = 64;  // output tile edge of every stage
 
 struct StagePlan {

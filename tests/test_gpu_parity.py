@@ -293,3 +293,19 @@ def test_depth12_against_oracle(ctx, rnlib, oracle):
     got = ctx.terrain2d_host(p)
     want = oracle.terrain2d(oracle_lib.params(seed=31337, depth=12, apply_volcano=1))
     assert_bitwise(got, want, "depth 12 seed 31337")
+
+
+def test_depth12_windows_of_every_strip_layout(ctx, rnlib, oracle):
+    """The streamed output level cuts a window into column strips (border strips into shorter segments): one strip, strips that
+    touch no border, only the left / right / top / bottom border, single rows and columns -- all seam-exact against the whole field."""
+    ctx.set_algorithm(0)
+    depth, seed = 12, 2718
+    S = (1 << depth) + 1
+    p = rnlib.default_params(seed=seed, depth=depth, apply_volcano=1)
+    full = oracle.terrain2d(oracle_lib.params(seed=seed, depth=depth, apply_volcano=1))
+    wins = [(1000, 1000, 300, 200), (1000, 1000, 64, 1500), (0, 1500, 500, 700), (S - 300, 2000, 300, 900), (1500, 0, 700, 260),
+            (1500, S - 260, 700, 260), (0, 0, 257, 257), (S - 129, S - 129, 129, 129), (2047, 2047, 3, 3), (2048, 0, 1, S), (0, 2048, S, 1),
+            (100, 3, 2200, 4000)]
+    for (i0, j0, ni, nj) in wins:
+        got = ctx.terrain2d_host(p, window=rnlib.Window(i0, j0, ni, nj))
+        assert_bitwise(got, full[i0:i0 + ni, j0:j0 + nj], f"depth 12 window {(i0, j0, ni, nj)}")

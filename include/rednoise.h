@@ -187,10 +187,11 @@ int rn_terrain2d_cells(rn_context* ctx, const rn_params* p, const rn_element* fi
  *          recursion's visiting order (children 4e..4e+3 of node e), with position relative to the parent, colour,
  *          quantised normal and radius of Rock.cpp:236-262.  The root PhysicalCell (:69,82-89) is scene graph and
  *          stays with the caller.  May be NULL.
- * The reference decides with `height == 0.0f` whether an edge midpoint still has to be displaced (:181-212); a
- * displaced height that is exactly 0.0f would be drawn again there.  This implementation addresses every rand()
- * call by index instead; it detects that case and returns RN_ERR_UNSUPPORTED rather than different samples.  The call
- * synchronises `stream` (the status needs the device's answer). */
+ * The reference decides with `height == 0.0f` whether an edge midpoint still has to be displaced (:181-212).  This
+ * implementation addresses every rand() call by a closed-form index and evaluates the levels in parallel; when a
+ * displaced height comes out exactly 0.0f (about 1 rock in 500) the reference's next visitor draws again and the call
+ * sequence becomes value-dependent, so the rock is regenerated by the literal recursion on one device thread (slower,
+ * same samples as the reference, more rand() calls than rn_rock_draw_count).  The call synchronises `stream`. */
 #define RN_ROCK_MIN_DEPTH 1
 #define RN_ROCK_MAX_DEPTH 12
 typedef struct rn_rock_params {

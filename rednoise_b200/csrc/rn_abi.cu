@@ -643,17 +643,26 @@ int rock_or_cloud(rn_context* ctx, int kind, const rn_rock_params* p, rn_rock_el
     if (st != RN_OK) return st;
     dcells = ctx->cells;
   }
-  RN_CUDA(rock_generate(dfaces, dcells, (int*)ctx->small, kind, p->depth, p->lcg_state, p->amplitude, stream, &ctx->launches));
+  uint64_t draws = kind ? cloud_draw_count(p->depth) : rock_draw_count(p->depth);
+  RN_CUDA(rock_generate(dfaces, dcells, (int*)ctx->small, kind, p->depth, p->lcg_state, p->amplitude, 0, stream, &ctx->launches));
+  int collision = 0;
+  RN_CUDA(cudaMemcpyAsync(&collision, ctx->small, sizeof collision, cudaMemcpyDeviceToHost, stream));
+  RN_CUDA(cudaStreamSynchronize(stream));
+  if (collision) {
+    // a displaced height is exactly 0.0f: the reference's `height == 0.0f` test (Rock.cpp:181, Cloud.cpp:134) draws again and the
+    // call sequence becomes value-dependent -- regenerate with the literal one-thread recursion on the device
+    RN_CUDA(rock_generate(dfaces, dcells, (int*)ctx->small, kind, p->depth, p->lcg_state, p->amplitude, 1, stream, &ctx->launches));
+    unsigned long long n = 0;
+    RN_CUDA(cudaMemcpyAsync(&n, ctx->small, sizeof n, cudaMemcpyDeviceToHost, stream));
+    RN_CUDA(cudaStreamSynchronize(stream));
+    draws = n;
+  }
   if (faces && dfaces != faces)
     RN_CUDA(cudaMemcpyAsync(faces, dfaces, face_bytes, dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
   if (cells && dcells != cells)
     RN_CUDA(cudaMemcpyAsync(cells, dcells, ncells * sizeof(rn_cell), dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
-  int collision = 0;
-  RN_CUDA(cudaMemcpyAsync(&collision, ctx->small, sizeof collision, cudaMemcpyDeviceToHost, stream));
   RN_CUDA(cudaStreamSynchronize(stream));
-  if (collision)
-    return fail(RN_ERR_UNSUPPORTED, "a displaced height is exactly 0.0f: the reference's `height == 0.0f` test (Rock.cpp:181, Cloud.cpp:134) would draw again");
-  if (lcg_state_after) *lcg_state_after = rn_lcg_state_after(p->lcg_state, kind ? cloud_draw_count(p->depth) : rock_draw_count(p->depth));
+  if (lcg_state_after) *lcg_state_after = rn_lcg_state_after(p->lcg_state, draws);
   return RN_OK;
 }
 }  // namespace

@@ -27,8 +27,10 @@ cudaError_t cells_generate(void* cells, const Elem* field, size_t pitch, int dep
 // kind 0 = Rock (6 faces), 1 = Cloud (Cloud.cpp: 2 sheets sharing their border, preset control heights).
 uint64_t rock_draw_count(int depth);
 uint64_t cloud_draw_count(int depth);
-cudaError_t rock_generate(void* faces, void* cells, int* flag, int kind, int depth, uint32_t state, float amplitude, cudaStream_t stream,
-                          uint64_t* launches);
+// flag: 16 bytes of device memory.  sequential = 0: the index-addressed parallel path, flag[0] (int) is set when a displaced height is exactly
+// 0.0f (then the result is not the reference's); sequential = 1: the literal one-thread recursion, *(uint64*)flag = rand() calls made.
+cudaError_t rock_generate(void* faces, void* cells, int* flag, int kind, int depth, uint32_t state, float amplitude, int sequential,
+                          cudaStream_t stream, uint64_t* launches);
 
 // 3D density-volume extension (rn_volume.cu; defined by the CPU specification of DESIGN.md section 5.8, no reference counterpart):
 // planes [i0, i0+ni) of the (W+1)^3 float volume d (full-volume layout).

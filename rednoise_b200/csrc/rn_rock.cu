@@ -170,6 +170,90 @@ __global__ void k_rock_init(float2* faces, size_t n, int cloud_W)
   faces[i] = v;
 }
 
+// ---- The literal algorithm, for the rare inputs whose draws are value-dependent ----
+// When a displaced height is exactly 0.0f the reference's next visitor of that sample draws again (Rock.cpp:181-212), the
+// subtree visited in between has used the first value, and every later call index moves: there is no closed form.  Those
+// inputs (about 1 rock in 500) are generated by ONE thread that runs the reference's recursion itself -- same visiting order,
+// same tests -- on the storage Rock::element / Cloud::element resolve to (here: the lowest-numbered face that contains the
+// sample), after which k_rock_resolve copies the shared samples into every face's view.  Slow (tens of ms at depth 7), exact.
+template <int KIND>
+__device__ inline float2* rock_canon(float2* faces, int W, int f, int x, int y)
+{
+  const size_t P = (size_t)W + 1;
+  if (KIND == kCloud) {
+    const bool border = x == 0 || y == 0 || x == W || y == W;
+    return faces + ((size_t)(border ? 0 : f) * P + (size_t)x) * P + (size_t)y;
+  }
+  int X, Y, Z;
+  cube_of(W, f, x, y, X, Y, Z);
+  for (int g = 0; g < 6; g++) {
+    int gx, gy;
+    if (face_local(W, g, X, Y, Z, gx, gy)) return faces + ((size_t)g * P + (size_t)gx) * P + (size_t)gy;
+  }
+  return faces;
+}
+
+template <int KIND>
+__device__ inline void rock_seq_edge(const RockParams& rp, int W, int f, int x, int y, int ax, int ay, int bx, int by, int extent, uint32_t& state,
+                                     unsigned long long& draws)
+{
+  float2* el = rock_canon<KIND>(rp.faces, W, f, x, y);
+  if (el->x == 0.0f) {
+    const float2 a = *rock_canon<KIND>(rp.faces, W, f, ax, ay), b = *rock_canon<KIND>(rp.faces, W, f, bx, by);
+    state = state * kLcgA + kLcgC;
+    draws++;
+    const float offset = rp.amplitude * random_from_draw(lcg_draw_from_state(state)) * (float)extent / (float)W;
+    *el = make_float2((a.x + b.x) * 0.5f + offset, (a.y + b.y) * 0.5f + offset * 1.5f);
+  }
+}
+
+template <int KIND>
+__global__ void k_rock_sequential(const __grid_constant__ RockParams rp, unsigned long long* draws_out)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int W = 1 << rp.depth;
+  uint32_t state = rp.state;
+  unsigned long long draws = 0;
+  for (int f = 0; f < (KIND == kCloud ? 2 : 6); f++) {
+    int sx[48], sy[48], sw[48];  // pre-order stack: at most 3 pending siblings per level
+    int sp = 0;
+    sx[0] = 0; sy[0] = 0; sw[0] = W; sp = 1;
+    while (sp > 0) {
+      sp--;
+      const int x0 = sx[sp], y0 = sy[sp], w = sw[sp];
+      if (w <= 1) continue;
+      const int h = w >> 1, x1 = x0 + w, y1 = y0 + w, mx = x0 + h, my = y0 + h;
+      float2* m = rock_canon<KIND>(rp.faces, W, f, mx, my);
+      if (KIND == kRock || m->x == 0.0f) {  // Rock.cpp:179 / Cloud.cpp:131-132
+        const float2 a = *rock_canon<KIND>(rp.faces, W, f, x0, y0), b = *rock_canon<KIND>(rp.faces, W, f, x1, y0),
+                     c = *rock_canon<KIND>(rp.faces, W, f, x0, y1), d = *rock_canon<KIND>(rp.faces, W, f, x1, y1);
+        *m = make_float2((a.x + b.x + c.x + d.x) * 0.25f, (a.y + b.y + c.y + d.y) * 0.25f);
+      }
+      rock_seq_edge<KIND>(rp, W, f, x0, my, x0, y0, x0, y1, w, state, draws);
+      rock_seq_edge<KIND>(rp, W, f, x1, my, x1, y0, x1, y1, w, state, draws);
+      rock_seq_edge<KIND>(rp, W, f, mx, y0, x1, y0, x0, y0, w, state, draws);
+      rock_seq_edge<KIND>(rp, W, f, mx, y1, x1, y1, x0, y1, w, state, draws);
+      // children in the order of Rock.cpp:213-216 (pushed in reverse)
+      sx[sp] = mx; sy[sp] = my; sw[sp] = h; sp++;
+      sx[sp] = x0; sy[sp] = my; sw[sp] = h; sp++;
+      sx[sp] = mx; sy[sp] = y0; sw[sp] = h; sp++;
+      sx[sp] = x0; sy[sp] = y0; sw[sp] = h; sp++;
+    }
+  }
+  *draws_out = draws;
+}
+
+template <int KIND>
+__global__ void k_rock_resolve(float2* faces, int W, size_t n)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t P = (size_t)W + 1, per = P * P;
+  const int f = (int)(i / per), x = (int)((i % per) / P), y = (int)(i % P);
+  const float2* src = rock_canon<KIND>(faces, W, f, x, y);
+  if (src != faces + i) faces[i] = *src;
+}
+
 // ---- Cell attributes: Rock::generateRecursive (Rock.cpp:228-271) ----
 __device__ inline V3 rock_box_pos(int W, int f, int x, int y)  // Rock.cpp:100-124
 {
@@ -274,8 +358,9 @@ uint64_t rock_draw_count(int depth)
 
 // faces: device, nfaces x (W+1)^2 float2 (6 for a rock, 2 for a cloud); cells: device or nullptr, nfaces x (4^depth - 1)/3 rn_cell;
 // flag: device int (collision)
-cudaError_t rock_generate(void* faces_v, void* cells_v, int* flag, int kind, int depth, uint32_t state, float amplitude, cudaStream_t stream,
-                          uint64_t* launches)
+// sequential != 0: the literal one-thread path (k_rock_sequential); flag then receives the rand() call count as an unsigned long long
+cudaError_t rock_generate(void* faces_v, void* cells_v, int* flag, int kind, int depth, uint32_t state, float amplitude, int sequential,
+                          cudaStream_t stream, uint64_t* launches)
 {
   float2* faces = static_cast<float2*>(faces_v);
   const int W = 1 << depth, nfaces = kind == kCloud ? 2 : 6;
@@ -299,11 +384,22 @@ cudaError_t rock_generate(void* faces_v, void* cells_v, int* flag, int kind, int
       acc += rock_E(depth) - (uint32_t)(W - 1) * (uint32_t)(rp.topo.pre[f][0] + rp.topo.pre[f][1] + rp.topo.pre[f][2] + rp.topo.pre[f][3]);
     }
   }
-  cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), stream);
+  cudaError_t e = cudaMemsetAsync(flag, 0, 2 * sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
   k_rock_init<<<(unsigned)((nall + 255) / 256), 256, 0, stream>>>(faces, nall, kind == kCloud ? W : 0);
   uint64_t nl = 1;
-  for (int l = 0; l < depth; l++) {
+  if (sequential) {
+    unsigned long long* draws = reinterpret_cast<unsigned long long*>(flag);
+    if (kind == kCloud) {
+      k_rock_sequential<kCloud><<<1, 32, 0, stream>>>(rp, draws);
+      k_rock_resolve<kCloud><<<(unsigned)((nall + 255) / 256), 256, 0, stream>>>(faces, W, nall);
+    } else {
+      k_rock_sequential<kRock><<<1, 32, 0, stream>>>(rp, draws);
+      k_rock_resolve<kRock><<<(unsigned)((nall + 255) / 256), 256, 0, stream>>>(faces, W, nall);
+    }
+    nl += 2;
+  }
+  for (int l = 0; l < (sequential ? 0 : depth); l++) {
     const int n2 = (2 << l) + 1;
     const dim3 block(32, 8), grid((n2 + 31) / 32, (n2 + 7) / 8, nfaces);
     if (kind == kCloud) k_rock_level<kCloud><<<grid, block, 0, stream>>>(rp, l);

@@ -97,3 +97,36 @@ def test_cloud_golden(ctx, oracle, entry):
 def test_cloud_rejects_depth_1(ctx):
     with pytest.raises(Exception):
         ctx.rock_host(1, 1, cloud=True)
+
+
+# ---- value-dependent draws: a displaced height of exactly 0.0f makes the reference draw again ----
+@pytest.mark.parametrize("depth,state", [(5, 0x281C27C1), (5, 0x2F563CDE), (5, 0x0F21E415), (6, 0x8E8C261B), (6, 0x88CB5749), (7, 0xFA8CFB85),
+                                         (7, 0x66345930)])
+def test_rock_sentinel_collisions_follow_the_reference(ctx, oracle, depth, state):
+    """Seeds found by scanning with the oracle's index-addressed form (it reports the collision): the literal recursion -- the
+    reference's behaviour -- must be reproduced, including the extra rand() calls."""
+    _, status, _ = oracle.rock_indexed(state, depth, 0.3)
+    assert status == -3, "this seed is expected to hit the 0.0f sentinel"
+    fo, co, draws, so = oracle.rock(state, depth, 0.3)
+    fg, cg, sg = ctx.rock_host(state, depth, 0.3)
+    assert sg == so
+    assert np.array_equal(fo.view(np.uint32), fg.view(np.uint32))
+    assert co.tobytes() == cg.tobytes()
+
+
+def test_cloud_seed_scan_including_collisions(ctx, oracle):
+    """600 clouds of depth 4 and 5: every one equals the literal restatement; the scan is long enough to contain seeds whose call
+    count differs from the closed form (the 0.0f sentinel)."""
+    from rednoise_b200 import capi
+    lib = capi.lib()
+    odd = 0
+    for k in range(600):
+        depth = 4 + (k & 1)
+        state = (k * 2654435761 + 12345) & 0xFFFFFFFF
+        fg, cg, sg = ctx.rock_host(state, depth, 0.3, cloud=True)
+        fo, co, draws, so = oracle.cloud(state, depth, 0.3)
+        assert sg == so, (depth, hex(state))
+        assert np.array_equal(fo.view(np.uint32), fg.view(np.uint32)), (depth, hex(state))
+        assert co.tobytes() == cg.tobytes(), (depth, hex(state))
+        odd += draws != lib.rn_cloud_draw_count(depth)
+    print("clouds with value-dependent draws:", odd)

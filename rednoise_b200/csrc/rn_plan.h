@@ -37,7 +37,10 @@ constexpr int kStreamLevels = RN_STREAM_LEVELS;  // the last levels of a field a
 constexpr int kStreamMinDepth = 10;   // ... when the field is at least this deep
 constexpr int kStreamThreadsSmall = 64;   // narrower strips for small levels (more CTAs, fewer warm-up rows per sample)
 constexpr int kStreamMinBlocksSmall = 14;
-constexpr float kStreamEdgeCost = 1.28f;  // duration of a border-strip CTA relative to an interior one with the same rows
+#ifndef RN_STREAM_EDGE_COST
+#define RN_STREAM_EDGE_COST 1.28f
+#endif
+constexpr float kStreamEdgeCost = RN_STREAM_EDGE_COST;  // duration of a border-strip CTA relative to an interior one with the same rows
 #ifndef RN_STREAM_SMALL_COLS
 #define RN_STREAM_SMALL_COLS 1024
 #endif
@@ -248,11 +251,9 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
       // smallest interior segment length r (>= 8 rows) whose CTA count fits; border strips get r / kStreamEdgeCost rows
       int r = 8 < rows ? 8 : rows, re = r;
       for (;; r++) {
-        const int cnt_i = ni * ((rows + r - 1) / r);
         re = (int)((float)r / kStreamEdgeCost + 0.5f);
         re = re < 8 ? (8 < rows ? 8 : rows) : re;
-        while (re < r && cnt_i + ne * ((rows + re - 1) / re) > per_field) re++;
-        if (r >= rows || cnt_i + ne * ((rows + re - 1) / re) <= per_field) break;
+        if (r >= rows || ni * ((rows + r - 1) / r) + ne * ((rows + re - 1) / re) <= per_field) break;
       }
       st.seg_rows = r;
       st.nseg = (rows + r - 1) / r;

@@ -11,7 +11,7 @@ namespace rn {
 
 namespace {
 
-constexpr int kStageThreads = 512;
+constexpr int kStageThreads = kStageThreadsBig;
 
 template <int L, int T, int NT, bool EDGE, int P>
 __device__ __forceinline__ void run_phases(const StageParams& sp, const TileCtx& cx, float* sm)
@@ -23,10 +23,32 @@ __device__ __forceinline__ void run_phases(const StageParams& sp, const TileCtx&
   }
 }
 
+#ifdef RN_TIMELINE
+// Instrumented builds only: first CTA start / last CTA end (%globaltimer) of every launch of the chain.
+__device__ unsigned long long g_tl_start[1024], g_tl_end[1024];
+struct TlScope {
+  int s;
+  __device__ TlScope(int slot) : s(slot) { mark(false); }
+  __device__ ~TlScope() { mark(true); }
+  __device__ void mark(bool end) const
+  {
+    if (threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (end) atomicMax(&g_tl_end[s], t); else atomicMin(&g_tl_start[s], t);
+    }
+  }
+};
+#define RN_TL_SCOPE(slot) TlScope tl_scope__(slot)
+#else
+#define RN_TL_SCOPE(slot)
+#endif
+
 template <int L, int T, int NT>
-__global__ void __launch_bounds__(NT, (TileGeo<L, T>::BYTES <= 113 * 1024) ? 2 : 1) k_stage(const __grid_constant__ StageParams sp)
+__global__ void __launch_bounds__(NT, T == kTileSmall ? 8 : ((TileGeo<L, T>::BYTES <= 113 * 1024) ? 2 : 1)) k_stage(const __grid_constant__ StageParams sp)
 {
   extern __shared__ __align__(16) float sm[];
+  RN_TL_SCOPE(sp.tl_slot);
   TileCtx cx;
   cx.I0 = (sp.tile_i0 + (int)blockIdx.y) * T;
   cx.J0 = (sp.tile_j0 + (int)blockIdx.x) * T;
@@ -109,6 +131,7 @@ template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_stream(const __grid_constant__ StreamParams sp)
 {
   extern __shared__ __align__(16) float sm[];
+  RN_TL_SCOPE(sp.tl_slot);
   const StreamCtx cx = stream_ctx(sp, (int)blockIdx.x, blockIdx.z);
 #ifdef RN_STREAM_TRACE
   const unsigned bid = blockIdx.x;
@@ -152,21 +175,33 @@ cudaError_t launch_stream(const StreamParams& st, int nt, dim3 grid, cudaStream_
   return launch_stream_t<kStreamThreads, kStreamMinBlocks>(st, grid, stream);
 }
 
-template <int L>
-cudaError_t launch_stage(const StageParams& sp, dim3 grid, cudaStream_t stream)
+template <int L, int T, int NT>
+cudaError_t launch_stage_t(const StageParams& sp, dim3 grid, cudaStream_t stream)
 {
-  using G = TileGeo<L, kTile>;
+  using G = TileGeo<L, T>;
   static bool configured[64] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 64 && !configured[dev]) {
-    e = cudaFuncSetAttribute(k_stage<L, kTile, kStageThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES);
+    e = cudaFuncSetAttribute(k_stage<L, T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  k_stage<L, kTile, kStageThreads><<<grid, kStageThreads, G::BYTES, stream>>>(sp);
+  k_stage<L, T, NT><<<grid, NT, G::BYTES, stream>>>(sp);
   return cudaGetLastError();
+}
+
+template <int L>
+cudaError_t launch_stage(const StageParams& sp, int T, dim3 grid, cudaStream_t stream)
+{
+#if RN_SMALL_CHAIN
+  if constexpr (L <= RN_SMALL_CHAIN_L) {
+    if (T == kTileSmall) return launch_stage_t<L, kTileSmall, kStageThreadsSmall>(sp, grid, stream);
+  }
+#endif
+  (void)T;
+  return launch_stage_t<L, kTile, kStageThreads>(sp, grid, stream);
 }
 
 }  // namespace
@@ -175,6 +210,25 @@ cudaError_t launch_stage(const StageParams& sp, dim3 grid, cudaStream_t stream)
 extern "C" int rn_debug_trace(unsigned long long* host, int n)
 {
   return (int)cudaMemcpyFromSymbol(host, g_trace, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
+
+#ifdef RN_TIMELINE
+static int g_tl_next = 0;
+extern "C" int rn_debug_timeline(unsigned long long* host, int reset)
+{
+  if (reset) {
+    g_tl_next = 0;
+    void *a, *b;
+    cudaGetSymbolAddress(&a, g_tl_start);
+    cudaGetSymbolAddress(&b, g_tl_end);
+    cudaMemset(a, 0xff, sizeof(unsigned long long) * 1024);
+    cudaMemset(b, 0, sizeof(unsigned long long) * 1024);
+    return 0;
+  }
+  cudaMemcpyFromSymbol(host, g_tl_start, sizeof(unsigned long long) * 1024);
+  cudaMemcpyFromSymbol(host + 1024, g_tl_end, sizeof(unsigned long long) * 1024);
+  return g_tl_next;
 }
 #endif
 
@@ -206,7 +260,10 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
   const bool split = coarse_stream && coarse_done && coarse_stream != stream && !events && has_coarse;
   bool joined = false;
   for (int k = 0; k < nl; k++) {
-    const StageLaunch& sl = chain[k];
+    StageLaunch& sl = chain[k];
+#ifdef RN_TIMELINE
+    sl.sp.tl_slot = sl.st.tl_slot = (g_tl_next++) & 1023;
+#endif
     const dim3 grid(sl.gx, sl.gy, (unsigned)nfields);
     cudaStream_t s = (split && !sl.last) ? coarse_stream : stream;
     cudaError_t e;
@@ -221,10 +278,10 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
       e = launch_stream(sl.st, sl.nt, grid, s);
     } else {
       switch (sl.L) {
-        case 1: e = launch_stage<1>(sl.sp, grid, s); break;
-        case 2: e = launch_stage<2>(sl.sp, grid, s); break;
-        case 3: e = launch_stage<3>(sl.sp, grid, s); break;
-        default: e = launch_stage<4>(sl.sp, grid, s); break;
+        case 1: e = launch_stage<1>(sl.sp, sl.T, grid, s); break;
+        case 2: e = launch_stage<2>(sl.sp, sl.T, grid, s); break;
+        case 3: e = launch_stage<3>(sl.sp, sl.T, grid, s); break;
+        default: e = launch_stage<4>(sl.sp, sl.T, grid, s); break;
       }
     }
     if (e != cudaSuccess) return e;

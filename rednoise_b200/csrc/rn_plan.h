@@ -16,8 +16,8 @@
 
 namespace rn {
 
-constexpr int kMaxStages = 8;
-constexpr int kMaxLaunches = 2 * kMaxStages;
+constexpr int kMaxStages = 14;
+constexpr int kMaxLaunches = 16;
 #ifndef RN_STREAM_THREADS
 #define RN_STREAM_THREADS 128
 #endif
@@ -45,7 +45,23 @@ constexpr float kStreamEdgeCost = RN_STREAM_EDGE_COST;  // duration of a border-
 #define RN_STREAM_SMALL_COLS 1024
 #endif
 constexpr int kStreamSmallCols = RN_STREAM_SMALL_COLS;    // levels with fewer cell columns than this use the small configuration
-constexpr int kTile = 64;  // output tile edge of every stage
+constexpr int kTile = 64;  // output tile edge of a stage (and the unit in which streamed stages are cut out of a window)
+// Small chain (RN_SMALL_CHAIN): for one deep field per call the coarse levels run as stages of RN_SMALL_CHAIN_L levels with 32x32
+// tiles and 128-thread CTAs (<= 64 registers, 30.9 KB) that fit into ONE CTA slot of the streaming output kernel, which leaves one
+// slot per SM free: the coarse chain of the next call then runs underneath the output kernel of this one instead of after it
+// (measured with profiles/micro/timeline.py: 133 vs 143 us per depth-12 field; the 512-thread tile CTAs cannot become resident
+// while the output wave holds the slots).
+#ifndef RN_SMALL_CHAIN
+#define RN_SMALL_CHAIN 1
+#endif
+#ifndef RN_SMALL_CHAIN_FREE
+#define RN_SMALL_CHAIN_FREE 1   // CTA slots per SM the output kernel leaves to the next call's small stages
+#endif
+#ifndef RN_SMALL_CHAIN_L
+#define RN_SMALL_CHAIN_L 2   // levels per small stage: TileGeo<2,32> (30.9 KB) still fits beside 7 streaming CTAs per SM
+#endif
+constexpr int kTileSmall = 32;
+constexpr int kStageThreadsBig = 512, kStageThreadsSmall = 128;
 
 struct StagePlan {
   int din;  // depth of the input grid (2 = the analytic 5x5 initial lattice, Terrain.cpp:46-56)
@@ -83,8 +99,18 @@ inline int plan_tile_levels(int NL, int last, StagePlan* out)
 // level; the interior of those is streamed (rn_stream.cuh), their frame of border tiles goes through
 // the L = 1 tile kernel.
 inline bool plan_uses_streaming(int depth) { return depth >= kStreamMinDepth; }
-inline int plan_stages(int depth, StagePlan* out)
+inline bool plan_small_chain(int depth, int nfields) { return RN_SMALL_CHAIN && depth >= 12 && depth <= 13 && nfields <= 1; }
+inline int plan_stages(int depth, StagePlan* out, int nfields = 0)
 {
+  if (plan_small_chain(depth, nfields)) {
+    int ns = 0;
+    for (int d = 2; d < depth - kStreamLevels; d += RN_SMALL_CHAIN_L) {
+      const int rest = depth - kStreamLevels - d;
+      out[ns++] = StagePlan{d, rest < RN_SMALL_CHAIN_L ? rest : RN_SMALL_CHAIN_L};
+    }
+    for (int q = kStreamLevels; q > 0; q--) out[ns++] = StagePlan{depth - q, 1};
+    return ns;
+  }
   if (!plan_uses_streaming(depth)) return plan_tile_levels(depth - 2, kLastStageLevels, out);
   int ns = plan_tile_levels(depth - 2 - kStreamLevels, 0, out);
   for (int q = kStreamLevels; q > 0; q--) out[ns++] = StagePlan{depth - q, 1};
@@ -120,15 +146,15 @@ struct Rect {
 };
 
 // Tiles of a depth-d grid: tile t owns rows [t*T, t*T+T-1]; the last tile also owns row W.
-inline int tiles_per_side(int d) { const int W = 1 << d; return W >= kTile ? W / kTile : 1; }
-inline int tile_of(int d, int coord) { const int t = coord / kTile, nt = tiles_per_side(d); return t < nt ? t : nt - 1; }
+inline int tiles_per_side(int d, int T = kTile) { const int W = 1 << d; return W >= T ? W / T : 1; }
+inline int tile_of(int d, int coord, int T = kTile) { const int t = coord / T, nt = tiles_per_side(d, T); return t < nt ? t : nt - 1; }
 
 // Input-grid rectangle (depth d-L) a stage needs in order to produce tiles [t0,t1] of its output grid.
-inline void input_range_1d(int d, int L, int t0, int t1, int* lo, int* hi)
+inline void input_range_1d(int d, int L, int t0, int t1, int T, int* lo, int* hi)
 {
   const int W = 1 << d;
   const int H = stage_halo(L);
-  int a = t0 * kTile - H, b = (t1 + 1) * kTile + H;
+  int a = t0 * T - H, b = (t1 + 1) * T + H;
   if (a < 0) a = 0;
   if (b > W) b = W;
   *lo = a >> L;
@@ -144,6 +170,7 @@ struct StageLaunch {
   StageParams sp;         // kind 0
   StreamParams st;        // kind 1
   int L;
+  int T;                  // kind 0: tile edge (kTile, or kTileSmall with kStageThreadsSmall threads)
   int nt;                 // kind 1: threads per CTA (kStreamThreads or kStreamThreadsSmall)
   unsigned gx, gy;        // kind 0: tiles in j, tiles in i; kind 1: strips, segments
 };
@@ -153,7 +180,7 @@ inline size_t stage_grid_bytes(int d) { const size_t side = ((size_t)1 << d) + 1
 inline size_t chain_scratch_bytes(int depth, int nfields)
 {
   StagePlan plan[kMaxStages];
-  const int ns = plan_stages(depth, plan);
+  const int ns = plan_stages(depth, plan, nfields);
   size_t total = 0;
   for (int k = 0; k + 1 < ns; k++) total += stage_grid_bytes(plan[k].din + plan[k].L) * (size_t)nfields;
   return total;
@@ -167,22 +194,24 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
                        float amplitude)
 {
   StagePlan plan[kMaxStages];
-  const int ns = plan_stages(depth, plan);
+  const int ns = plan_stages(depth, plan, nfields);
   const bool streaming = plan_uses_streaming(depth);
-  int t_i0[kMaxStages], t_i1[kMaxStages], t_j0[kMaxStages], t_j1[kMaxStages];
-  t_i0[ns - 1] = tile_of(depth, i0);
-  t_i1[ns - 1] = tile_of(depth, i0 + ni - 1);
-  t_j0[ns - 1] = tile_of(depth, j0);
-  t_j1[ns - 1] = tile_of(depth, j0 + nj - 1);
+  const bool small_chain = plan_small_chain(depth, nfields);
+  int t_i0[kMaxStages], t_i1[kMaxStages], t_j0[kMaxStages], t_j1[kMaxStages], Tk[kMaxStages];
+  for (int k = 0; k < ns; k++) Tk[k] = (small_chain && k < ns - kStreamLevels) ? kTileSmall : kTile;
+  t_i0[ns - 1] = tile_of(depth, i0, Tk[ns - 1]);
+  t_i1[ns - 1] = tile_of(depth, i0 + ni - 1, Tk[ns - 1]);
+  t_j0[ns - 1] = tile_of(depth, j0, Tk[ns - 1]);
+  t_j1[ns - 1] = tile_of(depth, j0 + nj - 1, Tk[ns - 1]);
   for (int k = ns - 1; k > 0; k--) {
     const int d = plan[k].din + plan[k].L;
     int lo, hi;
-    input_range_1d(d, plan[k].L, t_i0[k], t_i1[k], &lo, &hi);
-    t_i0[k - 1] = tile_of(plan[k].din, lo);
-    t_i1[k - 1] = tile_of(plan[k].din, hi);
-    input_range_1d(d, plan[k].L, t_j0[k], t_j1[k], &lo, &hi);
-    t_j0[k - 1] = tile_of(plan[k].din, lo);
-    t_j1[k - 1] = tile_of(plan[k].din, hi);
+    input_range_1d(d, plan[k].L, t_i0[k], t_i1[k], Tk[k], &lo, &hi);
+    t_i0[k - 1] = tile_of(plan[k].din, lo, Tk[k - 1]);
+    t_i1[k - 1] = tile_of(plan[k].din, hi, Tk[k - 1]);
+    input_range_1d(d, plan[k].L, t_j0[k], t_j1[k], Tk[k], &lo, &hi);
+    t_j0[k - 1] = tile_of(plan[k].din, lo, Tk[k - 1]);
+    t_j1[k - 1] = tile_of(plan[k].din, hi, Tk[k - 1]);
   }
   const E4* gin = nullptr;
   size_t gin_pitch = 0, gin_stride = 0, off = 0;
@@ -235,7 +264,7 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
       st.close_j = t_j1[k] == nt - 1;
       const int cols = st.b_hi - st.b_lo, rows = st.a_hi - st.a_lo;
       sl.nt = cols < kStreamSmallCols ? kStreamThreadsSmall : kStreamThreads;
-      const int ctas_target = 148 * (cols < kStreamSmallCols ? kStreamMinBlocksSmall : kStreamMinBlocks);
+      const int ctas_target = 148 * ((cols < kStreamSmallCols ? kStreamMinBlocksSmall : kStreamMinBlocks) - ((small_chain && last) ? RN_SMALL_CHAIN_FREE : 0));
       const int strips = (cols + (sl.nt - 3) - 1) / (sl.nt - 3);
       st.strip_cols = (cols + strips - 1) / strips;
       st.nstrips = (cols + st.strip_cols - 1) / st.strip_cols;
@@ -273,7 +302,7 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
     }
     StageLaunch& sl = out[nl++];
     sl = StageLaunch{};
-    sl.kind = 0; sl.stage = k; sl.last = last; sl.L = plan[k].L;
+    sl.kind = 0; sl.stage = k; sl.last = last; sl.L = plan[k].L; sl.T = Tk[k];
     sl.sp = sp;
     sl.gx = (unsigned)(t_j1[k] - t_j0[k] + 1);
     sl.gy = (unsigned)(t_i1[k] - t_i0[k] + 1);

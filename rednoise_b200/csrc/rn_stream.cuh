@@ -58,6 +58,9 @@ struct StreamParams {
   StageLevel lev;
   Jump jn, jn1;    // LCG jumps over n and n+1 draws (one cell row of generateSquare / loop 1, of loop 2)
   int volcano;
+#ifdef RN_TIMELINE
+  int tl_slot;          // instrumented builds: launch number (profiles/micro/timeline.py)
+#endif
   float volcano_gain;
 };
 

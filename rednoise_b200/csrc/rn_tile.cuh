@@ -84,6 +84,9 @@ struct StageParams {
   Law law;
   StageLevel lev[kMaxStageLevels];
   int volcano;                         // addVolcano epilogue (final stage only)
+#ifdef RN_TIMELINE
+  int tl_slot;          // instrumented builds: launch number (profiles/micro/timeline.py)
+#endif
   float volcano_gain;                  // amplitude*0.008f, Terrain.cpp:137
 };
 

@@ -20,22 +20,24 @@ using namespace rn;
 
 namespace {
 
-constexpr int NT = 512;
+constexpr int threads_of(int T) { return T == kTileSmall ? kStageThreadsSmall : kStageThreadsBig; }
 static int g_reverse = 0;  // visit the threads of a phase in descending order: a phase whose threads depended on
                            // one another's writes (a race on the GPU) would give different bits
 constexpr int GUARD = 4096;  // words on each side
 
-template <int L, bool EDGE, int P>
+template <int L, int T, bool EDGE, int P>
 void run_phase(const StageParams& sp, const TileCtx& cx, float* sm)
 {
-  for (int q = 0; q < NT; q++) Tile<L, kTile, NT, EDGE>::template phase<P>(sp, cx, sm, g_reverse ? NT - 1 - q : q);
-  if constexpr (P + 1 < Tile<L, kTile, NT, EDGE>::NPHASES) run_phase<L, EDGE, P + 1>(sp, cx, sm);
+  constexpr int NT = threads_of(T);
+  for (int q = 0; q < NT; q++) Tile<L, T, NT, EDGE>::template phase<P>(sp, cx, sm, g_reverse ? NT - 1 - q : q);
+  if constexpr (P + 1 < Tile<L, T, NT, EDGE>::NPHASES) run_phase<L, T, EDGE, P + 1>(sp, cx, sm);
 }
 
-template <int L>
-int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
+template <int L, int T>
+int run_stage_t(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
 {
-  using G = TileGeo<L, kTile>;
+  constexpr int NT = threads_of(T);
+  using G = TileGeo<L, T>;
   std::vector<float> buf((size_t)G::WORDS + 2 * GUARD + 4);
   // 16-byte align the tile's shared memory
   float* base = buf.data();
@@ -50,13 +52,13 @@ int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
       for (unsigned bx = 0; bx < sl.gx; bx++) {
         for (size_t i = 0; i < (size_t)G::WORDS + 2 * GUARD; i++) base[i] = poison ? nanv : 0.0f;
         TileCtx cx;
-        cx.I0 = (sl.sp.tile_i0 + (int)by) * kTile;
-        cx.J0 = (sl.sp.tile_j0 + (int)bx) * kTile;
+        cx.I0 = (sl.sp.tile_i0 + (int)by) * T;
+        cx.J0 = (sl.sp.tile_j0 + (int)bx) * T;
         cx.seed = seeds ? seeds[f] : sl.sp.seed;
         cx.gin = sl.sp.gin ? sl.sp.gin + (size_t)f * sl.sp.gin_field_stride : nullptr;
         cx.gout = sl.sp.gout + (size_t)f * sl.sp.gout_field_stride;
-        if (force_edge || Tile<L, kTile, NT, true>::is_edge(cx, 1 << sl.sp.dout)) run_phase<L, true, 0>(sl.sp, cx, sm);
-        else run_phase<L, false, 0>(sl.sp, cx, sm);
+        if (force_edge || Tile<L, T, NT, true>::is_edge(cx, 1 << sl.sp.dout)) run_phase<L, T, true, 0>(sl.sp, cx, sm);
+        else run_phase<L, T, false, 0>(sl.sp, cx, sm);
         if (poison) {
           for (int i = 0; i < GUARD; i++) {
             uint32_t a, b;
@@ -67,6 +69,15 @@ int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
         }
       }
   return bad;
+}
+
+template <int L>
+int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
+{
+  if constexpr (L <= 2) {
+    if (sl.T == kTileSmall) return run_stage_t<L, kTileSmall>(sl, nfields, seeds, poison, force_edge);
+  }
+  return run_stage_t<L, kTile>(sl, nfields, seeds, poison, force_edge);
 }
 
 // One barrier interval for every thread, each in the instantiation the kernel's warp would run at this step.
@@ -182,7 +193,7 @@ int replay_smem_bytes(int L)
 int replay_plan(int depth, int* din, int* L)
 {
   StagePlan plan[kMaxStages];
-  const int ns = plan_stages(depth, plan);
+  const int ns = plan_stages(depth, plan, 1);
   for (int k = 0; k < ns; k++) {
     din[k] = plan[k].din;
     L[k] = plan[k].L;

@@ -54,6 +54,12 @@ constexpr int kTile = 64;  // output tile edge of a stage (and the unit in which
 #ifndef RN_SMALL_CHAIN
 #define RN_SMALL_CHAIN 1
 #endif
+#ifndef RN_SMALL_CHAIN_MIN
+#define RN_SMALL_CHAIN_MIN 11
+#endif
+#ifndef RN_SMALL_CHAIN_MAX
+#define RN_SMALL_CHAIN_MAX 14
+#endif
 #ifndef RN_SMALL_CHAIN_FREE
 #define RN_SMALL_CHAIN_FREE 1   // CTA slots per SM the output kernel leaves to the next call's small stages
 #endif
@@ -99,7 +105,7 @@ inline int plan_tile_levels(int NL, int last, StagePlan* out)
 // level; the interior of those is streamed (rn_stream.cuh), their frame of border tiles goes through
 // the L = 1 tile kernel.
 inline bool plan_uses_streaming(int depth) { return depth >= kStreamMinDepth; }
-inline bool plan_small_chain(int depth, int nfields) { return RN_SMALL_CHAIN && depth >= 12 && depth <= 13 && nfields <= 1; }
+inline bool plan_small_chain(int depth, int nfields) { return RN_SMALL_CHAIN && depth >= RN_SMALL_CHAIN_MIN && depth <= RN_SMALL_CHAIN_MAX && nfields <= 1; }
 inline int plan_stages(int depth, StagePlan* out, int nfields = 0)
 {
   if (plan_small_chain(depth, nfields)) {

@@ -74,7 +74,7 @@ int run_stage_t(const StageLaunch& sl, int nfields, const uint32_t* seeds, int p
 template <int L>
 int run_stage(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
 {
-  if constexpr (L <= 2) {
+  if constexpr (L <= RN_SMALL_CHAIN_L) {
     if (sl.T == kTileSmall) return run_stage_t<L, kTileSmall>(sl, nfields, seeds, poison, force_edge);
   }
   return run_stage_t<L, kTile>(sl, nfields, seeds, poison, force_edge);

@@ -44,10 +44,10 @@ def load_peaks():
 
 def alu_roofline(args, value_gs, kernel_ms, my_samples, sm_mhz):
     """The instruction-issue ("ALU") bound of the output kernel: thread instructions per sample counted by ncu on the
-    committed capture (profiles/r01z_stream_kernel_ncu_metrics.json) against 148 SMs x 4 schedulers x 32 lanes x the SM clock
+    committed capture (profiles/r01zz_stream_kernel_ncu_metrics.json) against 148 SMs x 4 schedulers x 32 lanes x the SM clock
     seen during this run.  The bit-exact contract forbids FMA contraction, so this bound sits below the HBM-write bound."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01z_stream_kernel_ncu_metrics.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01zz_stream_kernel_ncu_metrics.json")))
         if args.workload != "field" or args.depth != 12:
             return None
         warp_inst = float(d["smsp__inst_executed.sum"][0])
@@ -60,7 +60,7 @@ def alu_roofline(args, value_gs, kernel_ms, my_samples, sm_mhz):
         achieved = my_samples / (kernel_ms * 1e-3) / 1e9
         return {"bound": "issue", "thread_inst_per_sample": inst_per_sample, "peak_thread_inst_per_s": peak,
                 "gsamples_bound": bound, "achieved_gsamples_kernel": achieved, "frac": achieved / bound,
-                "source": "profiles/r01z_stream_kernel_ncu_metrics.json (ncu --set full, k_stream<128,8>)"}
+                "source": "profiles/r01zz_stream_kernel_ncu_metrics.json (ncu --set full, k_stream<128,8>)"}
     except Exception:
         return None
 

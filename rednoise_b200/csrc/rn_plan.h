@@ -41,6 +41,10 @@ constexpr int kStreamMinBlocksSmall = 14;
 #define RN_STREAM_EDGE_COST 1.28f
 #endif
 constexpr float kStreamEdgeCost = RN_STREAM_EDGE_COST;  // duration of a border-strip CTA relative to an interior one with the same rows
+#ifndef RN_STREAM_MIN_SEG_ROWS
+#define RN_STREAM_MIN_SEG_ROWS 8
+#endif
+constexpr int kStreamMinSegRows = RN_STREAM_MIN_SEG_ROWS;  // shortest row segment of a streaming CTA (2 warm-up rows on top; 6, 10, 12, 16 measured worse)
 #ifndef RN_STREAM_SMALL_COLS
 #define RN_STREAM_SMALL_COLS 1024
 #endif
@@ -284,10 +288,10 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
       // gets that much fewer rows.
       const int per_field = ctas_target / (nfields > 0 ? nfields : 1);
       // smallest interior segment length r (>= 8 rows) whose CTA count fits; border strips get r / kStreamEdgeCost rows
-      int r = 8 < rows ? 8 : rows, re = r;
+      int r = kStreamMinSegRows < rows ? kStreamMinSegRows : rows, re = r;
       for (;; r++) {
         re = (int)((float)r / kStreamEdgeCost + 0.5f);
-        re = re < 8 ? (8 < rows ? 8 : rows) : re;
+        re = re < kStreamMinSegRows ? (kStreamMinSegRows < rows ? kStreamMinSegRows : rows) : re;
         if (r >= rows || ni * ((rows + r - 1) / r) + ne * ((rows + re - 1) / re) <= per_field) break;
       }
       st.seg_rows = r;

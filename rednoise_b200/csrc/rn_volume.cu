@@ -30,18 +30,6 @@ struct VolLevel {
   int ia0;  // first index along i of this launch (the slab restriction)
 };
 
-__device__ __forceinline__ float& at(const VolLevel& L, int i, int j, int k)
-{
-  const size_t S = (size_t)L.W + 1;
-  return L.d[((size_t)i * S + (size_t)j) * S + (size_t)k];
-}
-__device__ __forceinline__ float vol_offset(const VolLevel& L, int i, int j, int k)
-{
-  const uint64_t S = (uint64_t)L.W + 1;
-  const float r = random_from_draw(vol_draw(L.seed, ((uint64_t)i * S + (uint64_t)j) * S + (uint64_t)k));
-  return ((L.amplitude * r) * (float)L.s) * L.inv_w;  // / (float)W, exact: W is a power of two
-}
-
 // PASS 1: cube centres (AXIS unused).  PASS 2: face centres, AXIS = the coordinate on the s lattice.
 // PASS 3: edge midpoints, AXIS = the coordinate that is an odd multiple of h.
 template <int PASS, int AXIS>
@@ -57,62 +45,51 @@ __global__ void k_volume(VolLevel L, int cnt_k)
   const int i = (L.ia0 + (int)blockIdx.z) * s + (odd0 ? h : 0);
   const int j = (int)blockIdx.y * s + (odd1 ? h : 0);
   const int k = kk * s + (odd2 ? h : 0);
+  // linear index of the sample and the three half-step strides: every neighbour is base +- a stride
+  const size_t S = (size_t)L.W + 1;
+  const ptrdiff_t st[3] = {(ptrdiff_t)(S * S) * h, (ptrdiff_t)S * h, (ptrdiff_t)h};
+  const size_t base = ((size_t)i * S + (size_t)j) * S + (size_t)k;
+  const float* p = L.d + base;
   float sum;
   float rcnt;
   if (PASS == 1) {
-    sum = at(L, i - h, j - h, k - h);
-    sum += at(L, i - h, j - h, k + h);
-    sum += at(L, i - h, j + h, k - h);
-    sum += at(L, i - h, j + h, k + h);
-    sum += at(L, i + h, j - h, k - h);
-    sum += at(L, i + h, j - h, k + h);
-    sum += at(L, i + h, j + h, k - h);
-    sum += at(L, i + h, j + h, k + h);
+    sum = p[-st[0] - st[1] - st[2]];
+    sum += p[-st[0] - st[1] + st[2]];
+    sum += p[-st[0] + st[1] - st[2]];
+    sum += p[-st[0] + st[1] + st[2]];
+    sum += p[st[0] - st[1] - st[2]];
+    sum += p[st[0] - st[1] + st[2]];
+    sum += p[st[0] + st[1] - st[2]];
+    sum += p[st[0] + st[1] + st[2]];
     rcnt = 0.125f;
   } else {
     constexpr int B0 = AXIS == 0 ? 1 : 0;               // the other two axes, ascending
     constexpr int B1 = AXIS == 2 ? 1 : 2;
-    int c[3] = {i, j, k};
+    const int c[3] = {i, j, k};
     int cnt;
     if (PASS == 2) {
       // 4 face corners (-,-), (-,+), (+,-), (+,+) in (B0, B1), then the cube centres along AXIS: -, +
-      int p[3] = {c[0], c[1], c[2]};
-      p[B0] -= h; p[B1] -= h;
-      sum = at(L, p[0], p[1], p[2]);
-      p[B1] += s;
-      sum += at(L, p[0], p[1], p[2]);
-      p[B0] += s; p[B1] -= s;
-      sum += at(L, p[0], p[1], p[2]);
-      p[B1] += s;
-      sum += at(L, p[0], p[1], p[2]);
+      sum = p[-st[B0] - st[B1]];
+      sum += p[-st[B0] + st[B1]];
+      sum += p[st[B0] - st[B1]];
+      sum += p[st[B0] + st[B1]];
       cnt = 4;
-      int q[3] = {c[0], c[1], c[2]};
-      q[AXIS] = c[AXIS] - h;
-      if (q[AXIS] >= 0) { sum += at(L, q[0], q[1], q[2]); cnt++; }
-      q[AXIS] = c[AXIS] + h;
-      if (q[AXIS] <= L.W) { sum += at(L, q[0], q[1], q[2]); cnt++; }
+      if (c[AXIS] - h >= 0) { sum += p[-st[AXIS]]; cnt++; }
+      if (c[AXIS] + h <= L.W) { sum += p[st[AXIS]]; cnt++; }
     } else {
       // 2 edge ends along AXIS: -, +; then the face centres along B0 (-, +), then along B1 (-, +)
-      int p[3] = {c[0], c[1], c[2]};
-      p[AXIS] -= h;
-      sum = at(L, p[0], p[1], p[2]);
-      p[AXIS] += s;
-      sum += at(L, p[0], p[1], p[2]);
+      sum = p[-st[AXIS]];
+      sum += p[st[AXIS]];
       cnt = 2;
-      int q[3] = {c[0], c[1], c[2]};
-      q[B0] = c[B0] - h;
-      if (q[B0] >= 0) { sum += at(L, q[0], q[1], q[2]); cnt++; }
-      q[B0] = c[B0] + h;
-      if (q[B0] <= L.W) { sum += at(L, q[0], q[1], q[2]); cnt++; }
-      q[B0] = c[B0];
-      q[B1] = c[B1] - h;
-      if (q[B1] >= 0) { sum += at(L, q[0], q[1], q[2]); cnt++; }
-      q[B1] = c[B1] + h;
-      if (q[B1] <= L.W) { sum += at(L, q[0], q[1], q[2]); cnt++; }
+      if (c[B0] - h >= 0) { sum += p[-st[B0]]; cnt++; }
+      if (c[B0] + h <= L.W) { sum += p[st[B0]]; cnt++; }
+      if (c[B1] - h >= 0) { sum += p[-st[B1]]; cnt++; }
+      if (c[B1] + h <= L.W) { sum += p[st[B1]]; cnt++; }
     }
     rcnt = cnt == 6 ? 1.0f / 6.0f : (cnt == 5 ? 1.0f / 5.0f : (cnt == 4 ? 1.0f / 4.0f : (cnt == 3 ? 1.0f / 3.0f : 1.0f / 2.0f)));
   }
-  at(L, i, j, k) = sum * rcnt + vol_offset(L, i, j, k);
+  const float r = random_from_draw(vol_draw(L.seed, (uint64_t)base));
+  L.d[base] = sum * rcnt + ((L.amplitude * r) * (float)L.s) * L.inv_w;
 }
 
 __global__ void k_volume_init(float* d, int W)

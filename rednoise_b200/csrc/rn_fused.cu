@@ -1,9 +1,8 @@
-// rn_fused.cu -- algorithm 2: the fused tile kernels (rn_tile.cuh) and their stage chain.
+// rn_fused.cu -- algorithm 2: the fused tile kernels (rn_tile.cuh), the streaming kernels (rn_stream.cuh) and their stage chain.
 //
-// Replaces the level loop of Terrain::Terrain (Terrain.cpp:60-82) + addVolcano (:88) with
-// 2-4 launches per field: each stage refines a complete coarse grid by 2-4 levels per CTA in
-// shared memory and stores finished 64x64 tiles with 128-bit coalesced writes.  Intermediate
-// grids (<= 1/64 of the output) stay L2-resident between stages.
+// Replaces the level loop of Terrain::Terrain (Terrain.cpp:60-82) + addVolcano (:88) with 2-6 launches per field (rn_plan.h):
+// tile stages refine a complete coarse grid by 1-4 levels per CTA in shared memory and store finished tiles with 128-bit
+// coalesced writes; the last two levels of a deep field are streamed.  Intermediate grids stay L2-resident between stages.
 #include "rn_kernels.h"
 #include "rn_plan.h"
 

@@ -10,9 +10,10 @@
 // The level's input is the complete coarser grid in global memory (L2-resident: it is 1/4 of the
 // level's output); the output is stored as full 128-bit coalesced rows, like the tile kernels.
 //
-// Strips / segments that touch the lattice border run the EDGE instantiation (existence tests, the
-// border forms of averageDiamond / generateDiamond, the closing row and column W); all others run
-// the lean one.
+// Strips on a lattice column border, and the steps of any strip that touch the first / last lattice rows, run the EDGE
+// instantiation (existence tests, the border forms of averageDiamond / generateDiamond, the closing row and column W); all
+// other (strip, step) pairs run the lean one, in which the two midpoints of a cell are evaluated as packed FP32 pairs
+// (rn_math.cuh: F2, displace2) and the thread's own samples stay in registers across the barrier intervals (RN_STREAM_CARRY).
 //
 // Step u of a strip (cell row u; cell (u,c) has its corner at output (2u, 2c')):
 //   interval 1   S(u): centre C(u,c) from lattice rows u, u+1        (averageSquare+generateSquare)

@@ -33,6 +33,7 @@ struct RockTopo {
 };
 
 constexpr int kRock = 0, kCloud = 1;
+constexpr int kRockNodeLevel = 7;  // levels from this one on use the node-major kernel (measured: depth 7 77 vs 92 us, depth 11 0.89 vs 2.1 ms)
 
 struct RockParams {
   float2* faces;       // nfaces x (W+1) x (W+1) {height, shade}: face f = the reference's currentFace, (x, y) as element() sees it
@@ -124,8 +125,10 @@ __device__ inline uint32_t rock_point_call_index(const RockTopo& t, int depth, i
 
 // One level: the centres (Rock.cpp:179) and edge midpoints (:181-212) of all nodes of width W >> l, on the
 // half-step lattice of that level ((2n+1)^2 points per face; those with two even coordinates are older).
+// One level, one thread per SAMPLE (used for the coarse levels, where a level is a handful of warps and latency counts): the centres (Rock.cpp:179) and edge midpoints (:181-212) of all nodes of width W >> l, on the
+// half-step lattice of that level ((2n+1)^2 points per face; those with two even coordinates are older).
 template <int KIND>
-__global__ void k_rock_level(const __grid_constant__ RockParams rp, int l)
+__global__ void k_rock_level_points(const __grid_constant__ RockParams rp, int l)
 {
   const int depth = rp.depth, W = 1 << depth, P = W + 1;
   const int n2 = (2 << l) + 1;  // points per side of the half-step lattice
@@ -154,6 +157,50 @@ __global__ void k_rock_level(const __grid_constant__ RockParams rp, int l)
     if (e.x == 0.0f) atomicExch(rp.collision, 1);
   }
   g[(size_t)x * P + y] = e;
+}
+
+// One level, one thread per quadtree NODE (f, qx, qy) of width W >> l: its centre (Rock.cpp:179) and the edge midpoints it is
+// responsible for -- right and top always, left / bottom only in column / row 0 -- so every sample of the face is written once
+// and the walk from the root that yields the call index is done once per node instead of once per sample.  A midpoint on a
+// face side that an earlier face has drawn takes its index from that face (rock_point_call_index).
+template <int KIND>
+__device__ __forceinline__ void rock_edge(const RockParams& rp, float2* g, int P, int W, int f, int l, int x, int y, bool along_x, int h, bool mine,
+                                          uint32_t k_mine)
+{
+  const float2 a = along_x ? g[(size_t)(x - h) * P + y] : g[(size_t)x * P + (y - h)], b = along_x ? g[(size_t)(x + h) * P + y] : g[(size_t)x * P + (y + h)];
+  const uint32_t k = mine ? k_mine : rock_point_call_index<KIND>(rp.topo, rp.depth, f, l, x, y);
+  const float r = random_from_draw(lcg_draw_from_state(lcg_skip(rp.state, k + 1u)));
+  const float offset = rp.amplitude * r * (float)(2 * h) / (float)W;  // Rock.cpp:185: amplitude * random() * extent / maxWidth
+  float2 e;
+  e.x = (a.x + b.x) * 0.5f + offset;                                   // Rock.h:30-34, Rock.cpp:186
+  e.y = (a.y + b.y) * 0.5f + offset * 1.5f;                            // radiosityStrength, Rock.cpp:171,187
+  if (e.x == 0.0f) atomicExch(rp.collision, 1);
+  g[(size_t)x * P + y] = e;
+}
+
+template <int KIND>
+__global__ void k_rock_level(const __grid_constant__ RockParams rp, int l)
+{
+  const int depth = rp.depth, W = 1 << depth, P = W + 1;
+  const int n = 1 << l;
+  const int f = blockIdx.z;
+  const int qx = blockIdx.y * blockDim.y + threadIdx.y, qy = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qx >= n || qy >= n) return;
+  const int w = W >> l, h = w >> 1;
+  const int x0 = qx * w, y0 = qy * w, x1 = x0 + w, y1 = y0 + w, mx = x0 + h, my = y0 + h;
+  float2* g = rp.faces + (size_t)f * P * P;
+  if (!(KIND == kCloud && g[(size_t)mx * P + my].x != 0.0f)) {  // (a preset control height of a cloud stays: Cloud.cpp:64-73,131)
+    const float2 a = g[(size_t)x0 * P + y0], b = g[(size_t)x1 * P + y0], c = g[(size_t)x0 * P + y1], d = g[(size_t)x1 * P + y1];
+    g[(size_t)mx * P + my] = make_float2((a.x + b.x + c.x + d.x) * 0.25f, (a.y + b.y + c.y + d.y) * 0.25f);  // Rock.h:25-29
+  }
+  const int* pre = rp.topo.pre[f];
+  const uint32_t k0 = rock_call_index(rp.topo, depth, f, l, qx, qy, 0);  // call index of the node's first draw
+  // which of the four slots (left, right, bottom, top) this node draws itself (Rock.cpp:181-212 and the visiting order)
+  const bool d0 = qx == 0 && !pre[0], d1 = !(qx == n - 1 && pre[1]), d2 = qy == 0 && !pre[2], d3 = !(qy == n - 1 && pre[3]);
+  if (qx == 0) rock_edge<KIND>(rp, g, P, W, f, l, x0, my, false, h, d0, k0);
+  rock_edge<KIND>(rp, g, P, W, f, l, x1, my, false, h, d1, k0 + (uint32_t)d0);
+  if (qy == 0) rock_edge<KIND>(rp, g, P, W, f, l, mx, y0, true, h, d2, k0 + (uint32_t)d0 + (uint32_t)d1);
+  rock_edge<KIND>(rp, g, P, W, f, l, mx, y1, true, h, d3, k0 + (uint32_t)d0 + (uint32_t)d1 + (uint32_t)d2);
 }
 
 __global__ void k_rock_init(float2* faces, size_t n, int cloud_W)
@@ -400,10 +447,17 @@ cudaError_t rock_generate(void* faces_v, void* cells_v, int* flag, int kind, int
     nl += 2;
   }
   for (int l = 0; l < (sequential ? 0 : depth); l++) {
-    const int n2 = (2 << l) + 1;
-    const dim3 block(32, 8), grid((n2 + 31) / 32, (n2 + 7) / 8, nfaces);
-    if (kind == kCloud) k_rock_level<kCloud><<<grid, block, 0, stream>>>(rp, l);
-    else k_rock_level<kRock><<<grid, block, 0, stream>>>(rp, l);
+    if (l < kRockNodeLevel) {  // few samples: one thread per sample (shortest critical path)
+      const int n2 = (2 << l) + 1;
+      const dim3 block(32, 8), grid((n2 + 31) / 32, (n2 + 7) / 8, nfaces);
+      if (kind == kCloud) k_rock_level_points<kCloud><<<grid, block, 0, stream>>>(rp, l);
+      else k_rock_level_points<kRock><<<grid, block, 0, stream>>>(rp, l);
+    } else {                   // many samples: one thread per node (one index walk for its 3-5 samples)
+      const int nn = 1 << l;
+      const dim3 block(32, 8), grid((nn + 31) / 32, (nn + 7) / 8, nfaces);
+      if (kind == kCloud) k_rock_level<kCloud><<<grid, block, 0, stream>>>(rp, l);
+      else k_rock_level<kRock><<<grid, block, 0, stream>>>(rp, l);
+    }
     nl++;
   }
   if (cells_v) {

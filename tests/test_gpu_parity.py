@@ -309,3 +309,30 @@ def test_depth12_windows_of_every_strip_layout(ctx, rnlib, oracle):
     for (i0, j0, ni, nj) in wins:
         got = ctx.terrain2d_host(p, window=rnlib.Window(i0, j0, ni, nj))
         assert_bitwise(got, full[i0:i0 + ni, j0:j0 + nj], f"depth 12 window {(i0, j0, ni, nj)}")
+
+
+def test_deep_batches_of_one_and_two(ctx, rnlib, oracle):
+    """One deep field per call takes the small coarse chain (32x32 tiles, 128-thread CTAs), two or more the 64x64 tile stages:
+    both through the batch entry point (seeds from device memory), device destination, against the oracle."""
+    import torch
+    ctx.set_algorithm(0)
+    depth = 11
+    S = (1 << depth) + 1
+    p = rnlib.default_params(depth=depth, apply_volcano=1)
+    for seeds in ([777], [31337, 4]):
+        d = torch.empty((len(seeds), S, S, 4), device="cuda", dtype=torch.float32)
+        ctx.terrain2d_batch_ptr(p, seeds, d.data_ptr(), dst_is_device=True)
+        torch.cuda.synchronize()
+        got = d.cpu().numpy()
+        for t, seed in enumerate(seeds):
+            want = oracle.terrain2d(oracle_lib.params(seed=seed, depth=depth, apply_volcano=1))
+            assert_bitwise(got[t], want, f"batch of {len(seeds)}, tile {t}")
+    # back-to-back single-field calls (call pipelining: the next call's coarse chain runs under this call's output kernel)
+    outs = [torch.empty((S, S, 4), device="cuda", dtype=torch.float32) for _ in range(4)]
+    s = torch.cuda.Stream()
+    for k, o in enumerate(outs):
+        ctx.terrain2d_ptr(rnlib.default_params(seed=100 + k, depth=depth, apply_volcano=1), o.data_ptr(), dst_is_device=True, stream=s.cuda_stream)
+    torch.cuda.synchronize()
+    for k, o in enumerate(outs):
+        want = oracle.terrain2d(oracle_lib.params(seed=100 + k, depth=depth, apply_volcano=1))
+        assert_bitwise(o.cpu().numpy(), want, f"pipelined call {k}")

@@ -27,6 +27,8 @@ struct rn_context {
   // algorithm 2 pipelining: the coarse stages run on a high-priority side stream into one of two
   // scratch slots, so that they overlap the output stage of the previous call
   cudaStream_t coarse_stream = nullptr;
+  cudaStream_t tile_stream = nullptr;               // the tile stages of a call run here, ahead of its streamed coarse level
+  cudaEvent_t tiles_done[2] = {nullptr, nullptr};   // tile stages of the call using slot s have finished
   void* slot[2] = {nullptr, nullptr};
   size_t slot_bytes[2] = {0, 0};
   cudaEvent_t coarse_done[2] = {nullptr, nullptr};  // coarse stages of the call using slot s have finished
@@ -43,6 +45,10 @@ struct rn_context {
   cudaEvent_t ev[17] = {};
   int ev_stages = 0;
 };
+
+#ifndef RN_TILE_STREAM
+#define RN_TILE_STREAM 1   // a third stream for the tile stages, so that they need not wait for the previous call's streamed coarse level
+#endif
 
 namespace {
 
@@ -144,11 +150,11 @@ int synth_window_fused(rn_context* ctx, const rn_params* p, const rn_window& w, 
   ctx->ev_stages = 0;
   const bool overlap = ctx->overlap && !ctx->profiling && ctx->coarse_stream;
   if (ctx->slot_used[sl])  // the previous user of this scratch slot must have consumed it
-    RN_CUDA(cudaStreamWaitEvent(overlap ? ctx->coarse_stream : stream, ctx->slot_free[sl], 0));
+    RN_CUDA(cudaStreamWaitEvent(overlap ? (ctx->tile_stream ? ctx->tile_stream : ctx->coarse_stream) : stream, ctx->slot_free[sl], 0));
   RN_CUDA(fused_generate(g, pitch, field_stride, p->depth, w.i0, w.j0, w.ni, w.nj, law, p->persistence, p->seed, dev_seeds, nfields,
                          p->apply_volcano != 0, p->amplitude, ctx->slot[sl], stream, &ctx->launches, ctx->profiling ? ctx->ev : nullptr,
                          ctx->profiling ? &ctx->ev_stages : nullptr, overlap ? ctx->coarse_stream : nullptr,
-                         overlap ? ctx->coarse_done[sl] : nullptr));
+                         overlap ? ctx->coarse_done[sl] : nullptr, overlap ? ctx->tile_stream : nullptr, overlap ? ctx->tiles_done[sl] : nullptr));
   RN_CUDA(cudaEventRecord(ctx->slot_free[sl], stream));
   ctx->slot_used[sl] = true;
   return RN_OK;
@@ -266,9 +272,11 @@ int rn_create(int device, rn_context** out_ctx)
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   e = cudaStreamCreateWithPriority(&ctx->coarse_stream, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess && RN_TILE_STREAM) e = cudaStreamCreateWithPriority(&ctx->tile_stream, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   for (int k = 0; k < 2 && e == cudaSuccess; k++) {
     e = cudaEventCreateWithFlags(&ctx->coarse_done[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->tiles_done[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slot_free[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->chunk_ready[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->chunk_copied[k], cudaEventDisableTiming);
@@ -289,6 +297,10 @@ int rn_destroy(rn_context* ctx)
     cudaStreamSynchronize(ctx->coarse_stream);
     cudaStreamDestroy(ctx->coarse_stream);
   }
+  if (ctx->tile_stream) {
+    cudaStreamSynchronize(ctx->tile_stream);
+    cudaStreamDestroy(ctx->tile_stream);
+  }
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
@@ -299,6 +311,7 @@ int rn_destroy(rn_context* ctx)
   }
   for (int k = 0; k < 2; k++) {
     if (ctx->coarse_done[k]) cudaEventDestroy(ctx->coarse_done[k]);
+    if (ctx->tiles_done[k]) cudaEventDestroy(ctx->tiles_done[k]);
     if (ctx->slot_free[k]) cudaEventDestroy(ctx->slot_free[k]);
     if (ctx->chunk_ready[k]) cudaEventDestroy(ctx->chunk_ready[k]);
     if (ctx->chunk_copied[k]) cudaEventDestroy(ctx->chunk_copied[k]);

@@ -244,7 +244,7 @@ size_t fused_scratch_bytes(int depth, int nfields) { return chain_scratch_bytes(
 cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int depth, int i0, int j0, int ni, int nj, const Law& law,
                            float persistence, uint32_t seed, const uint32_t* seeds, int nfields, int volcano, float amplitude,
                            void* scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events, int* nstages,
-                           cudaStream_t coarse_stream, cudaEvent_t coarse_done)
+                           cudaStream_t coarse_stream, cudaEvent_t coarse_done, cudaStream_t tile_stream, cudaEvent_t tiles_done)
 {
   StageLaunch chain[kMaxLaunches];
   const int nl = build_chain(chain, depth, i0, j0, ni, nj, reinterpret_cast<E4*>(dst), pitch, field_stride, scratch, nfields, law,
@@ -257,22 +257,28 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
   bool has_coarse = false;
   for (int k = 0; k < nl; k++) has_coarse = has_coarse || !chain[k].last;
   const bool split = coarse_stream && coarse_done && coarse_stream != stream && !events && has_coarse;
-  bool joined = false;
+  // Streams of a split call: tile stages on tile_stream (if given), streamed coarse levels on coarse_stream, the output stage on
+  // the caller's stream; where the chain moves from one stream to the next an event carries the dependency.  The three streams
+  // are in-order, so consecutive calls pipeline stage by stage (the caller guards the scratch slot, see rn_abi.cu).
+  const bool three = split && tile_stream && tiles_done && tile_stream != stream && tile_stream != coarse_stream;
+  cudaStream_t prev_s = nullptr;
   for (int k = 0; k < nl; k++) {
     StageLaunch& sl = chain[k];
 #ifdef RN_TIMELINE
     sl.sp.tl_slot = sl.st.tl_slot = (g_tl_next++) & 1023;
 #endif
     const dim3 grid(sl.gx, sl.gy, (unsigned)nfields);
-    cudaStream_t s = (split && !sl.last) ? coarse_stream : stream;
+    cudaStream_t s = stream;
+    if (split && !sl.last) s = (three && sl.kind == 0) ? tile_stream : coarse_stream;
     cudaError_t e;
-    if (split && sl.last && !joined) {  // the output stage waits for the coarse stages
-      e = cudaEventRecord(coarse_done, coarse_stream);
+    if (split && k > 0 && s != prev_s) {  // the chain changes streams: this launch waits for the previous one
+      cudaEvent_t ev = (three && prev_s == tile_stream) ? tiles_done : coarse_done;
+      e = cudaEventRecord(ev, prev_s);
       if (e != cudaSuccess) return e;
-      e = cudaStreamWaitEvent(stream, coarse_done, 0);
+      e = cudaStreamWaitEvent(s, ev, 0);
       if (e != cudaSuccess) return e;
-      joined = true;
     }
+    prev_s = s;
     if (sl.kind == 1) {
       e = launch_stream(sl.st, sl.nt, grid, s);
     } else {

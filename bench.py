@@ -276,6 +276,20 @@ def workload_config(args):
     }
 
 
+def final_kernel_name(args):
+    """The kernel that writes the output of this workload (rn_plan.h: plan_stages)."""
+    if args.workload == "volume":
+        return "rn_volume.cu (3D extension)"
+    d = args.depth
+    half, full = (1 << (d - 1)) + 1, (1 << d) + 1
+    if d >= 10:
+        if args.algo == 3:
+            return f"k_stream<128,8> (round-1 block streaming kernel, last level {half}^2 -> {full}^2)"
+        return (f"k_march (warp-synchronous march, last level {half}^2 -> {full}^2: averageSquare/generateSquare, both generateDiamond loops, "
+                "ordered shade gather, addVolcano, 256-bit sector stores)")
+    return f"k_stage<2,64,512> (fused tile kernel, last two levels -> {full}^2)"
+
+
 # ------------------------------------------------------------------------ our arm ---
 def run_ours(args):
     import torch
@@ -391,7 +405,7 @@ def run_ours(args):
         if acc and acc[0]:
             ns = len(acc[0])
             mean = [statistics.mean(a[k] for a in acc) for k in range(ns)]
-            stage_ms = {"launch_ms": mean, "final_ms": mean[-1], "final_name": "k_stream<128> (last level 2049^2 -> 4097^2, streamed: S, D, G intervals + addVolcano + coalesced store)",
+            stage_ms = {"launch_ms": mean, "final_ms": mean[-1], "final_name": final_kernel_name(args),
                         "share_of_chain": mean[-1] / sum(mean)}
 
     # ---- e2e: the same C-ABI call with a HOST destination (pinned), D2H inside the timed region ----
@@ -461,6 +475,7 @@ def run_ours(args):
             "scaling": "weak" if args.workload == "field" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_step": (my_samples * bytes_per_sample / (statistics.mean(per_step) * 1e-3) / 1e9) / peak,
                          "traffic": ncu_traffic(args),
                          "kernel": k_name, "kernel_ms": k_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": my_samples * bytes_per_sample,

@@ -110,8 +110,10 @@ int rn_create(int device, rn_context** out_ctx);
 int rn_destroy(rn_context* ctx);
 /* Kernels launched by this context since creation (for the bench's claim). */
 uint64_t rn_launch_count(const rn_context* ctx);
-/* Select the synthesis algorithm: 0 = auto (fused tile kernels), 1 = level-synchronous
- * global-memory kernels (one launch set per level), 2 = fused tile kernels. */
+/* Select the synthesis algorithm: 0 = auto (= 2), 1 = level-synchronous global-memory kernels (one
+ * launch set per level), 2 = fused tile kernels for the coarse levels + the warp-synchronous march
+ * kernel for the last two levels of fields of depth >= 10, 3 = as 2 with the round-1 block streaming
+ * kernel for those levels.  1 and 3 are kept as independent cross-checks; all give the same bits. */
 int rn_set_algorithm(rn_context* ctx, int algo);
 
 /* Call pipelining (algorithm 2, on by default): the small coarse stages of a call run on the

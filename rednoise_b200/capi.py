@@ -196,9 +196,16 @@ class Context:
         return tuple(vpos) if want_volcano_pos else None
 
     def terrain2d_batch_ptr(self, p: Params, seeds, ptr: int, *, tile_stride_elems: int = 0,
-                            dst_is_device: bool = True, stream: int = 0):
-        arr = (C.c_uint32 * len(seeds))(*[int(s) & 0xFFFFFFFF for s in seeds])
-        _check(lib().rn_terrain2d_batch(self._h, C.byref(p), arr, len(seeds), C.c_void_p(ptr), tile_stride_elems,
+                            dst_is_device: bool = True, stream: int = 0, seeds_ptr: int = 0):
+        """seeds: sequence of ints, or -- with seeds_ptr -- the number of uint32 seeds at that HOST address (e.g. pinned memory,
+        which must stay untouched until the stream has passed the call: the upload is then truly asynchronous)."""
+        if seeds_ptr:
+            n = int(seeds)
+            arr = C.cast(C.c_void_p(seeds_ptr), C.POINTER(C.c_uint32))
+        else:
+            n = len(seeds)
+            arr = (C.c_uint32 * n)(*[int(s) & 0xFFFFFFFF for s in seeds])
+        _check(lib().rn_terrain2d_batch(self._h, C.byref(p), arr, n, C.c_void_p(ptr), tile_stride_elems,
                                         1 if dst_is_device else 0, C.c_void_p(stream) if stream else None))
 
     # -- numpy conveniences (host destination) -----------------------------------------

@@ -23,7 +23,15 @@ struct rn_context {
   void* field = nullptr;   size_t field_bytes = 0;    // full-field staging when dst is a window / host memory
   void* plane = nullptr;   size_t plane_bytes = 0;    // algorithm 1: offset plane; algorithm 2: coarse grids
   void* cells = nullptr;   size_t cells_bytes = 0;    // staging for rn_terrain2d_cells with a host destination
-  void* small = nullptr;   size_t small_bytes = 0;    // staging for rn_lcg_draws_device with a host dst; batch seeds
+  void* small = nullptr;   size_t small_bytes = 0;    // staging for rn_lcg_draws_device with a host dst; status words
+  // batch seeds: two buffers used alternately by consecutive rn_terrain2d_batch calls.  seeds_ready[b] is recorded on the
+  // caller's stream after the upload (the side streams wait for it before their first stage), seeds_free[b] after the last
+  // kernel of the call that reads buffer b (the next upload into b waits for it, whichever stream it is issued on).
+  void* seeds[2] = {nullptr, nullptr};   size_t seeds_bytes[2] = {0, 0};
+  cudaEvent_t seeds_ready[2] = {nullptr, nullptr};
+  cudaEvent_t seeds_free[2] = {nullptr, nullptr};
+  bool seeds_used[2] = {false, false};
+  uint64_t batch_seq = 0;
   // algorithm 2 pipelining: the coarse stages run on a high-priority side stream into one of two
   // scratch slots, so that they overlap the output stage of the previous call
   cudaStream_t coarse_stream = nullptr;
@@ -136,8 +144,9 @@ int synth_full_levelsync(rn_context* ctx, const rn_params* p, Elem* g, size_t pi
 }
 
 // Algorithm 2: the window `w` of `nfields` fields (seeds on the device, or p->seed) straight into device memory.
+// `after` (optional): an event on the caller's stream that every stage of the call must follow (the seeds upload of a batch).
 int synth_window_fused(rn_context* ctx, const rn_params* p, const rn_window& w, Elem* g, size_t pitch, size_t field_stride,
-                       const uint32_t* dev_seeds, int nfields, cudaStream_t stream)
+                       const uint32_t* dev_seeds, int nfields, cudaStream_t stream, cudaEvent_t after = nullptr)
 {
   const Law law = law_of(p);
   const size_t need = fused_scratch_bytes(p->depth, nfields);
@@ -149,12 +158,24 @@ int synth_window_fused(rn_context* ctx, const rn_params* p, const rn_window& w, 
     for (int k = 0; k < 17; k++) RN_CUDA(cudaEventCreate(&ctx->ev[k]));
   ctx->ev_stages = 0;
   const bool overlap = ctx->overlap && !ctx->profiling && ctx->coarse_stream;
-  if (ctx->slot_used[sl])  // the previous user of this scratch slot must have consumed it
-    RN_CUDA(cudaStreamWaitEvent(overlap ? (ctx->tile_stream ? ctx->tile_stream : ctx->coarse_stream) : stream, ctx->slot_free[sl], 0));
+  // The previous user of this scratch slot must have consumed it, and the call's inputs (batch seeds) must have landed, before
+  // ANY stream of this call starts: every side stream waits, whichever of them the plan happens to use first.
+  cudaStream_t first[3] = {stream, nullptr, nullptr};
+  int nfirst = 1;
+  if (overlap) {
+    nfirst = 0;
+    first[nfirst++] = ctx->coarse_stream;
+    if (ctx->tile_stream) first[nfirst++] = ctx->tile_stream;
+  }
+  for (int k = 0; k < nfirst; k++) {
+    if (ctx->slot_used[sl]) RN_CUDA(cudaStreamWaitEvent(first[k], ctx->slot_free[sl], 0));
+    if (after && first[k] != stream) RN_CUDA(cudaStreamWaitEvent(first[k], after, 0));
+  }
   RN_CUDA(fused_generate(g, pitch, field_stride, p->depth, w.i0, w.j0, w.ni, w.nj, law, p->persistence, p->seed, dev_seeds, nfields,
                          p->apply_volcano != 0, p->amplitude, ctx->slot[sl], stream, &ctx->launches, ctx->profiling ? ctx->ev : nullptr,
                          ctx->profiling ? &ctx->ev_stages : nullptr, overlap ? ctx->coarse_stream : nullptr,
-                         overlap ? ctx->coarse_done[sl] : nullptr, overlap ? ctx->tile_stream : nullptr, overlap ? ctx->tiles_done[sl] : nullptr));
+                         overlap ? ctx->coarse_done[sl] : nullptr, overlap ? ctx->tile_stream : nullptr, overlap ? ctx->tiles_done[sl] : nullptr,
+                         ctx->sm_count, ctx->algo != 3));
   RN_CUDA(cudaEventRecord(ctx->slot_free[sl], stream));
   ctx->slot_used[sl] = true;
   return RN_OK;
@@ -257,7 +278,8 @@ int rn_create(int device, rn_context** out_ctx)
   if (device >= count) return fail(RN_ERR_BAD_PARAM, "device index out of range");
   cudaDeviceProp prop;
   RN_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) return fail(RN_ERR_NO_DEVICE, "device is not sm_100 (the library ships sm_100a code only)");
+  if (prop.major != 10 || prop.minor != 0)  // arch-specific SASS only (no PTX): another CC 10.x part could not run it
+    return fail(RN_ERR_NO_DEVICE, "device is not sm_100 (the library ships sm_100a code only)");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
   rn_context* ctx = new (std::nothrow) rn_context();
@@ -280,6 +302,8 @@ int rn_create(int device, rn_context** out_ctx)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->slot_free[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->chunk_ready[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->chunk_copied[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->seeds_ready[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->seeds_free[k], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
     rn_destroy(ctx);
@@ -315,6 +339,9 @@ int rn_destroy(rn_context* ctx)
     if (ctx->slot_free[k]) cudaEventDestroy(ctx->slot_free[k]);
     if (ctx->chunk_ready[k]) cudaEventDestroy(ctx->chunk_ready[k]);
     if (ctx->chunk_copied[k]) cudaEventDestroy(ctx->chunk_copied[k]);
+    if (ctx->seeds_ready[k]) cudaEventDestroy(ctx->seeds_ready[k]);
+    if (ctx->seeds_free[k]) cudaEventDestroy(ctx->seeds_free[k]);
+    cudaFree(ctx->seeds[k]);
     cudaFree(ctx->slot[k]);
   }
   for (int k = 0; k < 17; k++)
@@ -332,7 +359,8 @@ uint64_t rn_launch_count(const rn_context* ctx) { return ctx ? ctx->launches : 0
 int rn_set_algorithm(rn_context* ctx, int algo)
 {
   if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
-  if (algo < 0 || algo > 2) return fail(RN_ERR_BAD_PARAM, "algorithm must be 0 (auto), 1 (level-synchronous) or 2 (fused tiles)");
+  if (algo < 0 || algo > 3)
+    return fail(RN_ERR_BAD_PARAM, "algorithm must be 0 (auto), 1 (level-synchronous), 2 (fused tiles + warp march) or 3 (fused tiles + block streaming)");
   ctx->algo = algo;
   return RN_OK;
 }
@@ -522,29 +550,38 @@ int rn_terrain2d_batch(rn_context* ctx, const rn_params* p, const uint32_t* seed
   cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
   const bool direct = dst_is_device && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
   const size_t field_bytes = side * side * sizeof(Elem);
-  // chunk so that staging (host destination) and the intermediate grids stay bounded
-  size_t chunk = direct ? 4096 : ((size_t)1 << 30) / field_bytes;
+  // chunk so that staging (host destination) and the intermediate grids (two scratch slots) stay bounded: the scratch of a
+  // chunk scales with its field count (21 MB per depth-11 field, 84 MB per depth-12 field)
+  const size_t scratch_per_field = fused_scratch_bytes(p->depth, 2) / 2;
+  const size_t budget = (size_t)1 << 30;
+  size_t chunk = direct ? budget / (scratch_per_field ? scratch_per_field : 1) : budget / field_bytes;
   if (chunk < 1) chunk = 1;
-  if (chunk > 32768) chunk = 32768;
-  st = ensure(&ctx->small, &ctx->small_bytes, sizeof(uint32_t) * (size_t)ntiles);
+  if (chunk > 32768) chunk = 32768;  // gridDim.z
+  const int sb = (int)(ctx->batch_seq++ & 1);
+  st = ensure(&ctx->seeds[sb], &ctx->seeds_bytes[sb], sizeof(uint32_t) * (size_t)ntiles);
   if (st != RN_OK) return st;
-  RN_CUDA(cudaMemcpyAsync(ctx->small, seeds, sizeof(uint32_t) * (size_t)ntiles, cudaMemcpyHostToDevice, stream));
+  if (ctx->seeds_used[sb]) RN_CUDA(cudaStreamWaitEvent(stream, ctx->seeds_free[sb], 0));
+  RN_CUDA(cudaMemcpyAsync(ctx->seeds[sb], seeds, sizeof(uint32_t) * (size_t)ntiles, cudaMemcpyHostToDevice, stream));
+  RN_CUDA(cudaEventRecord(ctx->seeds_ready[sb], stream));
   const rn_window w{0, 0, (int)side, (int)side};
   for (size_t t0 = 0; t0 < (size_t)ntiles; t0 += chunk) {
     const int nf = (int)(((size_t)ntiles - t0 < chunk) ? (size_t)ntiles - t0 : chunk);
-    const uint32_t* dseeds = reinterpret_cast<const uint32_t*>(ctx->small) + t0;
+    const uint32_t* dseeds = reinterpret_cast<const uint32_t*>(ctx->seeds[sb]) + t0;
     if (direct) {
-      st = synth_window_fused(ctx, p, w, reinterpret_cast<Elem*>(dst + t0 * tile_stride_elems), side, tile_stride_elems, dseeds, nf, stream);
+      st = synth_window_fused(ctx, p, w, reinterpret_cast<Elem*>(dst + t0 * tile_stride_elems), side, tile_stride_elems, dseeds, nf, stream,
+                              ctx->seeds_ready[sb]);
       if (st != RN_OK) return st;
     } else {
       st = ensure(&ctx->field, &ctx->field_bytes, field_bytes * (size_t)nf);
       if (st != RN_OK) return st;
-      st = synth_window_fused(ctx, p, w, reinterpret_cast<Elem*>(ctx->field), side, side * side, dseeds, nf, stream);
+      st = synth_window_fused(ctx, p, w, reinterpret_cast<Elem*>(ctx->field), side, side * side, dseeds, nf, stream, ctx->seeds_ready[sb]);
       if (st != RN_OK) return st;
       RN_CUDA(cudaMemcpy2DAsync(dst + t0 * tile_stride_elems, tile_stride_elems * sizeof(Elem), ctx->field, field_bytes, field_bytes, (size_t)nf,
                                 dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
     }
   }
+  RN_CUDA(cudaEventRecord(ctx->seeds_free[sb], stream));  // every stage of the call precedes its output stage on `stream`
+  ctx->seeds_used[sb] = true;
   if (!(stream_v && dst_is_device)) RN_CUDA(cudaStreamSynchronize(stream));
   return RN_OK;
 }

@@ -5,6 +5,7 @@
 // coalesced writes; the last two levels of a deep field are streamed.  Intermediate grids stay L2-resident between stages.
 #include "rn_kernels.h"
 #include "rn_plan.h"
+#include <atomic>
 
 namespace rn {
 
@@ -151,18 +152,74 @@ __global__ void __launch_bounds__(NT, MINB) k_stream(const __grid_constant__ Str
 #endif
 }
 
+// Warp-synchronous march (rn_march.cuh): every warp is an independent (strip, segment) unit; no shared memory, no barriers.
+template <bool EDGE, int PH>
+__device__ __forceinline__ void march_step(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, int u, int lane)
+{
+  using M = March<EDGE>;
+  M::template p1<PH>(sp, cx, L, u, lane);
+  M::template x1<PH>(L, nullptr, nullptr);
+  M::template p2<PH>(sp, cx, L, u, lane);
+  M::template x2<PH>(L, nullptr, nullptr);
+  M::template p3<PH>(sp, cx, L, u);
+  M::store(sp, cx, L, u, lane, nullptr);
+}
+
+template <int WPB, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB) k_march(const __grid_constant__ StreamParams sp, const int nunits)
+{
+  RN_TL_SCOPE(sp.tl_slot);
+  const int lane = (int)threadIdx.x & 31;
+  const int id = (int)blockIdx.x * WPB + ((int)threadIdx.x >> 5);
+  if (id >= nunits) return;
+  const MarchCtx cx = march_ctx(sp, id, blockIdx.z);
+  MarchLane L;
+  March<true>::init(sp, cx, L, lane, false);
+  const int last = cx.a1e;
+  int u = cx.a0 - 1;
+  while (u <= last) {
+    if (march_step_is_lean(cx, u)) {
+      // two steps per trip: the register bank of every carried value is a compile-time constant
+      const int hi = cx.lean_hi;
+      for (;;) {
+        march_step<false, 0>(sp, cx, L, u, lane);
+        if (u == hi) {
+          March<false>::swap_banks(L);  // an odd number of lean steps: the next (EDGE) step expects its row in bank 0
+          break;
+        }
+        march_step<false, 1>(sp, cx, L, u + 1, lane);
+        if (u + 1 == hi) break;
+        u += 2;
+      }
+      u = hi + 1;
+    } else {
+      march_step<true, 0>(sp, cx, L, u, lane);
+      March<true>::swap_banks(L);
+      u++;
+    }
+  }
+}
+
+cudaError_t launch_march(const StreamParams& st, dim3 grid_units, cudaStream_t stream)
+{
+  const int nunits = (int)grid_units.x;
+  const dim3 grid((unsigned)((nunits + kMarchWPB - 1) / kMarchWPB), 1, grid_units.z);
+  k_march<kMarchWPB, kMarchWarpsPerSM / kMarchWPB><<<grid, 32 * kMarchWPB, 0, stream>>>(st, nunits);
+  return cudaGetLastError();
+}
+
 template <int NT, int MINB>
 cudaError_t launch_stream_t(const StreamParams& st, dim3 grid, cudaStream_t stream)
 {
   using G = StreamGeo<NT>;
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64] = {};  // contexts may launch from several host threads
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev < 64 && !configured[dev]) {
+  if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     e = cudaFuncSetAttribute(k_stream<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES);
     if (e != cudaSuccess) return e;
-    configured[dev] = true;
+    if (dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   k_stream<NT, MINB><<<grid, NT, G::BYTES, stream>>>(st);
   return cudaGetLastError();
@@ -178,14 +235,14 @@ template <int L, int T, int NT>
 cudaError_t launch_stage_t(const StageParams& sp, dim3 grid, cudaStream_t stream)
 {
   using G = TileGeo<L, T>;
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64] = {};  // contexts may launch from several host threads
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev < 64 && !configured[dev]) {
+  if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     e = cudaFuncSetAttribute(k_stage<L, T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BYTES);
     if (e != cudaSuccess) return e;
-    configured[dev] = true;
+    if (dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   k_stage<L, T, NT><<<grid, NT, G::BYTES, stream>>>(sp);
   return cudaGetLastError();
@@ -244,11 +301,12 @@ size_t fused_scratch_bytes(int depth, int nfields) { return chain_scratch_bytes(
 cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int depth, int i0, int j0, int ni, int nj, const Law& law,
                            float persistence, uint32_t seed, const uint32_t* seeds, int nfields, int volcano, float amplitude,
                            void* scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events, int* nstages,
-                           cudaStream_t coarse_stream, cudaEvent_t coarse_done, cudaStream_t tile_stream, cudaEvent_t tiles_done)
+                           cudaStream_t coarse_stream, cudaEvent_t coarse_done, cudaStream_t tile_stream, cudaEvent_t tiles_done, int sm_count,
+                           int march)
 {
   StageLaunch chain[kMaxLaunches];
   const int nl = build_chain(chain, depth, i0, j0, ni, nj, reinterpret_cast<E4*>(dst), pitch, field_stride, scratch, nfields, law,
-                             persistence, seed, seeds, volcano, amplitude);
+                             persistence, seed, seeds, volcano, amplitude, sm_count > 0 ? sm_count : 148, march);
   if (nstages) *nstages = nl;
   if (events) {
     cudaError_t e0 = cudaEventRecord(events[0], stream);
@@ -279,7 +337,9 @@ cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int dep
       if (e != cudaSuccess) return e;
     }
     prev_s = s;
-    if (sl.kind == 1) {
+    if (sl.kind == 2) {
+      e = launch_march(sl.st, grid, s);
+    } else if (sl.kind == 1) {
       e = launch_stream(sl.st, sl.nt, grid, s);
     } else {
       switch (sl.L) {

@@ -11,13 +11,14 @@ namespace rn {
 cudaError_t levelsync_generate(Elem* g, float* off, size_t pitch, int depth, int nlevels, const Law& law, float persistence,
                                uint32_t seed, cudaStream_t stream, uint64_t* launches);
 
-// Algorithm 2 (rn_fused.cu): fused tile kernels, 2-4 launches per field; writes only the requested window.
+// Algorithm 2 (rn_fused.cu): fused tile kernels + streamed last levels, 2-6 launches per field; writes only the requested window.
+// march: streamed levels run the warp-synchronous kernel (rn_march.cuh), else the round-1 block kernel (rn_stream.cuh).
 size_t fused_scratch_bytes(int depth, int nfields);
 cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int depth, int i0, int j0, int ni, int nj, const Law& law,
                            float persistence, uint32_t seed, const uint32_t* seeds, int nfields, int volcano, float amplitude,
                            void* scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events = nullptr, int* nstages = nullptr,
                            cudaStream_t coarse_stream = nullptr, cudaEvent_t coarse_done = nullptr, cudaStream_t tile_stream = nullptr,
-                           cudaEvent_t tiles_done = nullptr);
+                           cudaEvent_t tiles_done = nullptr, int sm_count = 0, int march = 1);
 
 // Cell-quadtree attributes of a finished field (rn_cells.cu; Terrain.cpp:260-356): `cells` = rn_cell[(4^depth-1)/3].
 cudaError_t cells_generate(void* cells, const Elem* field, size_t pitch, int depth, float feature_scale, float size, float amplitude,

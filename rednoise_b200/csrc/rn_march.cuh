@@ -1,0 +1,477 @@
+// rn_march.cuh -- algorithm 2, warp-synchronous streaming form of ONE level of the diamond-square path
+// (Terrain.cpp:60-82 for a single `step`): the output kernel of deep fields since round 2.
+//
+// Same march as rn_stream.cuh (a strip of cell columns walked row by row, nothing recomputed in the marching
+// direction, ordered shade gather), re-cut for the instruction-issue bound that kernel ran into:
+//   * ONE WARP owns a strip and nothing is shared between warps: no shared memory, no block barriers.  What a lane needs
+//     from its neighbours (one centre, two generateSquare losses, two generateDiamond losses per step) travels by
+//     warp shuffles; everything else lives in registers across steps.
+//   * a lane owns TWO adjacent cell columns, so its two square centres, its two loop-1 midpoints and its two loop-2
+//     midpoints are each evaluated as ONE packed-FP32 instruction stream (rn_math.cuh: F2, displace2), the values the two
+//     cells share are loaded once, and the per-step bookkeeping is paid once per eight output samples;
+//   * a lane's four output columns of a row are contiguous: finished rows go from registers to global memory as full
+//     32-byte sectors (st.global.v8.f32 -> STG.E.ENL2.256).  Rows whose first sample sits on an odd 16-byte slot (every
+//     other row of a (W+1)-pitched field) are shifted by one sample with four shuffles; the two samples at the warp's
+//     ends are stored as 16-byte halves.  The input lattice (this library's own scratch, even pitch) is read with one
+//     256-bit and one 128-bit load per lane and step.
+//
+// Lanes: lane l holds the lattice / cell columns k0 = L0 + 2l and k1 = k0 + 1 (L0 even) and reads column k1 + 1 as well.
+// Lanes 0 and 31 are halo: their samples are incomplete (they have no left / right neighbour) and are never stored, so a
+// warp finishes the 60 cell columns [L0 + 2, L0 + 62) = 120 output columns per row.
+//
+// Step u (cell row u; vocabulary of rn_tile.cuh):
+//   P1   S(u): centres C(u, k0), C(u, k1) from lattice rows u, u+1        (averageSquare + generateSquare)
+//   X1   losses TS(u, .) to both neighbours, C(u, k1) to the right neighbour
+//   P2   D(u): mids M1(u, k0), M1(u, k1) and M2(u-1, k0), M2(u-1, k1)       (averageDiamond + generateDiamond);
+//        lattice row u+2 is requested from global memory into the registers row u occupied
+//   X2   losses TD1(u, k1) to the right, TD2(u-1, k0) to the left neighbour
+//   P3   G(u-1): final shade of corners K(u-1, .) and centres C(u-1, .) (ordered gather), addVolcano, store of output
+//        rows 2(u-1) and 2(u-1)+1
+// Values of step u-1 that step u needs sit in the other of two register banks; the march is unrolled by two with the bank
+// as a template argument, so no value is ever moved.  Steps that touch the first / last lattice rows and strips on a
+// lattice column border run the EDGE instantiation (existence tests, border forms, per-sample stores).
+//
+// Compiles as plain C++ for tests/host_replay (a warp = 32 MarchLane structs, a shuffle = a read of the neighbour's struct).
+#pragma once
+#include "rn_stream.cuh"
+
+namespace rn {
+
+constexpr int kMarchCols = 60;  // cell columns a warp finishes
+
+struct MarchLane {
+  E4 lat[2][3];    // bank (t&1): K(u, k0), K(u, k1), K(u, k1+1) as read (pos + input shade); other bank: row u+1
+  E4 kc[2][2];     // bank (t&1): K'(u, k0/k1) = corner with the shade generateSquare's scatter left (written in P2)
+  E4 cen[2][3];    // bank (t&1): C(u, k0-1), C(u, k0), C(u, k1)
+  E4 m1[2][2];     // bank (t&1): M1(u, k0/k1)
+  float ts[2][4];  // bank (t&1): TS(u; k0-1, k0, k1, k1+1)
+  float td1[2][3]; // bank (t&1): TD1(u; k0-1, k0, k1)
+  float td2[2][3]; // bank (t&1): TD2(u-1; k0, k1, k1+1)
+  uint32_t sS, sD1, sD2;  // LCG states whose extraction is the draw of column k0's next S / loop-1 / loop-2 call
+  const E4* src;   // lattice (row of the next prefetch, column k0)
+  E4* dst;         // output (row 2(u-1), column 2*k0) of the step in progress, relative to the window
+  float fy2[4];    // squared column distance of the lane's four output columns from the volcano
+  int ok;          // bit j: output column 2*k0 + j belongs to the strip and lies inside the stored window
+  E4 out[2][4];    // P3: the two finished output rows of the lane (transient)
+};
+
+struct MarchCtx {
+  int L0;          // lattice column of lane 0's first column (even)
+  int B0, CW, CWe; // owned cell columns [B0, B0+CW), B0 = L0 + 2; CWe = CW + 1 with the closing output column W
+  int a0, a1, a1e; // owned cell rows [a0, a1); a1e = a1 + 1 with the closing output row W
+  uint32_t seed;
+  const E4* gin;
+  E4* gout;
+  int far;         // every sample of the warp lies outside the volcano's crater
+  int lean_lo, lean_hi;  // steps that touch no lattice row border
+  int col_lean;    // all 65 lattice columns of the warp exist and it owns no closing column
+  int fast;        // the warp's 120 output columns are all owned and inside the window: sector stores
+  int in256;       // the input rows can be read with 256-bit loads
+};
+
+// id enumerates (strip, segment) pairs exactly like stream_ctx: the strips on a lattice column border first, cut into
+// shorter segments because every one of their steps runs the slower EDGE instantiation.
+RN_HD MarchCtx march_ctx(const StreamParams& sp, int id, unsigned f)
+{
+  MarchCtx cx;
+  const int ne = sp.edge_first + sp.edge_last;
+  int strip, seg, rows;
+  if (id < ne * sp.nseg_edge) {
+    seg = ne == 2 ? id >> 1 : id;
+    strip = (ne == 2 ? (id & 1) : sp.edge_last) ? sp.nstrips - 1 : 0;
+    if (ne == 1 && sp.edge_first) strip = 0;
+    rows = sp.seg_rows_edge;
+  } else {
+    const int k = id - ne * sp.nseg_edge, ni = sp.nstrips - ne;
+    seg = k / ni;
+    strip = sp.edge_first + (k - seg * ni);
+    rows = sp.seg_rows;
+  }
+  const int n = sp.lev.n;
+  cx.B0 = sp.b_lo + strip * sp.strip_cols;
+  cx.L0 = cx.B0 - 2;
+  cx.CW = imin_(sp.strip_cols, sp.b_hi - cx.B0);
+  cx.CWe = cx.CW + ((sp.close_j && cx.B0 + cx.CW == sp.b_hi) ? 1 : 0);
+  cx.a0 = sp.a_lo + seg * rows;
+  cx.a1 = imin_(cx.a0 + rows, sp.a_hi);
+  cx.a1e = cx.a1 + ((sp.close_i && cx.a1 == sp.a_hi) ? 1 : 0);
+  cx.seed = sp.seeds ? sp.seeds[f] : sp.seed;
+  cx.gin = sp.gin + (size_t)f * sp.gin_field_stride;
+  cx.gout = sp.gout + (size_t)f * sp.gout_field_stride;
+  cx.far = stream_box_is_far(2 * cx.a0, 2 * cx.a1e - 1, 2 * cx.B0, 2 * (cx.B0 + cx.CWe) - 1, 1 << sp.dout);
+  cx.col_lean = cx.L0 >= 0 && cx.L0 + 64 <= n && cx.CWe == cx.CW;
+  cx.lean_lo = imax_(cx.a0 - 1, 1);
+  cx.lean_hi = cx.a1e <= n - 1 ? cx.a1e : n - 2;
+  cx.fast = cx.CW == kMarchCols && cx.CWe == cx.CW && 2 * cx.B0 >= sp.win_j0 && 2 * (cx.B0 + cx.CW) <= sp.win_j0 + sp.win_nj;
+  cx.in256 = (sp.gin_pitch % 2 == 0) && (sp.gin_field_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(sp.gin) % 32 == 0);
+  return cx;
+}
+RN_HD bool march_step_is_lean(const MarchCtx& cx, int u) { return cx.col_lean && u >= cx.lean_lo && u <= cx.lean_hi; }
+
+// ---------------------------------------------------------------- lane <-> lane and lane <-> memory ----
+// On the device a value from the neighbouring lane is a shuffle; in the host replay the caller passes the neighbour's struct
+// (nullptr at the ends of the warp, where the device shuffle returns the lane's own value: such values only ever reach
+// the halo lanes' own, never stored, samples -- the replay feeds NaN there to prove it).
+RN_HD float march_nan()
+{
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(0x7fc0beef);
+#else
+  union { uint32_t u; float f; } v;
+  v.u = 0x7fc0beefu;
+  return v.f;
+#endif
+}
+RN_HD float from_left(float mine, const float* theirs)   // the value `mine` names, as held by lane - 1
+{
+#if defined(__CUDA_ARCH__)
+  (void)theirs;
+  return __shfl_up_sync(0xffffffffu, mine, 1);
+#else
+  (void)mine;
+  return theirs ? *theirs : march_nan();
+#endif
+}
+RN_HD float from_right(float mine, const float* theirs)  // ... by lane + 1
+{
+#if defined(__CUDA_ARCH__)
+  (void)theirs;
+  return __shfl_down_sync(0xffffffffu, mine, 1);
+#else
+  (void)mine;
+  return theirs ? *theirs : march_nan();
+#endif
+}
+RN_HD E4 from_left4(const E4& mine, const E4* theirs)
+{
+  E4 r;
+  r.x = from_left(mine.x, theirs ? &theirs->x : nullptr);
+  r.y = from_left(mine.y, theirs ? &theirs->y : nullptr);
+  r.z = from_left(mine.z, theirs ? &theirs->z : nullptr);
+  r.w = from_left(mine.w, theirs ? &theirs->w : nullptr);
+  return r;
+}
+
+RN_HD void st128(E4* p, const E4& a) { *p = a; }
+RN_HD void st256(E4* p, const E4& a, const E4& b)  // p is 32-byte aligned: one full sector
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y),
+               "f"(b.z), "f"(b.w)
+               : "memory");
+#else
+  p[0] = a;
+  p[1] = b;
+#endif
+}
+RN_HD void ld256(const E4* p, E4& a, E4& b)
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+#else
+  a = p[0];
+  b = p[1];
+#endif
+}
+
+// Two samples displaced at once from their averaged elements and direction vectors (the tail of generateSquare /
+// generateDiamond, Terrain.cpp:185-213,230-257): displace2 + the shade terms, bit for bit what mid_interior2 does.
+RN_HD void displaced_pair(const Law& law, F2 a_xy, F2 a_zw, F2 b_xy, F2 b_zw, const V3P& dir1, const V3P& dir2, float blah, uint32_t draw_a,
+                          uint32_t draw_b, E4* out_a, E4* out_b, float* loss_a, float* loss_b)
+{
+  const Displaced2 dp = displace2(law, f2lo(a_xy), f2hi(a_xy), f2lo(b_xy), f2hi(b_xy), dir1, dir2, blah, draw_a, draw_b);
+  const F2 rs = f2s(law.radiosity_strength);
+  const F2 gain = f2mul(dp.offset, rs);
+  const F2 loss = f2mul(f2mul(f2s(0.25f), dp.offset), rs);
+  *loss_a = f2lo(loss);
+  *loss_b = f2hi(loss);
+  *out_a = E4{f2lo(a_xy) + f2lo(dp.shift.x), f2hi(a_xy) + f2lo(dp.shift.y), f2lo(a_zw) + f2lo(dp.shift.z), f2hi(a_zw) + f2lo(gain)};
+  *out_b = E4{f2lo(b_xy) + f2hi(dp.shift.x), f2hi(b_xy) + f2hi(dp.shift.y), f2lo(b_zw) + f2hi(dp.shift.z), f2hi(b_zw) + f2hi(gain)};
+}
+
+// averageSquare + generateSquare (Terrain.cpp:216-258) for the two cells of a lane: cell A has corners a00 (u, k), a10 (u+1, k),
+// a01 (u, k+1), a11 (u+1, k+1); cell B likewise.  Same operand order as the scalar form in rn_stream.cuh interval1.
+RN_HD void centre_pair(const Law& law, const E4& a00, const E4& a10, const E4& a01, const E4& a11, const E4& b00, const E4& b10, const E4& b01,
+                       const E4& b11, float blah, uint32_t draw_a, uint32_t draw_b, E4* out_a, E4* out_b, float* loss_a, float* loss_b)
+{
+  const F2 q = f2s(0.25f);
+  const F2 a_xy = f2mul(f2add(f2add(f2add(e4_xy(a00), e4_xy(a10)), e4_xy(a01)), e4_xy(a11)), q);
+  const F2 a_zw = f2mul(f2add(f2add(f2add(e4_zw(a00), e4_zw(a10)), e4_zw(a01)), e4_zw(a11)), q);
+  const F2 b_xy = f2mul(f2add(f2add(f2add(e4_xy(b00), e4_xy(b10)), e4_xy(b01)), e4_xy(b11)), q);
+  const F2 b_zw = f2mul(f2add(f2add(f2add(e4_zw(b00), e4_zw(b10)), e4_zw(b01)), e4_zw(b11)), q);
+  const V3P dir1 = v3p(vsub(pos4(a11), pos4(a00)), vsub(pos4(b11), pos4(b00)));
+  const V3P dir2 = v3p(vsub(pos4(a10), pos4(a01)), vsub(pos4(b10), pos4(b01)));
+  displaced_pair(law, a_xy, a_zw, b_xy, b_zw, dir1, dir2, blah, draw_a, draw_b, out_a, out_b, loss_a, loss_b);
+}
+
+template <bool EDGE>
+struct March {
+  static RN_HD bool lattice_exists(const StreamParams& sp, int r, int k)
+  {
+    const int n = sp.lev.n;
+    return r >= 0 && r <= n && k >= 0 && k <= n;
+  }
+  // lattice row r, columns k0 .. k0+2 of the lane, from p = &gin[r][k0]
+  static RN_HD void load_row(const StreamParams& sp, const MarchCtx& cx, const E4* p, int r, int k0, E4* dst3)
+  {
+    if (!EDGE) {
+      if (cx.in256) ld256(p, dst3[0], dst3[1]);
+      else { dst3[0] = p[0]; dst3[1] = p[1]; }
+      dst3[2] = p[2];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+        if (lattice_exists(sp, r, k0 + q)) dst3[q] = p[q];
+    }
+  }
+
+  // ------------------------------------------------------------------ start-up ----
+  static RN_HD void init(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, int lane, bool poison)
+  {
+    const int u0 = cx.a0 - 1;
+    const int k0 = cx.L0 + 2 * lane;
+    const uint32_t n = (uint32_t)sp.lev.n;
+    const float z = poison ? march_nan() : 0.0f;
+    const E4 z4 = E4{z, z, z, z};
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) { L.lat[b][q] = z4; L.cen[b][q] = z4; L.td1[b][q] = z; L.td2[b][q] = z; }
+#pragma unroll
+      for (int q = 0; q < 2; q++) { L.kc[b][q] = z4; L.m1[b][q] = z4; }
+#pragma unroll
+      for (int q = 0; q < 4; q++) { L.ts[b][q] = z; L.out[b][q] = z4; }
+    }
+    L.sS = lcg_skip(cx.seed, sp.lev.kS + (uint32_t)u0 * n + (uint32_t)k0);
+    L.sD1 = lcg_skip(cx.seed, sp.lev.kD1 + (uint32_t)u0 * n + (uint32_t)k0);
+    L.sD2 = lcg_skip(cx.seed, sp.lev.kD2 + (uint32_t)(u0 - 1) * (n + 1u) + (uint32_t)k0);
+    const int Wout = 1 << sp.dout;
+    L.ok = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int gj = 2 * k0 + j;
+      const int b = k0 + (j >> 1);  // owning cell column
+      const float fy = (float)(gj - Wout / 2);
+      L.fy2[j] = fy * fy;
+      const bool owned = (b >= cx.B0 && b < cx.B0 + cx.CW) || (gj == 2 * (cx.B0 + cx.CW) && cx.CWe != cx.CW);
+      if (owned && (unsigned)(gj - sp.win_j0) < (unsigned)sp.win_nj) L.ok |= 1 << j;
+    }
+    // (both pointers may start outside their grids; they are only dereferenced where the row / column exists)
+    L.src = cx.gin + ((ptrdiff_t)u0 * (ptrdiff_t)sp.gin_pitch + (ptrdiff_t)k0);
+    L.dst = cx.gout + ((ptrdiff_t)(2 * (u0 - 1) - sp.win_i0) * (ptrdiff_t)sp.gout_pitch + (ptrdiff_t)(2 * k0 - sp.win_j0));  // the first step finishes cell row u0 - 1
+#pragma unroll
+    for (int b = 0; b < 2; b++) {  // rows u0, u0+1 -> banks 0, 1
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+        if (lattice_exists(sp, u0 + b, k0 + q)) L.lat[b][q] = L.src[q];
+      L.src += sp.gin_pitch;
+    }
+  }
+
+  // ------------------------------------------------------------------ P1: S(u) ----
+  template <int PH>
+  static RN_HD void p1(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, int u, int lane)
+  {
+    const E4* ka = L.lat[PH];
+    const E4* kb = L.lat[PH ^ 1];
+    const uint32_t sB = kLcgA * L.sS + kLcgC;
+    const uint32_t draw_a = lcg_draw_from_state(L.sS), draw_b = lcg_draw_from_state(sB);
+    L.sS = jump_apply(sp.jn, L.sS);
+    if (!EDGE) {
+      centre_pair(sp.law, ka[0], kb[0], ka[1], kb[1], ka[1], kb[1], ka[2], kb[2], sp.lev.blahS, draw_a, draw_b, &L.cen[PH][1], &L.cen[PH][2],
+                  &L.ts[PH][1], &L.ts[PH][2]);
+    } else {
+      const int n = sp.lev.n;
+      const int k0 = cx.L0 + 2 * lane;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int bg = k0 + q;
+        float loss = 0.0f;
+        if (u >= 0 && u < n && bg >= 0 && bg < n) {
+          const E4 k00 = ka[q], k01 = ka[q + 1], k10 = kb[q], k11 = kb[q + 1];
+          const E4 a4 = avg4_packed(k00, k10, k01, k11);
+          const Displaced dp = displace<true>(sp.law, pos4(a4), vsub(pos4(k11), pos4(k00)), vsub(pos4(k10), pos4(k01)), sp.lev.blahS, q ? draw_b : draw_a);
+          L.cen[PH][1 + q] = e4_of(dp.pos, a4.w + shade_gain(sp.law, dp.offset));
+          loss = shade_loss(sp.law, dp.offset);
+        }
+        L.ts[PH][1 + q] = loss;
+      }
+    }
+  }
+  template <int PH>
+  static RN_HD void x1(MarchLane& L, const MarchLane* left, const MarchLane* right)
+  {
+    L.ts[PH][0] = from_left(L.ts[PH][2], left ? &left->ts[PH][2] : nullptr);
+    L.ts[PH][3] = from_right(L.ts[PH][1], right ? &right->ts[PH][1] : nullptr);
+    L.cen[PH][0] = from_left4(L.cen[PH][2], left ? &left->cen[PH][2] : nullptr);
+  }
+
+  // ------------------------------------------------------------------ P2: D(u) ----
+  template <int PH>
+  static RN_HD void p2(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, int u, int lane)
+  {
+    const E4* ka = L.lat[PH];
+    const float* tsm = L.ts[PH ^ 1];
+    const float* tsc = L.ts[PH];
+    const E4* cenm = L.cen[PH ^ 1];
+    const E4* cenc = L.cen[PH];
+    const E4* kcm = L.kc[PH ^ 1];
+    // corner shades as generateSquare left them (Terrain.cpp:252-255): minus the scatter of the 4 surrounding centres,
+    // in call order (u-1, k-1), (u-1, k), (u, k-1), (u, k)
+    E4 K0 = ka[0], K1 = ka[1], K2 = ka[2];
+    K0.w = (((K0.w - tsm[0]) - tsm[1]) - tsc[0]) - tsc[1];
+    K1.w = (((K1.w - tsm[1]) - tsm[2]) - tsc[1]) - tsc[2];
+    K2.w = (((K2.w - tsm[2]) - tsm[3]) - tsc[2]) - tsc[3];
+    const uint32_t s1B = kLcgA * L.sD1 + kLcgC, s2B = kLcgA * L.sD2 + kLcgC;
+    const uint32_t d1a = lcg_draw_from_state(L.sD1), d1b = lcg_draw_from_state(s1B);
+    const uint32_t d2a = lcg_draw_from_state(L.sD2), d2b = lcg_draw_from_state(s2B);
+    L.sD1 = jump_apply(sp.jn, L.sD1);
+    L.sD2 = jump_apply(sp.jn1, L.sD2);
+    if (!EDGE) {
+      // loop 1: M1(u, k) at output (2u, 2k+1): x neighbours C(u-1, k), C(u, k); y neighbours K'(u, k), K'(u, k+1)
+      mid_interior2(sp.law, cenm[1], cenc[1], K0, K1, cenm[2], cenc[2], K1, K2, sp.lev.blahD, d1a, d1b, &L.m1[PH][0], &L.m1[PH][1], &L.td1[PH][1],
+                    &L.td1[PH][2]);
+      // loop 2: M2(u-1, k) at output (2u-1, 2k): x neighbours K'(u-1, k), K'(u, k); y neighbours C(u-1, k-1), C(u-1, k)
+      mid_interior2(sp.law, kcm[0], K0, cenm[0], cenm[1], kcm[1], K1, cenm[1], cenm[2], sp.lev.blahD, d2a, d2b, &L.out[1][0], &L.out[1][2],
+                    &L.td2[PH][0], &L.td2[PH][1]);
+    } else {
+      const int n = sp.lev.n;
+      const int k0 = cx.L0 + 2 * lane;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int bg = k0 + q;
+        const bool v1 = u >= 0 && u <= n && bg >= 0 && bg < n;
+        const bool v2 = u - 1 >= 0 && u - 1 < n && bg >= 0 && bg <= n;
+        const E4 k00 = q ? K1 : K0, k01 = q ? K2 : K1;
+        float loss1 = 0.0f, loss2 = 0.0f;
+        if (v1) {
+          if (u == 0 || u == n) {
+            const E4 dummy = k00;
+            L.m1[PH][q] = mid_border(sp.law, u == 0 ? dummy : cenm[1 + q], u == n ? dummy : cenc[1 + q], k00, k01, u == 0, u == n, false, false,
+                                     sp.lev.blahDh, q ? d1b : d1a, &loss1);
+          } else {
+            L.m1[PH][q] = mid_interior(sp.law, cenm[1 + q], cenc[1 + q], k00, k01, sp.lev.blahD, q ? d1b : d1a, &loss1);
+          }
+        }
+        if (v2) L.out[1][2 * q] = mid_select_y(sp.law, kcm[q], k00, cenm[q], cenm[1 + q], bg == 0, bg == n, sp.lev.blahD, q ? d2b : d2a, &loss2);
+        L.td1[PH][1 + q] = loss1;
+        L.td2[PH][q] = loss2;
+      }
+    }
+    L.kc[PH][0] = K0;
+    L.kc[PH][1] = K1;
+    // lattice row u+2 (S(u+1) and D(u+2) need it) into the bank row u occupied
+    if (u + 1 <= cx.a1e) load_row(sp, cx, L.src, u + 2, cx.L0 + 2 * lane, L.lat[PH]);
+    L.src += sp.gin_pitch;
+  }
+  template <int PH>
+  static RN_HD void x2(MarchLane& L, const MarchLane* left, const MarchLane* right)
+  {
+    L.td1[PH][0] = from_left(L.td1[PH][2], left ? &left->td1[PH][2] : nullptr);
+    L.td2[PH][2] = from_right(L.td2[PH][0], right ? &right->td2[PH][0] : nullptr);
+  }
+
+  // ------------------------------------------------------------------ P3: G(u-1), addVolcano ----
+  template <int PH>
+  static RN_HD void p3(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, int u)
+  {
+    const float* tdm = L.td1[PH ^ 1];
+    const float* tdc = L.td1[PH];
+    const float* t2mm = L.td2[PH ^ 1];
+    const float* t2 = L.td2[PH];
+    // corner K(u-1, k): generateSquare's scatter (carried), then loop 1 (same row: k-1, k), loop 2 (same column: u-2, u-1)
+    E4 c0 = L.kc[PH ^ 1][0], c1 = L.kc[PH ^ 1][1];
+    c0.w = (((c0.w - tdm[0]) - tdm[1]) - t2mm[0]) - t2[0];
+    c1.w = (((c1.w - tdm[1]) - tdm[2]) - t2mm[1]) - t2[1];
+    // centre C(u-1, k): loop-1 mids above and below, loop-2 mids left and right
+    E4 e0 = L.cen[PH ^ 1][1], e1 = L.cen[PH ^ 1][2];
+    e0.w = (((e0.w - tdm[1]) - tdc[1]) - t2[0]) - t2[1];
+    e1.w = (((e1.w - tdm[2]) - tdc[2]) - t2[1]) - t2[2];
+    L.out[0][0] = c0;
+    L.out[0][1] = L.m1[PH ^ 1][0];
+    L.out[0][2] = c1;
+    L.out[0][3] = L.m1[PH ^ 1][1];
+    L.out[1][1] = e0;
+    L.out[1][3] = e1;
+    if (sp.volcano) {  // uniform
+      const int Wout = 1 << sp.dout;
+      const float gain_w = sp.volcano_gain * (float)Wout;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const float fx = (float)(2 * (u - 1) + r - Wout / 2);
+        const float fx2 = fx * fx;
+        if (!EDGE && cx.far) {  // uniform; two columns at once (packed pair)
+          const F2 h01 = f2mul(rcp_rn_normal2(sqrt_rn_normal2(f2add(f2s(fx2), f2(L.fy2[0], L.fy2[1])))), f2s(gain_w));
+          const F2 h23 = f2mul(rcp_rn_normal2(sqrt_rn_normal2(f2add(f2s(fx2), f2(L.fy2[2], L.fy2[3])))), f2s(gain_w));
+          L.out[r][0].y = L.out[r][0].y + f2lo(h01);
+          L.out[r][1].y = L.out[r][1].y + f2hi(h01);
+          L.out[r][2].y = L.out[r][2].y + f2lo(h23);
+          L.out[r][3].y = L.out[r][3].y + f2hi(h23);
+        } else {
+          const float inv_w = 1.0f / (float)Wout;
+#pragma unroll
+          for (int j = 0; j < 4; j++) L.out[r][j].y = L.out[r][j].y + volcano_height_r2<false>(fx2 + L.fy2[j], inv_w, sp.volcano_gain, gain_w);
+        }
+      }
+    }
+  }
+
+  static RN_HD void swap_banks(MarchLane& L)
+  {
+#define RN_SWAP_(T, a, b) { const T t__ = a; a = b; b = t__; }
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      RN_SWAP_(E4, L.lat[0][q], L.lat[1][q]) RN_SWAP_(E4, L.cen[0][q], L.cen[1][q]) RN_SWAP_(float, L.td1[0][q], L.td1[1][q])
+      RN_SWAP_(float, L.td2[0][q], L.td2[1][q])
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++) { RN_SWAP_(E4, L.kc[0][q], L.kc[1][q]) RN_SWAP_(E4, L.m1[0][q], L.m1[1][q]) }
+#pragma unroll
+    for (int q = 0; q < 4; q++) RN_SWAP_(float, L.ts[0][q], L.ts[1][q])
+#undef RN_SWAP_
+  }
+
+  // ------------------------------------------------------------------ store of cell row a = u-1 ----
+  // `left`: host replay only (the lane to the left); on the device the shifted rows shuffle.
+  static RN_HD void store(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, int u, int lane, const MarchLane* left)
+  {
+    const int a = u - 1;
+    const int Wout = 1 << sp.dout;
+    E4* dst = L.dst;
+    L.dst = dst + 2 * sp.gout_pitch;
+    if (a < cx.a0 || a >= cx.a1e) return;  // uniform
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int gi = 2 * a + r;
+      if ((unsigned)(gi - sp.win_i0) >= (unsigned)sp.win_ni || gi > Wout) continue;  // uniform
+      E4* row = r == 0 ? dst : dst + sp.gout_pitch;
+      const E4* v = L.out[r];
+      if (!EDGE && cx.fast) {
+        const bool mine = lane >= 1 && lane <= 30;
+        if ((reinterpret_cast<uintptr_t>(row) & 16u) == 0) {  // uniform: the lane's four samples are two whole sectors
+          if (mine) {
+            st256(row, v[0], v[1]);
+            st256(row + 2, v[2], v[3]);
+          }
+        } else {  // sectors straddle the lanes: take the left neighbour's last sample, leave the own last one to the right neighbour
+          const E4 lv = from_left4(v[3], left ? &left->out[r][3] : nullptr);
+          if (mine) {
+            if (lane == 1) st128(row, v[0]);
+            else st256(row - 1, lv, v[0]);
+            st256(row + 1, v[1], v[2]);
+            if (lane == 30) st128(row + 3, v[3]);
+          }
+        }
+      } else {
+        // closing row W (a == n) and closing column W hold corners and one mid class only; `ok` knows the columns
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (L.ok & (1 << j)) row[j] = v[j];
+      }
+    }
+  }
+};
+
+}  // namespace rn

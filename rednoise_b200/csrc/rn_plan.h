@@ -13,6 +13,7 @@
 #include "rn_math.cuh"
 #include "rn_tile.cuh"
 #include "rn_stream.cuh"
+#include "rn_march.cuh"
 
 namespace rn {
 
@@ -49,6 +50,27 @@ constexpr int kStreamMinSegRows = RN_STREAM_MIN_SEG_ROWS;  // shortest row segme
 #define RN_STREAM_SMALL_COLS 1024
 #endif
 constexpr int kStreamSmallCols = RN_STREAM_SMALL_COLS;    // levels with fewer cell columns than this use the small configuration
+// Warp-synchronous march (rn_march.cuh), the streamed levels' kernel since round 2: one warp per (strip of 60 cell columns, row
+// segment); the launch is one wave of about kMarchWarpsPerSM independent warps per SM.
+#ifndef RN_MARCH
+#define RN_MARCH 1              // 0: streamed levels run the round-1 block kernel (rn_stream.cuh)
+#endif
+#ifndef RN_MARCH_WARPS
+#define RN_MARCH_WARPS 12       // resident warps per SM the kernel is compiled for (register cap 65536 / 32 / this)
+#endif
+#ifndef RN_MARCH_WPB
+#define RN_MARCH_WPB 1          // independent warps per CTA
+#endif
+#ifndef RN_MARCH_FREE
+#define RN_MARCH_FREE 2         // warps per SM the output launch leaves to the next call's small coarse stages
+#endif
+#ifndef RN_MARCH_EDGE_COST
+#define RN_MARCH_EDGE_COST 2.0f // duration of a border-strip warp relative to an interior one with the same rows
+#endif
+#ifndef RN_MARCH_MIN_SEG_ROWS
+#define RN_MARCH_MIN_SEG_ROWS 8
+#endif
+constexpr int kMarchWarpsPerSM = RN_MARCH_WARPS, kMarchWPB = RN_MARCH_WPB;
 constexpr int kTile = 64;  // output tile edge of a stage (and the unit in which streamed stages are cut out of a window)
 // Small chain (RN_SMALL_CHAIN): for one deep field per call the coarse levels run as stages of RN_SMALL_CHAIN_L levels with 32x32
 // tiles and 128-thread CTAs (<= 64 registers, 30.9 KB) that fit into ONE CTA slot of the streaming output kernel, which leaves one
@@ -174,7 +196,7 @@ inline void input_range_1d(int d, int L, int t0, int t1, int T, int* lo, int* hi
 
 // One launch of the chain.
 struct StageLaunch {
-  int kind;               // 0 = tile kernel k_stage<L>, 1 = streaming kernel k_stream
+  int kind;               // 0 = tile kernel k_stage<L>, 1 = streaming block kernel k_stream, 2 = warp-synchronous k_march
   int stage;              // index of the stage this launch belongs to
   int last;               // belongs to the last stage (runs on the caller's stream)
   StageParams sp;         // kind 0
@@ -185,7 +207,10 @@ struct StageLaunch {
   unsigned gx, gy;        // kind 0: tiles in j, tiles in i; kind 1: strips, segments
 };
 
-inline size_t stage_grid_bytes(int d) { const size_t side = ((size_t)1 << d) + 1; return ((side * side * sizeof(E4) + 255) / 256) * 256; }
+// Intermediate grids have an EVEN row pitch (side + 1 elements) and 256-byte aligned bases, so that rn_march.cuh can read a
+// lane's two lattice columns with one 256-bit load.
+inline size_t stage_grid_pitch(int d) { return ((size_t)1 << d) + 2; }
+inline size_t stage_grid_bytes(int d) { const size_t side = ((size_t)1 << d) + 1; return ((side * stage_grid_pitch(d) * sizeof(E4) + 255) / 256) * 256; }
 
 inline size_t chain_scratch_bytes(int depth, int nfields)
 {
@@ -201,7 +226,7 @@ inline size_t chain_scratch_bytes(int depth, int nfields)
 // stages only compute the tiles the window's dependency cone touches.  Returns the launch count.
 inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int nj, E4* dst, size_t pitch, size_t field_stride,
                        void* scratch, int nfields, const Law& law, float persistence, uint32_t seed, const uint32_t* seeds, int volcano,
-                       float amplitude)
+                       float amplitude, int sm_count = 148, int march = RN_MARCH)
 {
   StagePlan plan[kMaxStages];
   const int ns = plan_stages(depth, plan, nfields);
@@ -245,7 +270,7 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
     } else {
       const size_t fbytes = stage_grid_bytes(sp.dout);
       sp.gout = reinterpret_cast<E4*>(static_cast<char*>(scratch) + off);
-      sp.gout_pitch = side;
+      sp.gout_pitch = stage_grid_pitch(sp.dout);
       sp.gout_field_stride = fbytes / sizeof(E4);
       off += fbytes * (size_t)nfields;
       sp.win_i0 = 0; sp.win_j0 = 0; sp.win_ni = (int)side; sp.win_nj = (int)side;
@@ -273,25 +298,47 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
       st.close_i = t_i1[k] == nt - 1;
       st.close_j = t_j1[k] == nt - 1;
       const int cols = st.b_hi - st.b_lo, rows = st.a_hi - st.a_lo;
-      sl.nt = cols < kStreamSmallCols ? kStreamThreadsSmall : kStreamThreads;
-      const int ctas_target = 148 * ((cols < kStreamSmallCols ? kStreamMinBlocksSmall : kStreamMinBlocks) - ((small_chain && last) ? RN_SMALL_CHAIN_FREE : 0));
-      const int strips = (cols + (sl.nt - 3) - 1) / (sl.nt - 3);
-      st.strip_cols = (cols + strips - 1) / strips;
-      st.nstrips = (cols + st.strip_cols - 1) / st.strip_cols;
-      // strips on a column border (same rule as StreamCtx::col_lean)
-      st.edge_first = st.b_lo < 1 || (st.nstrips == 1 && (st.b_hi > n - 1 || st.close_j));
-      st.edge_last = st.nstrips > 1 && (st.b_hi > n - 1 || st.close_j);
+      int ctas_target, min_rows;
+      float edge_cost;
+      if (march) {
+        // warp-synchronous march: strips of 60 cell columns (the closing output column counts as one)
+        sl.kind = 2;
+        sl.nt = 32 * kMarchWPB;
+        st.strip_cols = kMarchCols;
+        st.nstrips = (cols + st.close_j + kMarchCols - 1) / kMarchCols;
+        auto strip_is_edge = [&](int s) {  // same rule as MarchCtx::col_lean
+          const int B0 = st.b_lo + s * kMarchCols;
+          const int CW = kMarchCols < st.b_hi - B0 ? kMarchCols : st.b_hi - B0;
+          return B0 - 2 < 0 || B0 + 62 > n || (st.close_j && B0 + CW == st.b_hi);
+        };
+        st.edge_first = strip_is_edge(0);
+        st.edge_last = st.nstrips > 1 && strip_is_edge(st.nstrips - 1);
+        ctas_target = sm_count * (kMarchWarpsPerSM - ((small_chain && last) ? RN_MARCH_FREE : 0));
+        min_rows = RN_MARCH_MIN_SEG_ROWS;
+        edge_cost = RN_MARCH_EDGE_COST;
+      } else {
+        sl.nt = cols < kStreamSmallCols ? kStreamThreadsSmall : kStreamThreads;
+        ctas_target = sm_count * ((cols < kStreamSmallCols ? kStreamMinBlocksSmall : kStreamMinBlocks) - ((small_chain && last) ? RN_SMALL_CHAIN_FREE : 0));
+        const int strips = (cols + (sl.nt - 3) - 1) / (sl.nt - 3);
+        st.strip_cols = (cols + strips - 1) / strips;
+        st.nstrips = (cols + st.strip_cols - 1) / st.strip_cols;
+        // strips on a column border (same rule as StreamCtx::col_lean)
+        st.edge_first = st.b_lo < 1 || (st.nstrips == 1 && (st.b_hi > n - 1 || st.close_j));
+        st.edge_last = st.nstrips > 1 && (st.b_hi > n - 1 || st.close_j);
+        min_rows = kStreamMinSegRows;
+        edge_cost = kStreamEdgeCost;
+      }
       const int ne = st.edge_first + st.edge_last, ni = st.nstrips - ne;
-      // One wave: about ctas_target CTAs of equal duration.  A segment costs 2 warm-up steps, but small levels are
-      // latency-bound: filling every CTA slot wins (measured: 1025 -> 2049 level 40 us with 8-row segments, 52 us
-      // with 24-row segments).  A border-strip CTA takes kStreamEdgeCost times as long per row (measured), so it
+      // One wave: about ctas_target CTAs (warps) of equal duration.  A segment costs 2 warm-up steps, but small levels are
+      // latency-bound: filling every slot wins (measured: 1025 -> 2049 level 40 us with 8-row segments, 52 us
+      // with 24-row segments).  A border strip takes edge_cost times as long per row (measured), so it
       // gets that much fewer rows.
       const int per_field = ctas_target / (nfields > 0 ? nfields : 1);
-      // smallest interior segment length r (>= 8 rows) whose CTA count fits; border strips get r / kStreamEdgeCost rows
-      int r = kStreamMinSegRows < rows ? kStreamMinSegRows : rows, re = r;
+      // smallest interior segment length r (>= min_rows) whose unit count fits; border strips get r / edge_cost rows
+      int r = min_rows < rows ? min_rows : rows, re = r;
       for (;; r++) {
-        re = (int)((float)r / kStreamEdgeCost + 0.5f);
-        re = re < kStreamMinSegRows ? (kStreamMinSegRows < rows ? kStreamMinSegRows : rows) : re;
+        re = (int)((float)r / edge_cost + 0.5f);
+        re = re < min_rows ? (min_rows < rows ? min_rows : rows) : re;
         if (r >= rows || ni * ((rows + r - 1) / r) + ne * ((rows + re - 1) / re) <= per_field) break;
       }
       st.seg_rows = r;
@@ -303,7 +350,7 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
       st.jn = jump_of((uint64_t)st.lev.n);
       st.jn1 = jump_of((uint64_t)st.lev.n + 1);
       st.volcano = sp.volcano; st.volcano_gain = sp.volcano_gain;
-      sl.gx = (unsigned)stream_grid_size(st);
+      sl.gx = (unsigned)stream_grid_size(st);  // kind 2: warps
       sl.gy = 1;
       gin = sp.gout;
       gin_pitch = sp.gout_pitch;

@@ -170,6 +170,61 @@ int run_stream_t(const StageLaunch& sl, int nfields, const uint32_t* seeds, int 
   return bad;
 }
 
+// The warp-synchronous march (rn_march.cuh): the 32 lanes of a warp are replayed phase by phase in lockstep; a shuffle is a read
+// of the neighbouring lane's struct after every lane has finished the phase before it.  With `poison` all lane state starts as
+// NaN and the values the device shuffles in from outside the warp (lane 0's left, lane 31's right) are NaN too.
+template <bool EDGE, int PH>
+void march_step_host(const StreamParams& sp, const MarchCtx& cx, std::vector<MarchLane>& L, int u)
+{
+  using M = March<EDGE>;
+#define RN_LANES(call) for (int q = 0; q < 32; q++) { const int l = g_reverse ? 31 - q : q; call; }
+  RN_LANES(M::template p1<PH>(sp, cx, L[l], u, l))
+  RN_LANES(M::template x1<PH>(L[l], l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
+  RN_LANES(M::template p2<PH>(sp, cx, L[l], u, l))
+  RN_LANES(M::template x2<PH>(L[l], l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
+  RN_LANES(M::template p3<PH>(sp, cx, L[l], u))
+  RN_LANES(M::store(sp, cx, L[l], u, l, l > 0 ? &L[l - 1] : nullptr))
+#undef RN_LANES
+}
+
+int run_march(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
+{
+  std::vector<MarchLane> L(32);
+  for (int f = 0; f < nfields; f++)
+    for (unsigned id = 0; id < sl.gx; id++) {
+      StreamParams sp = sl.st;
+      if (seeds) { sp.seeds = nullptr; sp.seed = seeds[f]; }
+      MarchCtx cx = march_ctx(sp, (int)id, (unsigned)f);
+      if (force_edge) cx.col_lean = 0;
+      memset(L.data(), poison ? 0xff : 0, sizeof(MarchLane) * L.size());
+      for (int l = 0; l < 32; l++) March<true>::init(sp, cx, L[l], l, poison != 0);
+      // the kernel's loop (rn_fused.cu: k_march), including its bank bookkeeping
+      const int last = cx.a1e;
+      int u = cx.a0 - 1;
+      while (u <= last) {
+        if (march_step_is_lean(cx, u)) {
+          const int hi = cx.lean_hi;
+          for (;;) {
+            march_step_host<false, 0>(sp, cx, L, u);
+            if (u == hi) {
+              for (int l = 0; l < 32; l++) March<false>::swap_banks(L[l]);
+              break;
+            }
+            march_step_host<false, 1>(sp, cx, L, u + 1);
+            if (u + 1 == hi) break;
+            u += 2;
+          }
+          u = hi + 1;
+        } else {
+          march_step_host<true, 0>(sp, cx, L, u);
+          for (int l = 0; l < 32; l++) March<true>::swap_banks(L[l]);
+          u++;
+        }
+      }
+    }
+  return 0;
+}
+
 int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
 {
   if (sl.nt == kStreamThreadsSmall) return run_stream_t<kStreamThreadsSmall>(sl, nfields, seeds, poison, force_edge);
@@ -201,9 +256,22 @@ int replay_plan(int depth, int* din, int* L)
   return ns;
 }
 
+// kinds[k] of the launches that synthesize a whole depth-`depth` field (0 tile stage, 1 block streaming, 2 warp march).
+int replay_chain_kinds(int depth, int march, int* kinds)
+{
+  std::vector<StageLaunch> chain(kMaxLaunches);
+  Law law{};
+  const int side = (1 << depth) + 1;
+  std::vector<char> dummy(256);
+  const int ns = build_chain(chain.data(), depth, 0, 0, side, side, nullptr, (size_t)side, 0, dummy.data(), 1, law, 0.5f, 1u, nullptr, 1, 0.2f, 148, march);
+  for (int k = 0; k < ns; k++) kinds[k] = chain[k].kind;
+  return ns;
+}
+
 // Same contract as rn_terrain2d with a host destination (window may be NULL).  poison bit 0: NaN-fill
 // shared memory and scratch; bit 1: run every tile through the EDGE instantiation; bit 2: visit the
-// threads of every phase in descending order.  Returns 0 on
+// threads of every phase in descending order; bit 3: streamed levels through the round-1 block kernel (rn_stream.cuh) instead of
+// the warp march.  Returns 0 on
 // success, 100 if a tile wrote outside its shared memory.
 int replay_terrain2d(const rn_params* p, const rn_window* win, rn_element* dst, size_t pitch_elems, int poison)
 {
@@ -229,9 +297,13 @@ int replay_terrain2d(const rn_params* p, const rn_window* win, rn_element* dst, 
   std::vector<StageLaunch> chainv(kMaxLaunches);
   StageLaunch* chain = chainv.data();
   const int ns = build_chain(chain, p->depth, w.i0, w.j0, w.ni, w.nj, reinterpret_cast<E4*>(dst), pitch_elems, 0, scratch, 1, law,
-                             p->persistence, p->seed, nullptr, p->apply_volcano, p->amplitude);
+                             p->persistence, p->seed, nullptr, p->apply_volcano, p->amplitude, 148, (poison >> 3) & 1 ? 0 : RN_MARCH);
   int bad = 0;
   for (int k = 0; k < ns; k++) {
+    if (chain[k].kind == 2) {
+      bad |= run_march(chain[k], 1, nullptr, poison & 1, (poison >> 1) & 1);
+      continue;
+    }
     if (chain[k].kind == 1) {
       bad |= run_stream(chain[k], 1, nullptr, poison & 1, (poison >> 1) & 1);
       continue;

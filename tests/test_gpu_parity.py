@@ -336,3 +336,74 @@ def test_deep_batches_of_one_and_two(ctx, rnlib, oracle):
     for k, o in enumerate(outs):
         want = oracle.terrain2d(oracle_lib.params(seed=100 + k, depth=depth, apply_volcano=1))
         assert_bitwise(o.cpu().numpy(), want, f"pipelined call {k}")
+
+
+def test_async_batches_with_pinned_seeds_do_not_mix(ctx, rnlib, oracle):
+    """Three back-to-back asynchronous rn_terrain2d_batch calls, different seeds in PINNED host arrays, no synchronisation in
+    between: the seeds upload of a call is truly asynchronous then, and the call's first stages run on the context's side
+    streams -- they must wait for the upload and must not see the previous call's seeds (round-1 ADVICE, rn_abi.cu)."""
+    import torch
+    ctx.set_algorithm(0)
+    for depth, ntiles in ((10, 3), (8, 5)):
+        S = (1 << depth) + 1
+        p = rnlib.default_params(depth=depth, apply_volcano=1)
+        calls = 3
+        seeds = [torch.empty((ntiles,), dtype=torch.int32).pin_memory() for _ in range(calls)]
+        for k in range(calls):
+            for t in range(ntiles):
+                seeds[k][t] = 1000 * (k + 1) + 17 * t
+        outs = [torch.empty((ntiles, S, S, 4), device="cuda", dtype=torch.float32) for _ in range(calls)]
+        s = torch.cuda.Stream()
+        # keep the stream busy first so that the uploads really queue behind device work
+        busy = torch.empty((1 << 26,), device="cuda", dtype=torch.float32)
+        with torch.cuda.stream(s):
+            for _ in range(4):
+                busy.add_(1.0)
+        for k in range(calls):
+            ctx.terrain2d_batch_ptr(p, ntiles, outs[k].data_ptr(), dst_is_device=True, stream=s.cuda_stream, seeds_ptr=seeds[k].data_ptr())
+        torch.cuda.synchronize()
+        for k in range(calls):
+            got = outs[k].cpu().numpy()
+            for t in range(ntiles):
+                want = oracle.terrain2d(oracle_lib.params(seed=int(seeds[k][t]), depth=depth, apply_volcano=1))
+                assert_bitwise(got[t], want, f"depth {depth} call {k} tile {t}")
+
+
+def test_block_streaming_kernel_still_agrees(ctx, rnlib, oracle):
+    """Algorithm 3 (the round-1 block streaming kernel for the last two levels) is kept as an independent implementation of what
+    the warp march (algorithm 2, the default) computes: same bits at depth 10-13, and on a window."""
+    import torch
+    for depth, seed in ((10, 5), (11, 77), (12, 12345), (13, 9)):
+        S = (1 << depth) + 1
+        p = rnlib.default_params(seed=seed, depth=depth, apply_volcano=1)
+        a = torch.empty((S, S, 4), device="cuda", dtype=torch.float32)
+        b = torch.empty((S, S, 4), device="cuda", dtype=torch.float32)
+        ctx.set_algorithm(3)
+        ctx.terrain2d_ptr(p, a.data_ptr(), dst_is_device=True)
+        ctx.set_algorithm(2)
+        ctx.terrain2d_ptr(p, b.data_ptr(), dst_is_device=True)
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), depth
+        del a, b
+    ctx.set_algorithm(3)
+    p = rnlib.default_params(seed=4711, depth=10, apply_volcano=1)
+    full = oracle.terrain2d(oracle_lib.params(seed=4711, depth=10, apply_volcano=1))
+    got = ctx.terrain2d_host(p, window=rnlib.Window(100, 37, 300, 500))
+    assert_bitwise(got, full[100:400, 37:537], "algorithm 3 window")
+    ctx.set_algorithm(0)
+
+
+def test_march_even_pitch_and_odd_alignment(ctx, rnlib, oracle):
+    """The march kernel stores whole 32-byte sectors; which rows are sector-aligned depends on the destination's base address
+    and pitch parity.  Full fields into destinations with even / odd pitch and a base shifted by one element."""
+    import torch
+    ctx.set_algorithm(0)
+    depth, seed = 11, 321
+    S = (1 << depth) + 1
+    p = rnlib.default_params(seed=seed, depth=depth, apply_volcano=1)
+    want = oracle.terrain2d(oracle_lib.params(seed=seed, depth=depth, apply_volcano=1))
+    for pitch, shift in ((S, 0), (S + 1, 0), (S, 1), (S + 1, 1), (S + 7, 3)):
+        buf = torch.full((S * pitch + 8, 4), -3.0, device="cuda", dtype=torch.float32)
+        ctx.terrain2d_ptr(p, buf.data_ptr() + 16 * shift, pitch_elems=pitch, dst_is_device=True)
+        h = buf.cpu().numpy()[shift:shift + S * pitch].reshape(S, pitch, 4)
+        assert_bitwise(h[:, :S], want, f"pitch {pitch} shift {shift}")
+        assert (h[:, S:] == -3.0).all()

@@ -25,7 +25,7 @@ class Win(C.Structure):
 
 @pytest.fixture(scope="module")
 def replay():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rn_tile.cuh", "rn_stream.cuh", "rn_plan.h", "rn_math.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rn_tile.cuh", "rn_stream.cuh", "rn_march.cuh", "rn_plan.h", "rn_math.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", SO, SRC], check=True)
     L = C.CDLL(SO)
@@ -128,3 +128,49 @@ def test_stage_plans(replay):
         assert all(1 <= l[k] <= 4 for k in range(n)) and all(d[k + 1] == d[k] + l[k] for k in range(n - 1))
     for L in (1, 2, 3, 4):
         assert replay.replay_smem_bytes(L) <= 227 * 1024
+
+
+def test_replay_march_depth12_windows_of_every_strip_layout(replay, oracle):
+    """The warp march (rn_march.cuh) cuts a window into strips of 60 cell columns: one strip, strips that touch no border, only
+    the left / right / top / bottom border, single rows and columns, odd pitches (sector-aligned and shifted rows) -- all seam-exact."""
+    depth, seed = 12, 2718
+    S = (1 << depth) + 1
+    p = oracle_lib.params(seed=seed, depth=depth, apply_volcano=1)
+    full = oracle.terrain2d(p)
+    wins = [(1000, 1000, 300, 200), (1000, 1000, 64, 1500), (0, 1500, 500, 700), (S - 300, 2000, 300, 900), (1500, 0, 700, 260),
+            (1500, S - 260, 700, 260), (0, 0, 257, 257), (S - 129, S - 129, 129, 129), (2047, 2047, 3, 3), (2048, 0, 1, S), (0, 2048, S, 1),
+            (100, 3, 2200, 4000)]
+    for k, (i0, j0, ni, nj) in enumerate(wins):
+        got = run(replay, p, Win(i0, j0, ni, nj), pitch=nj + (k % 3), poison=1 if k % 2 else 5)
+        assert np.array_equal(got[:, :nj].view(np.uint32), full[i0:i0 + ni, j0:j0 + nj].view(np.uint32)), (i0, j0, ni, nj)
+        assert (got[:, nj:] == -7.0).all()
+
+
+@pytest.mark.parametrize("depth,seed", [(10, 31), (11, 2024)])
+def test_replay_block_streaming_kernel_agrees(replay, oracle, depth, seed):
+    """poison bit 3: the streamed levels through the round-1 block kernel (rn_stream.cuh, algorithm 3) -- kept as a cross-check."""
+    p = oracle_lib.params(seed=seed, depth=depth, apply_volcano=1)
+    want = oracle.terrain2d(p)
+    assert np.array_equal(run(replay, p, poison=9).view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(run(replay, p, poison=1).view(np.uint32), want.view(np.uint32))
+
+
+def test_replay_march_is_the_default_for_deep_fields(replay):
+    k = (C.c_int * 16)()
+    for depth in (10, 12, 14):
+        n = replay.replay_chain_kinds(depth, 1, k)
+        assert list(k[:n])[-2:] == [2, 2]
+        n = replay.replay_chain_kinds(depth, 0, k)
+        assert list(k[:n])[-2:] == [1, 1]
+    n = replay.replay_chain_kinds(9, 1, k)
+    assert set(k[:n]) == {0}
+
+
+def test_replay_march_deep_slab(replay, oracle):
+    """A thin row slab and a column window of a depth-13 field (8193^2): strips far from every border, nseg > 1."""
+    depth, seed = 13, 5
+    p = oracle_lib.params(seed=seed, depth=depth, apply_volcano=1)
+    full = oracle.terrain2d(p)
+    for (i0, j0, ni, nj) in [(4000, 0, 200, 8193), (0, 4090, 8193, 70)]:
+        got = run(replay, p, Win(i0, j0, ni, nj))
+        assert np.array_equal(got.view(np.uint32), full[i0:i0 + ni, j0:j0 + nj].view(np.uint32)), (i0, j0, ni, nj)

@@ -237,6 +237,52 @@ typedef struct rn_volume_params {
 } rn_volume_params;
 int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, float* vol, void* stream);
 
+/* ---- memory helpers ---------------------------------------------------------------------------
+ * So that a C/C++ caller (the adapter inside Terrain::Terrain) needs no CUDA runtime of its own:
+ * device memory on a context's device, page-locked host memory (a pinned destination lets rn_terrain2d's device-to-host
+ * copies run at full PCIe rate and asynchronously; `new TerrainElement[]`, Terrain.cpp:45-49, is pageable), and a blocking
+ * device-to-host copy. */
+int rn_device_count(void); /* CUDA devices visible (0 without a driver) */
+int rn_device_alloc(rn_context* ctx, size_t bytes, void** out);
+int rn_device_free(rn_context* ctx, void* ptr);
+int rn_host_alloc(size_t bytes, void** out);
+int rn_host_free(void* ptr);
+int rn_copy_to_host(rn_context* ctx, void* dst_host, const void* src_device, size_t bytes);
+
+/* ---- several GPUs from one host thread ----------------------------------------------------------
+ * The path shards with no exchange step: every sample is a pure function of (seed, params, lattice
+ * index), and what a slab needs beyond its own rows (its dependency cone through the coarser levels) is RECOMPUTED on its
+ * device, never communicated.  An rn_multi owns one rn_context (own streams, own scratch) per listed device; the calls below
+ * enqueue the work of every device from the calling thread and then wait for all of them.  The reference's one caller
+ * (Core::init -> new Terrain, Core.cpp:58-65) is a single host thread, which is why this is not one-process-per-GPU only.
+ *   rn_slab_rows / rn_slab_window   n equal row slabs of a (side x side) field: slab k = rows [k*rows, min(side, (k+1)*rows));
+ *                                   trailing slabs may be shorter or empty (ni == 0)
+ *   rn_terrain2d_sharded            ONE field: slab k is synthesized on device k.
+ *       slab_dst   n device pointers (slab_dst[k] on device k, row pitch slab_pitch_elems, 0 = side), or NULL
+ *       host_dst   the whole field assembled in HOST memory (row pitch host_pitch_elems, 0 = side): every device sends its
+ *                  slab straight into its rows, all devices concurrently; or NULL
+ *   rn_terrain2d_batch_sharded      `ntiles` independent fields, tile t on device t % n (round-robin): tile t is written at
+ *                                   tile_dst[t % n] + (t / n) * tile_stride_elems (device memory of that device)
+ *   rn_gather                       the optional final assembly (the only collective of the path): every device ends up with
+ *                                   all n slabs, slab j at full_dst[k] + j * rows * side.  slab_src[k] holds rn_slab_rows x side
+ *                                   elements (dense); full_dst[k] n * rn_slab_rows x side.  use_nccl != 0: one ncclAllGather per
+ *                                   device inside a group (NCCL over NVLink / NVSwitch; the library binds libnccl.so.2 at run
+ *                                   time, RN_ERR_UNSUPPORTED if it is absent or a device is listed twice); 0: peer copies
+ *                                   (cudaMemcpyPeerAsync), which also work without NCCL. */
+#define RN_MAX_DEVICES 16
+typedef struct rn_multi rn_multi;
+int rn_create_multi(const int* devices, int n, rn_multi** out_multi);
+int rn_destroy_multi(rn_multi* m);
+int rn_multi_size(const rn_multi* m);
+rn_context* rn_multi_context(rn_multi* m, int k);
+int rn_slab_rows(int side, int nparts);
+int rn_slab_window(int side, int part, int nparts, rn_window* out);
+int rn_terrain2d_sharded(rn_multi* m, const rn_params* p, rn_element* const* slab_dst, size_t slab_pitch_elems, rn_element* host_dst,
+                         size_t host_pitch_elems);
+int rn_terrain2d_batch_sharded(rn_multi* m, const rn_params* p, const uint32_t* seeds, int ntiles, rn_element* const* tile_dst,
+                               size_t tile_stride_elems);
+int rn_gather(rn_multi* m, const rn_params* p, const rn_element* const* slab_src, rn_element* const* full_dst, int use_nccl);
+
 /* Device self-test of the arithmetic shortcuts: the normal-range sqrt / reciprocal sequences
  * used by the fused kernels are compared with the IEEE-rounded intrinsics over every binary32
  * value in 2^-100 .. 2^100.  mismatches[0..2] = sqrt, reciprocal, 1/sqrt (all must be 0). */

@@ -17,13 +17,16 @@ LIB_PATH = os.environ.get("RN_LIB") or os.path.join(HERE, "librednoise_b200.so")
 RN_OK, RN_ERR_BAD_PARAM, RN_ERR_UNSUPPORTED, RN_ERR_NO_DEVICE, RN_ERR_CUDA, RN_ERR_OOM = range(6)
 RN_MIN_DEPTH, RN_MAX_DEPTH = 3, 14
 
-# every symbol include/rednoise.h declares (tests/test_abi_symbols.py checks the two agree)
+# every symbol include/rednoise.h declares (tests/test_abi_host.py::test_header_symbols_exported checks the two agree)
 SYMBOLS = [
     "rn_version", "rn_last_error_string", "rn_status_string", "rn_params_default", "rn_terrain2d_side",
     "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
     "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_set_pipelining", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device", "rn_selftest_math",
     "rn_terrain2d_cell_count", "rn_terrain2d_cell_level_offset", "rn_terrain2d_cells", "rn_volume3d",
     "rn_rock_draw_count", "rn_rock", "rn_cloud_draw_count", "rn_cloud",
+    "rn_device_count", "rn_device_alloc", "rn_device_free", "rn_host_alloc", "rn_host_free", "rn_copy_to_host",
+    "rn_create_multi", "rn_destroy_multi", "rn_multi_size", "rn_multi_context", "rn_slab_rows", "rn_slab_window",
+    "rn_terrain2d_sharded", "rn_terrain2d_batch_sharded", "rn_gather",
 ]
 
 
@@ -117,6 +120,21 @@ def lib() -> C.CDLL:
     L.rn_cloud_draw_count.argtypes = [i32]
     L.rn_cloud.restype = i32
     L.rn_cloud.argtypes = [vp, C.POINTER(RockParams), vp, vp, i32, vp, C.POINTER(C.c_uint32)]
+    L.rn_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.rn_device_free.argtypes = [vp, vp]
+    L.rn_host_alloc.argtypes = [sz, C.POINTER(vp)]
+    L.rn_host_free.argtypes = [vp]
+    L.rn_copy_to_host.argtypes = [vp, vp, vp, sz]
+    L.rn_create_multi.argtypes = [C.POINTER(i32), i32, C.POINTER(vp)]
+    L.rn_destroy_multi.argtypes = [vp]
+    L.rn_multi_size.argtypes = [vp]
+    L.rn_multi_context.restype = vp
+    L.rn_multi_context.argtypes = [vp, i32]
+    L.rn_slab_rows.argtypes = [i32, i32]
+    L.rn_slab_window.argtypes = [i32, i32, i32, C.POINTER(Window)]
+    L.rn_terrain2d_sharded.argtypes = [vp, C.POINTER(Params), C.POINTER(vp), sz, vp, sz]
+    L.rn_terrain2d_batch_sharded.argtypes = [vp, C.POINTER(Params), C.POINTER(u32), i32, C.POINTER(vp), sz]
+    L.rn_gather.argtypes = [vp, C.POINTER(Params), C.POINTER(vp), C.POINTER(vp), i32]
     _lib = L
     return L
 
@@ -275,3 +293,39 @@ class Context:
         out = np.empty(n, np.uint16)
         _check(lib().rn_lcg_draws_device(self._h, seed & 0xFFFFFFFF, first, n, C.c_void_p(out.ctypes.data), 0, None))
         return out
+
+
+class Multi:
+    """rn_multi: several devices driven from one host thread (include/rednoise.h, "several GPUs from one host thread")."""
+
+    def __init__(self, devices):
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        _check(lib().rn_create_multi(arr, len(devices), C.byref(self._h)))
+        self.n = len(devices)
+
+    def close(self):
+        if self._h:
+            lib().rn_destroy_multi(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def terrain2d_sharded(self, p: Params, slab_ptrs=None, slab_pitch: int = 0, host_ptr: int = 0, host_pitch: int = 0):
+        arr = (C.c_void_p * self.n)(*slab_ptrs) if slab_ptrs is not None else None
+        _check(lib().rn_terrain2d_sharded(self._h, C.byref(p), arr, slab_pitch, C.c_void_p(host_ptr) if host_ptr else None, host_pitch))
+
+    def gather(self, p: Params, slab_ptrs, full_ptrs, use_nccl: bool = True):
+        a = (C.c_void_p * self.n)(*slab_ptrs)
+        b = (C.c_void_p * self.n)(*full_ptrs)
+        _check(lib().rn_gather(self._h, C.byref(p), a, b, 1 if use_nccl else 0))
+
+
+def slab_window(side: int, part: int, nparts: int) -> Window:
+    w = Window()
+    _check(lib().rn_slab_window(side, part, nparts, C.byref(w)))
+    return w

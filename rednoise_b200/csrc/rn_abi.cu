@@ -10,6 +10,7 @@
 #include <string.h>
 #include <string>
 #include <new>
+#include <vector>
 
 using namespace rn;
 
@@ -178,6 +179,37 @@ int synth_window_fused(rn_context* ctx, const rn_params* p, const rn_window& w, 
                          ctx->sm_count, ctx->algo != 3));
   RN_CUDA(cudaEventRecord(ctx->slot_free[sl], stream));
   ctx->slot_used[sl] = true;
+  return RN_OK;
+}
+
+// Large host destination: the window is produced in row chunks through two staging halves, so that synthesis of chunk k+1
+// overlaps the PCIe transfer of chunk k (the transfer is the bottleneck: 16 B/sample at ~55 GB/s).  Everything is enqueued
+// (synthesis on `stream`, copies on ctx->copy_stream); the caller waits for ctx->copy_stream.
+int enqueue_window_to_host(rn_context* ctx, const rn_params* p, const rn_window& w, rn_element* dst, size_t pitch_elems, cudaStream_t stream)
+{
+  int rows = (int)(((size_t)32 << 20) / ((size_t)w.nj * sizeof(Elem)));  // ~32 MB per chunk
+  rows = rows < 64 ? 64 : (rows / 64) * 64;
+  const size_t half = (size_t)rows * (size_t)w.nj;
+  int st = ensure(&ctx->field, &ctx->field_bytes, sizeof(Elem) * 2 * half);
+  if (st != RN_OK) return st;
+  int k = 0;
+  for (int r0 = 0; r0 < w.ni; r0 += rows, k++) {
+    const int nr = (w.ni - r0 < rows) ? w.ni - r0 : rows;
+    const int h = k & 1;
+    Elem* stage = reinterpret_cast<Elem*>(ctx->field) + (size_t)h * half;
+    if (k >= 2) RN_CUDA(cudaStreamWaitEvent(stream, ctx->chunk_copied[h], 0));  // the staging half is free again
+    const rn_window cw{w.i0 + r0, w.j0, nr, w.nj};
+    st = synth_window_fused(ctx, p, cw, stage, (size_t)w.nj, 0, nullptr, 1, stream);
+    if (st != RN_OK) return st;
+    RN_CUDA(cudaEventRecord(ctx->chunk_ready[h], stream));
+    RN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ready[h], 0));
+    if (pitch_elems == (size_t)w.nj)  // dense rows: one linear copy
+      RN_CUDA(cudaMemcpyAsync(dst + (size_t)r0 * pitch_elems, stage, (size_t)nr * (size_t)w.nj * sizeof(Elem), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    else
+      RN_CUDA(cudaMemcpy2DAsync(dst + (size_t)r0 * pitch_elems, pitch_elems * sizeof(Elem), stage, (size_t)w.nj * sizeof(Elem),
+                                (size_t)w.nj * sizeof(Elem), (size_t)nr, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    RN_CUDA(cudaEventRecord(ctx->chunk_copied[h], ctx->copy_stream));
+  }
   return RN_OK;
 }
 
@@ -459,29 +491,9 @@ int rn_terrain2d(rn_context* ctx, const rn_params* p, const rn_window* win, rn_e
       st = synth_window_fused(ctx, p, w, g, gpitch, 0, nullptr, 1, stream);
       if (st != RN_OK) return st;
     } else if (!dst_is_device && ctx->copy_stream && (size_t)w.ni * (size_t)w.nj >= ((size_t)1 << 22)) {
-      // Large host destination: row chunks through two staging halves, so that synthesis of chunk k+1 overlaps the
-      // PCIe transfer of chunk k (the transfer is the bottleneck: 16 B/sample at ~55 GB/s).
       chunked = true;
-      int rows = (int)(((size_t)32 << 20) / ((size_t)w.nj * sizeof(Elem)));  // ~32 MB per chunk
-      rows = rows < 64 ? 64 : (rows / 64) * 64;
-      const size_t half = (size_t)rows * (size_t)w.nj;
-      st = ensure(&ctx->field, &ctx->field_bytes, sizeof(Elem) * 2 * half);
+      st = enqueue_window_to_host(ctx, p, w, dst, pitch_elems, stream);
       if (st != RN_OK) return st;
-      int k = 0;
-      for (int r0 = 0; r0 < w.ni; r0 += rows, k++) {
-        const int nr = (w.ni - r0 < rows) ? w.ni - r0 : rows;
-        const int h = k & 1;
-        Elem* stage = reinterpret_cast<Elem*>(ctx->field) + (size_t)h * half;
-        if (k >= 2) RN_CUDA(cudaStreamWaitEvent(stream, ctx->chunk_copied[h], 0));  // the staging half is free again
-        const rn_window cw{w.i0 + r0, w.j0, nr, w.nj};
-        st = synth_window_fused(ctx, p, cw, stage, (size_t)w.nj, 0, nullptr, 1, stream);
-        if (st != RN_OK) return st;
-        RN_CUDA(cudaEventRecord(ctx->chunk_ready[h], stream));
-        RN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ready[h], 0));
-        RN_CUDA(cudaMemcpy2DAsync(dst + (size_t)r0 * pitch_elems, pitch_elems * sizeof(Elem), stage, (size_t)w.nj * sizeof(Elem),
-                                  (size_t)w.nj * sizeof(Elem), (size_t)nr, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        RN_CUDA(cudaEventRecord(ctx->chunk_copied[h], ctx->copy_stream));
-      }
       RN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     } else {
       st = ensure(&ctx->field, &ctx->field_bytes, sizeof(Elem) * (size_t)w.ni * (size_t)w.nj);
@@ -769,6 +781,298 @@ int rn_lcg_draws_device(rn_context* ctx, uint32_t seed, uint64_t first, uint64_t
   RN_CUDA(cudaMemcpyAsync(dst, ctx->small, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, stream));
   RN_CUDA(cudaStreamSynchronize(stream));
   return RN_OK;
+}
+
+// ---------------------------------------------------------------- memory helpers ----
+int rn_device_count(void)
+{
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+
+int rn_device_alloc(rn_context* ctx, size_t bytes, void** out)
+{
+  if (!ctx || !out) return fail(RN_ERR_BAD_PARAM, "ctx/out is NULL");
+  *out = nullptr;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  RN_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  return RN_OK;
+}
+
+int rn_device_free(rn_context* ctx, void* ptr)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  RN_CUDA(cudaFree(ptr));
+  return RN_OK;
+}
+
+int rn_host_alloc(size_t bytes, void** out)
+{
+  if (!out) return fail(RN_ERR_BAD_PARAM, "out is NULL");
+  *out = nullptr;
+  RN_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return RN_OK;
+}
+
+int rn_host_free(void* ptr)
+{
+  RN_CUDA(cudaFreeHost(ptr));
+  return RN_OK;
+}
+
+int rn_copy_to_host(rn_context* ctx, void* dst_host, const void* src_device, size_t bytes)
+{
+  if (!ctx || (!dst_host && bytes) || (!src_device && bytes)) return fail(RN_ERR_BAD_PARAM, "ctx/dst/src is NULL");
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  RN_CUDA(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  RN_CUDA(cudaStreamSynchronize(ctx->stream));
+  return RN_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- several GPUs, one host thread ----
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: libnccl.so.2 is bound at run time (a host process such as PyTorch brings its own copy)
+
+struct rn_multi {
+  int n = 0;
+  int devices[RN_MAX_DEVICES] = {};
+  rn_context* ctx[RN_MAX_DEVICES] = {};
+  bool distinct = true;             // no device listed twice (NCCL needs that)
+  // NCCL, bound lazily
+  void* nccl_lib = nullptr;
+  bool nccl_tried = false;
+  ncclComm_t comms[RN_MAX_DEVICES] = {};
+  bool comms_ready = false;
+  ncclResult_t (*pCommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*pCommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*pGroupStart)() = nullptr;
+  ncclResult_t (*pGroupEnd)() = nullptr;
+  ncclResult_t (*pAllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*pGetErrorString)(ncclResult_t) = nullptr;
+};
+
+namespace {
+
+int bind_nccl(rn_multi* m)
+{
+  if (m->nccl_tried) return m->nccl_lib ? RN_OK : fail(RN_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  m->nccl_tried = true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy the process already carries, if any
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!h) return fail(RN_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  *(void**)&m->pCommInitAll = dlsym(h, "ncclCommInitAll");
+  *(void**)&m->pCommDestroy = dlsym(h, "ncclCommDestroy");
+  *(void**)&m->pGroupStart = dlsym(h, "ncclGroupStart");
+  *(void**)&m->pGroupEnd = dlsym(h, "ncclGroupEnd");
+  *(void**)&m->pAllGather = dlsym(h, "ncclAllGather");
+  *(void**)&m->pGetErrorString = dlsym(h, "ncclGetErrorString");
+  if (!m->pCommInitAll || !m->pCommDestroy || !m->pGroupStart || !m->pGroupEnd || !m->pAllGather) {
+    dlclose(h);
+    return fail(RN_ERR_UNSUPPORTED, "libnccl.so.2 lacks a required symbol");
+  }
+  m->nccl_lib = h;
+  return RN_OK;
+}
+
+int fail_nccl(rn_multi* m, ncclResult_t r, const char* where)
+{
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s: %s", where, m->pGetErrorString ? m->pGetErrorString(r) : "NCCL error");
+  g_last_error = buf;
+  return RN_ERR_CUDA;
+}
+
+int sync_all(rn_multi* m, bool copy_streams)
+{
+  int status = RN_OK;
+  for (int k = 0; k < m->n; k++) {
+    DeviceGuard guard(m->ctx[k]->device);
+    cudaError_t e = cudaStreamSynchronize(m->ctx[k]->stream);
+    if (e == cudaSuccess && copy_streams) e = cudaStreamSynchronize(m->ctx[k]->copy_stream);
+    if (e != cudaSuccess && status == RN_OK) status = fail_cuda(e, "cudaStreamSynchronize (multi)");
+  }
+  return status;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rn_create_multi(const int* devices, int n, rn_multi** out_multi)
+{
+  if (!out_multi) return fail(RN_ERR_BAD_PARAM, "out_multi is NULL");
+  *out_multi = nullptr;
+  if (!devices || n < 1 || n > RN_MAX_DEVICES) return fail(RN_ERR_BAD_PARAM, "devices is NULL or n outside [1, RN_MAX_DEVICES]");
+  rn_multi* m = new (std::nothrow) rn_multi();
+  if (!m) return fail(RN_ERR_OOM, "host allocation failed");
+  m->n = n;
+  for (int k = 0; k < n; k++) {
+    m->devices[k] = devices[k];
+    for (int q = 0; q < k; q++)
+      if (devices[q] == devices[k]) m->distinct = false;
+    const int st = rn_create(devices[k], &m->ctx[k]);
+    if (st != RN_OK) {
+      const std::string keep = g_last_error;
+      rn_destroy_multi(m);
+      g_last_error = keep;
+      return st;
+    }
+    m->devices[k] = m->ctx[k]->device;
+  }
+  // peer access for the copy form of rn_gather (best effort: NVLink-connected B200s allow it)
+  for (int k = 0; k < n; k++)
+    for (int q = 0; q < n; q++) {
+      if (m->devices[k] == m->devices[q]) continue;
+      DeviceGuard guard(m->devices[k]);
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, m->devices[k], m->devices[q]) == cudaSuccess && can) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(m->devices[q], 0);
+        if (e != cudaSuccess) cudaGetLastError();  // already enabled is fine
+      }
+    }
+  *out_multi = m;
+  return RN_OK;
+}
+
+int rn_destroy_multi(rn_multi* m)
+{
+  if (!m) return RN_OK;
+  if (m->comms_ready)
+    for (int k = 0; k < m->n; k++)
+      if (m->comms[k]) m->pCommDestroy(m->comms[k]);
+  for (int k = 0; k < m->n; k++) rn_destroy(m->ctx[k]);
+  // (the NCCL library stays loaded: other users of the process may hold it)
+  delete m;
+  return RN_OK;
+}
+
+int rn_multi_size(const rn_multi* m) { return m ? m->n : 0; }
+rn_context* rn_multi_context(rn_multi* m, int k) { return (m && k >= 0 && k < m->n) ? m->ctx[k] : nullptr; }
+
+int rn_slab_rows(int side, int nparts)
+{
+  if (side <= 0 || nparts <= 0) return 0;
+  return (side + nparts - 1) / nparts;
+}
+
+int rn_slab_window(int side, int part, int nparts, rn_window* out)
+{
+  if (!out || side <= 0 || nparts <= 0 || part < 0 || part >= nparts) return fail(RN_ERR_BAD_PARAM, "bad slab arguments");
+  const int rows = rn_slab_rows(side, nparts);
+  const int i0 = part * rows < side ? part * rows : side;
+  const int ni = rows < side - i0 ? rows : side - i0;
+  out->i0 = i0; out->j0 = 0; out->ni = ni; out->nj = side;
+  return RN_OK;
+}
+
+int rn_terrain2d_sharded(rn_multi* m, const rn_params* p, rn_element* const* slab_dst, size_t slab_pitch_elems, rn_element* host_dst,
+                         size_t host_pitch_elems)
+{
+  if (!m) return fail(RN_ERR_BAD_PARAM, "multi is NULL");
+  int st = check_params(p);
+  if (st != RN_OK) return st;
+  if (!slab_dst && !host_dst) return fail(RN_ERR_BAD_PARAM, "slab_dst and host_dst are both NULL");
+  const int side = (1 << p->depth) + 1;
+  if (slab_pitch_elems == 0) slab_pitch_elems = (size_t)side;
+  if (host_pitch_elems == 0) host_pitch_elems = (size_t)side;
+  if (slab_pitch_elems < (size_t)side || host_pitch_elems < (size_t)side) return fail(RN_ERR_BAD_PARAM, "pitch < side");
+  // enqueue on every device, then wait: the devices work concurrently although one thread drives them
+  for (int k = 0; k < m->n; k++) {
+    rn_window w;
+    rn_slab_window(side, k, m->n, &w);
+    if (w.ni == 0) continue;
+    rn_context* ctx = m->ctx[k];
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+    if (slab_dst) {
+      if (!slab_dst[k] || reinterpret_cast<uintptr_t>(slab_dst[k]) % 16 != 0) return fail(RN_ERR_BAD_PARAM, "slab_dst[k] is NULL or not 16-byte aligned");
+      st = synth_window_fused(ctx, p, w, reinterpret_cast<Elem*>(slab_dst[k]), slab_pitch_elems, 0, nullptr, 1, ctx->stream);
+      if (st != RN_OK) return st;
+      if (host_dst) {  // the slab is already in device memory: ship it from there
+        RN_CUDA(cudaEventRecord(ctx->chunk_ready[0], ctx->stream));
+        RN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ready[0], 0));
+        RN_CUDA(cudaMemcpy2DAsync(host_dst + (size_t)w.i0 * host_pitch_elems, host_pitch_elems * sizeof(Elem), slab_dst[k], slab_pitch_elems * sizeof(Elem),
+                                  (size_t)side * sizeof(Elem), (size_t)w.ni, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      }
+    } else {
+      st = enqueue_window_to_host(ctx, p, w, host_dst + (size_t)w.i0 * host_pitch_elems, host_pitch_elems, ctx->stream);
+      if (st != RN_OK) return st;
+    }
+  }
+  return sync_all(m, host_dst != nullptr);
+}
+
+int rn_terrain2d_batch_sharded(rn_multi* m, const rn_params* p, const uint32_t* seeds, int ntiles, rn_element* const* tile_dst,
+                               size_t tile_stride_elems)
+{
+  if (!m) return fail(RN_ERR_BAD_PARAM, "multi is NULL");
+  int st = check_params(p);
+  if (st != RN_OK) return st;
+  if (!seeds || !tile_dst || ntiles < 0) return fail(RN_ERR_BAD_PARAM, "seeds/tile_dst is NULL or ntiles < 0");
+  std::vector<uint32_t> mine;
+  for (int k = 0; k < m->n; k++) {
+    mine.clear();
+    for (int t = k; t < ntiles; t += m->n) mine.push_back(seeds[t]);
+    if (mine.empty()) continue;
+    if (!tile_dst[k]) return fail(RN_ERR_BAD_PARAM, "tile_dst[k] is NULL");
+    // (the seeds are staged by the runtime before the call returns: `mine` may be reused)
+    st = rn_terrain2d_batch(m->ctx[k], p, mine.data(), (int)mine.size(), tile_dst[k], tile_stride_elems, 1, m->ctx[k]->stream);
+    if (st != RN_OK) return st;
+  }
+  return sync_all(m, false);
+}
+
+int rn_gather(rn_multi* m, const rn_params* p, const rn_element* const* slab_src, rn_element* const* full_dst, int use_nccl)
+{
+  if (!m) return fail(RN_ERR_BAD_PARAM, "multi is NULL");
+  int st = check_params(p);
+  if (st != RN_OK) return st;
+  if (!slab_src || !full_dst) return fail(RN_ERR_BAD_PARAM, "slab_src/full_dst is NULL");
+  for (int k = 0; k < m->n; k++)
+    if (!slab_src[k] || !full_dst[k]) return fail(RN_ERR_BAD_PARAM, "slab_src[k]/full_dst[k] is NULL");
+  const int side = (1 << p->depth) + 1;
+  const size_t slab_elems = (size_t)rn_slab_rows(side, m->n) * (size_t)side;
+  if (use_nccl) {
+    if (!m->distinct) return fail(RN_ERR_UNSUPPORTED, "NCCL needs distinct devices (a device is listed twice): use the peer-copy form");
+    st = bind_nccl(m);
+    if (st != RN_OK) return st;
+    if (!m->comms_ready) {
+      const ncclResult_t r = m->pCommInitAll(m->comms, m->n, m->devices);
+      if (r != ncclSuccess) return fail_nccl(m, r, "ncclCommInitAll");
+      m->comms_ready = true;
+    }
+    ncclResult_t r = m->pGroupStart();
+    if (r != ncclSuccess) return fail_nccl(m, r, "ncclGroupStart");
+    for (int k = 0; k < m->n; k++) {
+      r = m->pAllGather(slab_src[k], full_dst[k], slab_elems * 4, ncclFloat, m->comms[k], m->ctx[k]->stream);
+      if (r != ncclSuccess) {
+        m->pGroupEnd();
+        return fail_nccl(m, r, "ncclAllGather");
+      }
+    }
+    r = m->pGroupEnd();
+    if (r != ncclSuccess) return fail_nccl(m, r, "ncclGroupEnd");
+  } else {
+    for (int k = 0; k < m->n; k++) {
+      DeviceGuard guard(m->ctx[k]->device);
+      if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+      for (int j = 0; j < m->n; j++)
+        RN_CUDA(cudaMemcpyPeerAsync(full_dst[k] + (size_t)j * slab_elems, m->devices[k], slab_src[j], m->devices[j], slab_elems * sizeof(Elem),
+                                    m->ctx[k]->stream));
+    }
+  }
+  return sync_all(m, false);
 }
 
 }  // extern "C"

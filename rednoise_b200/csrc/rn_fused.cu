@@ -154,12 +154,12 @@ __global__ void __launch_bounds__(NT, MINB) k_stream(const __grid_constant__ Str
 
 // Warp-synchronous march (rn_march.cuh): every warp is an independent (strip, segment) unit; no shared memory, no barriers.
 template <bool EDGE, int PH>
-__device__ __forceinline__ void march_step(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, int u, int lane)
+__device__ __forceinline__ void march_step(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* ring, int u, int lane)
 {
   using M = March<EDGE>;
-  M::template p1<PH>(sp, cx, L, u, lane);
+  M::template p1<PH>(sp, cx, L, ring, u, lane);
   M::template x1<PH>(L, nullptr, nullptr);
-  M::template p2<PH>(sp, cx, L, u, lane);
+  M::template p2<PH>(sp, cx, L, ring, u, lane);
   M::template x2<PH>(L, nullptr, nullptr);
   M::template p3<PH>(sp, cx, L, u);
   M::store(sp, cx, L, u, lane, nullptr);
@@ -172,9 +172,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) k_march(const __grid_constant_
   const int lane = (int)threadIdx.x & 31;
   const int id = (int)blockIdx.x * WPB + ((int)threadIdx.x >> 5);
   if (id >= nunits) return;
+  __shared__ __align__(16) E4 ring_s[WPB * kRingE4];  // per warp: four input lattice rows in flight (cp.async)
+  E4* ring = ring_s + ((int)threadIdx.x >> 5) * kRingE4 + 3 * lane;
   const MarchCtx cx = march_ctx(sp, id, blockIdx.z);
   MarchLane L;
-  March<true>::init(sp, cx, L, lane, false);
+  March<true>::init(sp, cx, L, ring, lane, false);
   const int last = cx.a1e;
   int u = cx.a0 - 1;
   while (u <= last) {
@@ -182,18 +184,18 @@ __global__ void __launch_bounds__(32 * WPB, MINB) k_march(const __grid_constant_
       // two steps per trip: the register bank of every carried value is a compile-time constant
       const int hi = cx.lean_hi;
       for (;;) {
-        march_step<false, 0>(sp, cx, L, u, lane);
+        march_step<false, 0>(sp, cx, L, ring, u, lane);
         if (u == hi) {
           March<false>::swap_banks(L);  // an odd number of lean steps: the next (EDGE) step expects its row in bank 0
           break;
         }
-        march_step<false, 1>(sp, cx, L, u + 1, lane);
+        march_step<false, 1>(sp, cx, L, ring, u + 1, lane);
         if (u + 1 == hi) break;
         u += 2;
       }
       u = hi + 1;
     } else {
-      march_step<true, 0>(sp, cx, L, u, lane);
+      march_step<true, 0>(sp, cx, L, ring, u, lane);
       March<true>::swap_banks(L);
       u++;
     }

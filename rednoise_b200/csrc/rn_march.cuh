@@ -3,17 +3,18 @@
 //
 // Same march as rn_stream.cuh (a strip of cell columns walked row by row, nothing recomputed in the marching
 // direction, ordered shade gather), re-cut for the instruction-issue bound that kernel ran into:
-//   * ONE WARP owns a strip and nothing is shared between warps: no shared memory, no block barriers.  What a lane needs
-//     from its neighbours (one centre, two generateSquare losses, two generateDiamond losses per step) travels by
-//     warp shuffles; everything else lives in registers across steps.
+//   * ONE WARP owns a strip and nothing is shared between warps: no block barriers.  What a lane needs from its
+//     neighbours (one centre, two generateSquare losses, two generateDiamond losses per step) travels by warp
+//     shuffles; everything else a step hands to the next lives in registers.  Shared memory only holds the input
+//     lattice rows on their way in: every lane copies its own three lattice points of row u+3 with cp.async while step u
+//     runs (a private ring of four rows per warp), so the L2 latency of the input never reaches the issue stream.
 //   * a lane owns TWO adjacent cell columns, so its two square centres, its two loop-1 midpoints and its two loop-2
 //     midpoints are each evaluated as ONE packed-FP32 instruction stream (rn_math.cuh: F2, displace2), the values the two
 //     cells share are loaded once, and the per-step bookkeeping is paid once per eight output samples;
 //   * a lane's four output columns of a row are contiguous: finished rows go from registers to global memory as full
 //     32-byte sectors (st.global.v8.f32 -> STG.E.ENL2.256).  Rows whose first sample sits on an odd 16-byte slot (every
 //     other row of a (W+1)-pitched field) are shifted by one sample with four shuffles; the two samples at the warp's
-//     ends are stored as 16-byte halves.  The input lattice (this library's own scratch, even pitch) is read with one
-//     256-bit and one 128-bit load per lane and step.
+//     ends are stored as 16-byte halves.
 //
 // Lanes: lane l holds the lattice / cell columns k0 = L0 + 2l and k1 = k0 + 1 (L0 even) and reads column k1 + 1 as well.
 // Lanes 0 and 31 are halo: their samples are incomplete (they have no left / right neighbour) and are never stored, so a
@@ -22,14 +23,14 @@
 // Step u (cell row u; vocabulary of rn_tile.cuh):
 //   P1   S(u): centres C(u, k0), C(u, k1) from lattice rows u, u+1        (averageSquare + generateSquare)
 //   X1   losses TS(u, .) to both neighbours, C(u, k1) to the right neighbour
-//   P2   D(u): mids M1(u, k0), M1(u, k1) and M2(u-1, k0), M2(u-1, k1)       (averageDiamond + generateDiamond);
-//        lattice row u+2 is requested from global memory into the registers row u occupied
+//   P2   D(u): mids M1(u, k0), M1(u, k1) and M2(u-1, k0), M2(u-1, k1)       (averageDiamond + generateDiamond)
 //   X2   losses TD1(u, k1) to the right, TD2(u-1, k0) to the left neighbour
 //   P3   G(u-1): final shade of corners K(u-1, .) and centres C(u-1, .) (ordered gather), addVolcano, store of output
 //        rows 2(u-1) and 2(u-1)+1
 // Values of step u-1 that step u needs sit in the other of two register banks; the march is unrolled by two with the bank
-// as a template argument, so no value is ever moved.  Steps that touch the first / last lattice rows and strips on a
-// lattice column border run the EDGE instantiation (existence tests, border forms, per-sample stores).
+// as a template argument, so no value is ever moved.  Steps that touch the first / last lattice rows, strips on a
+// lattice column border, strips cut by the window and the few warps inside the volcano's crater run the EDGE
+// instantiation (existence tests, border forms, the crater branch of addVolcano, per-sample stores).
 //
 // Compiles as plain C++ for tests/host_replay (a warp = 32 MarchLane structs, a shuffle = a read of the neighbour's struct).
 #pragma once
@@ -40,7 +41,6 @@ namespace rn {
 constexpr int kMarchCols = 60;  // cell columns a warp finishes
 
 struct MarchLane {
-  E4 lat[2][3];    // bank (t&1): K(u, k0), K(u, k1), K(u, k1+1) as read (pos + input shade); other bank: row u+1
   E4 kc[2][2];     // bank (t&1): K'(u, k0/k1) = corner with the shade generateSquare's scatter left (written in P2)
   E4 cen[2][3];    // bank (t&1): C(u, k0-1), C(u, k0), C(u, k1)
   E4 m1[2][2];     // bank (t&1): M1(u, k0/k1)
@@ -48,7 +48,7 @@ struct MarchLane {
   float td1[2][3]; // bank (t&1): TD1(u; k0-1, k0, k1)
   float td2[2][3]; // bank (t&1): TD2(u-1; k0, k1, k1+1)
   uint32_t sS, sD1, sD2;  // LCG states whose extraction is the draw of column k0's next S / loop-1 / loop-2 call
-  const E4* src;   // lattice (row of the next prefetch, column k0)
+  const E4* src;   // lattice (row of the next cp.async, column k0)
   E4* dst;         // output (row 2(u-1), column 2*k0) of the step in progress, relative to the window
   float fy2[4];    // squared column distance of the lane's four output columns from the volcano
   int ok;          // bit j: output column 2*k0 + j belongs to the strip and lies inside the stored window
@@ -64,10 +64,35 @@ struct MarchCtx {
   E4* gout;
   int far;         // every sample of the warp lies outside the volcano's crater
   int lean_lo, lean_hi;  // steps that touch no lattice row border
-  int col_lean;    // all 65 lattice columns of the warp exist and it owns no closing column
-  int fast;        // the warp's 120 output columns are all owned and inside the window: sector stores
-  int in256;       // the input rows can be read with 256-bit loads
+  int col_lean;    // all 65 lattice columns of the warp exist, it owns 60 whole cell columns inside the window (sector stores) and
+                   // lies outside the crater: its interior steps run the lean instantiation
 };
+
+// The warp's ring of input lattice rows in shared memory: row r sits in slot r & 3, lane l's three points (columns k0, k0+1,
+// k0+2) at [slot][3*l + q] -- every lane reads only what it copied itself, so no synchronisation beyond cp.async.wait_group.
+constexpr int kRingRowE4 = 96;               // 32 lanes x 3 points
+constexpr int kRingE4 = 4 * kRingRowE4;      // per warp (6 KB)
+RN_HD E4* ring_row(E4* ring_lane, int r) { return ring_lane + (r & 3) * kRingRowE4; }
+RN_HD void ring_copy16(E4* dst_smem, const E4* src_global)
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src_global) : "memory");
+#else
+  *dst_smem = *src_global;
+#endif
+}
+RN_HD void ring_commit()
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+RN_HD void ring_wait_all_but_2()  // everything but the two most recent groups has landed
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group 2;" ::: "memory");
+#endif
+}
 
 // id enumerates (strip, segment) pairs exactly like stream_ctx: the strips on a lattice column border first, cut into
 // shorter segments because every one of their steps runs the slower EDGE instantiation.
@@ -99,11 +124,10 @@ RN_HD MarchCtx march_ctx(const StreamParams& sp, int id, unsigned f)
   cx.gin = sp.gin + (size_t)f * sp.gin_field_stride;
   cx.gout = sp.gout + (size_t)f * sp.gout_field_stride;
   cx.far = stream_box_is_far(2 * cx.a0, 2 * cx.a1e - 1, 2 * cx.B0, 2 * (cx.B0 + cx.CWe) - 1, 1 << sp.dout);
-  cx.col_lean = cx.L0 >= 0 && cx.L0 + 64 <= n && cx.CWe == cx.CW;
+  const bool fast = cx.CW == kMarchCols && cx.CWe == cx.CW && 2 * cx.B0 >= sp.win_j0 && 2 * (cx.B0 + cx.CW) <= sp.win_j0 + sp.win_nj;
+  cx.col_lean = cx.L0 >= 0 && cx.L0 + 64 <= n && fast && (!sp.volcano || cx.far);
   cx.lean_lo = imax_(cx.a0 - 1, 1);
   cx.lean_hi = cx.a1e <= n - 1 ? cx.a1e : n - 2;
-  cx.fast = cx.CW == kMarchCols && cx.CWe == cx.CW && 2 * cx.B0 >= sp.win_j0 && 2 * (cx.B0 + cx.CW) <= sp.win_j0 + sp.win_nj;
-  cx.in256 = (sp.gin_pitch % 2 == 0) && (sp.gin_field_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(sp.gin) % 32 == 0);
   return cx;
 }
 RN_HD bool march_step_is_lean(const MarchCtx& cx, int u) { return cx.col_lean && u >= cx.lean_lo && u <= cx.lean_hi; }
@@ -164,18 +188,6 @@ RN_HD void st256(E4* p, const E4& a, const E4& b)  // p is 32-byte aligned: one 
   p[1] = b;
 #endif
 }
-RN_HD void ld256(const E4* p, E4& a, E4& b)
-{
-#if defined(__CUDA_ARCH__)
-  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-               : "l"(p));
-#else
-  a = p[0];
-  b = p[1];
-#endif
-}
-
 // Two samples displaced at once from their averaged elements and direction vectors (the tail of generateSquare /
 // generateDiamond, Terrain.cpp:185-213,230-257): displace2 + the shade terms, bit for bit what mid_interior2 does.
 RN_HD void displaced_pair(const Law& law, F2 a_xy, F2 a_zw, F2 b_xy, F2 b_zw, const V3P& dir1, const V3P& dir2, float blah, uint32_t draw_a,
@@ -208,27 +220,21 @@ RN_HD void centre_pair(const Law& law, const E4& a00, const E4& a10, const E4& a
 
 template <bool EDGE>
 struct March {
-  static RN_HD bool lattice_exists(const StreamParams& sp, int r, int k)
+  // cp.async of lattice row r (the lane's columns k0 .. k0+2, from p = &gin[r][k0]) into the ring; always one commit group
+  static RN_HD void prefetch_row(const StreamParams& sp, const MarchCtx& cx, E4* ring, const E4* p, int r, int k0)
   {
-    const int n = sp.lev.n;
-    return r >= 0 && r <= n && k >= 0 && k <= n;
-  }
-  // lattice row r, columns k0 .. k0+2 of the lane, from p = &gin[r][k0]
-  static RN_HD void load_row(const StreamParams& sp, const MarchCtx& cx, const E4* p, int r, int k0, E4* dst3)
-  {
-    if (!EDGE) {
-      if (cx.in256) ld256(p, dst3[0], dst3[1]);
-      else { dst3[0] = p[0]; dst3[1] = p[1]; }
-      dst3[2] = p[2];
-    } else {
+    if (r <= cx.a1e + 1 && r >= 0 && r <= sp.lev.n) {  // uniform: a later step reads the row, and it exists
+      E4* slot = ring_row(ring, r);
 #pragma unroll
       for (int q = 0; q < 3; q++)
-        if (lattice_exists(sp, r, k0 + q)) dst3[q] = p[q];
+        if (!EDGE || (k0 + q >= 0 && k0 + q <= sp.lev.n)) ring_copy16(slot + q, p + q);
     }
+    ring_commit();
   }
 
   // ------------------------------------------------------------------ start-up ----
-  static RN_HD void init(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, int lane, bool poison)
+  // ring: the lane's part of the warp's ring (ring_of_warp + 3 * lane)
+  static RN_HD void init(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* ring, int lane, bool poison)
   {
     const int u0 = cx.a0 - 1;
     const int k0 = cx.L0 + 2 * lane;
@@ -238,7 +244,7 @@ struct March {
 #pragma unroll
     for (int b = 0; b < 2; b++) {
 #pragma unroll
-      for (int q = 0; q < 3; q++) { L.lat[b][q] = z4; L.cen[b][q] = z4; L.td1[b][q] = z; L.td2[b][q] = z; }
+      for (int q = 0; q < 3; q++) { L.cen[b][q] = z4; L.td1[b][q] = z; L.td2[b][q] = z; }
 #pragma unroll
       for (int q = 0; q < 2; q++) { L.kc[b][q] = z4; L.m1[b][q] = z4; }
 #pragma unroll
@@ -261,21 +267,22 @@ struct March {
     // (both pointers may start outside their grids; they are only dereferenced where the row / column exists)
     L.src = cx.gin + ((ptrdiff_t)u0 * (ptrdiff_t)sp.gin_pitch + (ptrdiff_t)k0);
     L.dst = cx.gout + ((ptrdiff_t)(2 * (u0 - 1) - sp.win_i0) * (ptrdiff_t)sp.gout_pitch + (ptrdiff_t)(2 * k0 - sp.win_j0));  // the first step finishes cell row u0 - 1
-#pragma unroll
-    for (int b = 0; b < 2; b++) {  // rows u0, u0+1 -> banks 0, 1
-#pragma unroll
-      for (int q = 0; q < 3; q++)
-        if (lattice_exists(sp, u0 + b, k0 + q)) L.lat[b][q] = L.src[q];
+    for (int b = 0; b < 3; b++) {  // rows u0, u0+1, u0+2: one commit group each; step u requests row u+3
+      prefetch_row(sp, cx, ring, L.src, u0 + b, k0);
       L.src += sp.gin_pitch;
     }
   }
 
   // ------------------------------------------------------------------ P1: S(u) ----
   template <int PH>
-  static RN_HD void p1(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, int u, int lane)
+  static RN_HD void p1(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* ring, int u, int lane)
   {
-    const E4* ka = L.lat[PH];
-    const E4* kb = L.lat[PH ^ 1];
+    // lattice row u+3 sets out now; rows u and u+1 have landed once at most two groups are still in flight
+    prefetch_row(sp, cx, ring, L.src, u + 3, cx.L0 + 2 * lane);
+    L.src += sp.gin_pitch;
+    ring_wait_all_but_2();
+    const E4* ka = ring_row(ring, u);
+    const E4* kb = ring_row(ring, u + 1);
     const uint32_t sB = kLcgA * L.sS + kLcgC;
     const uint32_t draw_a = lcg_draw_from_state(L.sS), draw_b = lcg_draw_from_state(sB);
     L.sS = jump_apply(sp.jn, L.sS);
@@ -310,9 +317,9 @@ struct March {
 
   // ------------------------------------------------------------------ P2: D(u) ----
   template <int PH>
-  static RN_HD void p2(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, int u, int lane)
+  static RN_HD void p2(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, const E4* ring, int u, int lane)
   {
-    const E4* ka = L.lat[PH];
+    const E4* ka = ring_row(const_cast<E4*>(ring), u);
     const float* tsm = L.ts[PH ^ 1];
     const float* tsc = L.ts[PH];
     const E4* cenm = L.cen[PH ^ 1];
@@ -362,9 +369,6 @@ struct March {
     }
     L.kc[PH][0] = K0;
     L.kc[PH][1] = K1;
-    // lattice row u+2 (S(u+1) and D(u+2) need it) into the bank row u occupied
-    if (u + 1 <= cx.a1e) load_row(sp, cx, L.src, u + 2, cx.L0 + 2 * lane, L.lat[PH]);
-    L.src += sp.gin_pitch;
   }
   template <int PH>
   static RN_HD void x2(MarchLane& L, const MarchLane* left, const MarchLane* right)
@@ -402,7 +406,7 @@ struct March {
       for (int r = 0; r < 2; r++) {
         const float fx = (float)(2 * (u - 1) + r - Wout / 2);
         const float fx2 = fx * fx;
-        if (!EDGE && cx.far) {  // uniform; two columns at once (packed pair)
+        if (!EDGE) {  // lean warps lie outside the crater: no branch, two columns at once (packed pair)
           const F2 h01 = f2mul(rcp_rn_normal2(sqrt_rn_normal2(f2add(f2s(fx2), f2(L.fy2[0], L.fy2[1])))), f2s(gain_w));
           const F2 h23 = f2mul(rcp_rn_normal2(sqrt_rn_normal2(f2add(f2s(fx2), f2(L.fy2[2], L.fy2[3])))), f2s(gain_w));
           L.out[r][0].y = L.out[r][0].y + f2lo(h01);
@@ -423,8 +427,7 @@ struct March {
 #define RN_SWAP_(T, a, b) { const T t__ = a; a = b; b = t__; }
 #pragma unroll
     for (int q = 0; q < 3; q++) {
-      RN_SWAP_(E4, L.lat[0][q], L.lat[1][q]) RN_SWAP_(E4, L.cen[0][q], L.cen[1][q]) RN_SWAP_(float, L.td1[0][q], L.td1[1][q])
-      RN_SWAP_(float, L.td2[0][q], L.td2[1][q])
+      RN_SWAP_(E4, L.cen[0][q], L.cen[1][q]) RN_SWAP_(float, L.td1[0][q], L.td1[1][q]) RN_SWAP_(float, L.td2[0][q], L.td2[1][q])
     }
 #pragma unroll
     for (int q = 0; q < 2; q++) { RN_SWAP_(E4, L.kc[0][q], L.kc[1][q]) RN_SWAP_(E4, L.m1[0][q], L.m1[1][q]) }
@@ -448,7 +451,7 @@ struct March {
       if ((unsigned)(gi - sp.win_i0) >= (unsigned)sp.win_ni || gi > Wout) continue;  // uniform
       E4* row = r == 0 ? dst : dst + sp.gout_pitch;
       const E4* v = L.out[r];
-      if (!EDGE && cx.fast) {
+      if (!EDGE) {  // lean warps own 60 whole cell columns inside the window
         const bool mine = lane >= 1 && lane <= 30;
         if ((reinterpret_cast<uintptr_t>(row) & 16u) == 0) {  // uniform: the lane's four samples are two whole sectors
           if (mine) {

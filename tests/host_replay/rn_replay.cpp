@@ -174,13 +174,13 @@ int run_stream_t(const StageLaunch& sl, int nfields, const uint32_t* seeds, int 
 // of the neighbouring lane's struct after every lane has finished the phase before it.  With `poison` all lane state starts as
 // NaN and the values the device shuffles in from outside the warp (lane 0's left, lane 31's right) are NaN too.
 template <bool EDGE, int PH>
-void march_step_host(const StreamParams& sp, const MarchCtx& cx, std::vector<MarchLane>& L, int u)
+void march_step_host(const StreamParams& sp, const MarchCtx& cx, std::vector<MarchLane>& L, E4* ringw, int u)
 {
   using M = March<EDGE>;
 #define RN_LANES(call) for (int q = 0; q < 32; q++) { const int l = g_reverse ? 31 - q : q; call; }
-  RN_LANES(M::template p1<PH>(sp, cx, L[l], u, l))
+  RN_LANES(M::template p1<PH>(sp, cx, L[l], ringw + 3 * l, u, l))
   RN_LANES(M::template x1<PH>(L[l], l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
-  RN_LANES(M::template p2<PH>(sp, cx, L[l], u, l))
+  RN_LANES(M::template p2<PH>(sp, cx, L[l], ringw + 3 * l, u, l))
   RN_LANES(M::template x2<PH>(L[l], l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
   RN_LANES(M::template p3<PH>(sp, cx, L[l], u))
   RN_LANES(M::store(sp, cx, L[l], u, l, l > 0 ? &L[l - 1] : nullptr))
@@ -190,6 +190,8 @@ void march_step_host(const StreamParams& sp, const MarchCtx& cx, std::vector<Mar
 int run_march(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
 {
   std::vector<MarchLane> L(32);
+  std::vector<E4> ringv(kRingE4 + 1);
+  E4* ringw = ringv.data();
   for (int f = 0; f < nfields; f++)
     for (unsigned id = 0; id < sl.gx; id++) {
       StreamParams sp = sl.st;
@@ -197,7 +199,8 @@ int run_march(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
       MarchCtx cx = march_ctx(sp, (int)id, (unsigned)f);
       if (force_edge) cx.col_lean = 0;
       memset(L.data(), poison ? 0xff : 0, sizeof(MarchLane) * L.size());
-      for (int l = 0; l < 32; l++) March<true>::init(sp, cx, L[l], l, poison != 0);
+      memset(ringw, poison ? 0xff : 0, sizeof(E4) * kRingE4);
+      for (int l = 0; l < 32; l++) March<true>::init(sp, cx, L[l], ringw + 3 * l, l, poison != 0);
       // the kernel's loop (rn_fused.cu: k_march), including its bank bookkeeping
       const int last = cx.a1e;
       int u = cx.a0 - 1;
@@ -205,18 +208,18 @@ int run_march(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
         if (march_step_is_lean(cx, u)) {
           const int hi = cx.lean_hi;
           for (;;) {
-            march_step_host<false, 0>(sp, cx, L, u);
+            march_step_host<false, 0>(sp, cx, L, ringw, u);
             if (u == hi) {
               for (int l = 0; l < 32; l++) March<false>::swap_banks(L[l]);
               break;
             }
-            march_step_host<false, 1>(sp, cx, L, u + 1);
+            march_step_host<false, 1>(sp, cx, L, ringw, u + 1);
             if (u + 1 == hi) break;
             u += 2;
           }
           u = hi + 1;
         } else {
-          march_step_host<true, 0>(sp, cx, L, u);
+          march_step_host<true, 0>(sp, cx, L, ringw, u);
           for (int l = 0; l < 32; l++) March<true>::swap_banks(L[l]);
           u++;
         }

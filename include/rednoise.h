@@ -224,10 +224,13 @@ int rn_cloud(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, r
  * The reference has no volume generator: there is nothing to be bit-exact with, so the
  * definition is this repository's own CPU specification oracle/rn_oracle3d.c -- 3D midpoint displacement in the
  * reference's style (cube centres, face centres, edge midpoints per level; amplitude law of Rock.cpp:185,
- * random() of basics.h:16-19; depth-1 levels on a (W+1)^3 lattice, W = 1 << depth).  The CUDA path reproduces that
- * specification bit for bit.  Planes [i0, i0+ni) of the volume are final after the call; `vol` is DEVICE memory in
- * the full-volume layout, element (i,j,k) at vol[(i*(W+1)+j)*(W+1)+k] (planes outside the slab receive partial
- * coarse-level data): slabs of one volume are independent, which is how it shards across GPUs. */
+ * random() of basics.h:16-19; the draw of lattice point (i,j,k) is a 32-bit integer hash of (seed, i, j, k);
+ * depth-1 levels on a (W+1)^3 lattice, W = 1 << depth).  The CUDA path reproduces that specification bit for bit.
+ * The call produces planes [i0, i0+ni) of the volume into `slab`: DEVICE memory, ni x (W+1) x (W+1) floats, dense,
+ * element (i,j,k) at slab[((i-i0)*(W+1)+j)*(W+1)+k] (rn_volume3d_slab_elems floats).  Slabs of one volume are
+ * independent (what a slab needs of the coarser levels is recomputed on its device, in context-owned scratch), which
+ * is how a volume shards across GPUs without a collective and why a 2049^3 volume (34.4 GB) never has to exist on
+ * one device. */
 #define RN_VOLUME_MIN_DEPTH 2
 #define RN_VOLUME_MAX_DEPTH 11 /* 2049^3 floats = 34.4 GB */
 typedef struct rn_volume_params {
@@ -235,7 +238,8 @@ typedef struct rn_volume_params {
   int32_t depth;
   float amplitude;
 } rn_volume_params;
-int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, float* vol, void* stream);
+int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, float* slab, void* stream);
+uint64_t rn_volume3d_slab_elems(int depth, int ni);
 
 /* ---- memory helpers ---------------------------------------------------------------------------
  * So that a C/C++ caller (the adapter inside Terrain::Terrain) needs no CUDA runtime of its own:

@@ -58,8 +58,9 @@ long long rno_rock_indexed(uint32_t state_in, int depth, float amplitude, float*
 long long rno_cloud(uint32_t state_in, int depth, float amplitude, float* faces, rn_cell* cells, uint32_t* state_out);
 
 /* 3D density-volume extension (rn_oracle3d.c): NO reference counterpart, parity unpinned by the reference. */
-uint32_t rno_volume_draw(uint32_t seed, uint64_t idx);
-int rno_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, float* volume);
+uint32_t rno_volume_draw(uint32_t seed, uint32_t i, uint32_t j, uint32_t k); /* the integer lattice hash: 15-bit draw of lattice point (i,j,k) */
+/* planes [i0, i0+ni) of the (W+1)^3 volume into `slab` (ni x (W+1) x (W+1) floats, dense) */
+int rno_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, float* slab);
 
 uint64_t rno_fnv64(const void* data, size_t nbytes);
 

@@ -11,32 +11,55 @@
  *   3. edge midpoints (one odd, two even)           : mean of 2 edge ends + the 2-4 adjacent face centres    + offset
  * on a (W+1)^3 lattice of float densities, W = 2^depth, levels s = W/2 .. 2 (depth-1 levels), the 27
  * points at multiples of W/2 starting at 0.  Neighbours outside [0,W] are left out of the mean.
- * The draw of a point is a pure function of (seed, linear lattice index) through a 64-bit mix
- * (splitmix64 finaliser): 2048^3 needs 8.6 G draws, more than the 2^32 period of the CRT LCG the 2D path
- * reproduces, and an index-addressed generator is what makes slabs independent.
+ *
+ * The draw of a point is an INTEGER LATTICE HASH of (seed, i, j, k): 2048^3 needs 8.6 G draws, more than the 2^32
+ * period of the CRT LCG the 2D path reproduces, and an index-addressed generator is what makes slabs independent.
+ * Round 2 changed the definition of that hash (this file IS the specification, so digests changed with it): round 1
+ * mixed the 64-bit linear index with the splitmix64 finaliser, whose two 64-bit multiplications were 40 of the
+ * ~100 GPU instructions per sample; now the three coordinates are multiplied by odd 32-bit constants, xor-ed with the
+ * seed and passed through a 32-bit avalanche finaliser (two multiplications, three xor-shifts); the top 15 bits are
+ * the draw, in the range of the CRT's rand().
+ *
+ * Storage: planes are allocated on demand, so a thin slab of a 2049^3 volume (whose coarse levels reach far beyond
+ * the slab) can be computed without 34 GB of memory.
  */
 #include "rn_oracle.h"
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
-static uint32_t vol_draw(uint32_t seed, uint64_t idx)
+static uint32_t vol_draw(uint32_t seed, uint32_t i, uint32_t j, uint32_t k)
 {
-  uint64_t z = idx + 0x9E3779B97F4A7C15ull * ((uint64_t)seed + 1ull);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (uint32_t)(z >> 33) & 0x7fffu;
+  uint32_t h = seed ^ (i * 0x9E3779B1u) ^ (j * 0x85EBCA77u) ^ (k * 0xC2B2AE3Du);
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h >> 17;
 }
 
-uint32_t rno_volume_draw(uint32_t seed, uint64_t idx) { return vol_draw(seed, idx); }
+uint32_t rno_volume_draw(uint32_t seed, uint32_t i, uint32_t j, uint32_t k) { return vol_draw(seed, i, j, k); }
 
-typedef struct { float* d; int W; size_t S; uint32_t seed; float amplitude; } vol;
-#define VAT(v, i, j, k) ((v)->d[((size_t)(i) * (v)->S + (size_t)(j)) * (v)->S + (size_t)(k)])
+typedef struct { float** plane; int W; size_t S; uint32_t seed; float amplitude; int failed; } vol;
+
+/* element (i,j,k); the plane is created (zero-filled) when first touched */
+static float* vat(vol* v, int i, int j, int k)
+{
+  static float sink;
+  if (!v->plane[i])
+  {
+    v->plane[i] = (float*)calloc(v->S * v->S, sizeof(float));
+    if (!v->plane[i]) { v->failed = 1; return &sink; }
+  }
+  return v->plane[i] + (size_t)j * v->S + (size_t)k;
+}
+#define VAT(v, i, j, k) (*vat((v), (i), (j), (k)))
 
 static float vol_offset(const vol* v, int i, int j, int k, int s)
 {
-  const uint64_t idx = ((uint64_t)i * v->S + (uint64_t)j) * v->S + (uint64_t)k;
-  const float r = rno_random_from_draw((int)vol_draw(v->seed, idx)); /* basics.h:16-19 */
-  return ((v->amplitude * r) * (float)s) / (float)v->W;               /* Rock.cpp:185 */
+  const float r = rno_random_from_draw((int)vol_draw(v->seed, (uint32_t)i, (uint32_t)j, (uint32_t)k)); /* basics.h:16-19 */
+  return ((v->amplitude * r) * (float)s) / (float)v->W;                                                  /* Rock.cpp:185 */
 }
 
 static int inside(const vol* v, int c) { return c >= 0 && c <= v->W; }
@@ -139,17 +162,19 @@ static int vol_halo(int h)
   return e;
 }
 
-/* Fills planes [i0, i0+ni) of the (W+1)^3 volume (full-volume layout); planes outside hold partial data. */
-int rno_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, float* volume)
+/* Planes [i0, i0+ni) of the (W+1)^3 volume into `slab` (ni x (W+1) x (W+1) floats, dense). */
+int rno_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, float* slab)
 {
-  if (!volume || depth < 2 || depth > 11) return RN_ERR_BAD_PARAM;
+  if (!slab || depth < 2 || depth > 11) return RN_ERR_BAD_PARAM;
   vol v;
   v.W = 1 << depth;
   v.S = (size_t)v.W + 1;
-  v.d = volume;
   v.seed = seed;
   v.amplitude = amplitude;
+  v.failed = 0;
   if (i0 < 0 || ni <= 0 || i0 + ni > v.W + 1) return RN_ERR_BAD_PARAM;
+  v.plane = (float**)calloc(v.S, sizeof(float*));
+  if (!v.plane) return RN_ERR_OOM;
   for (int i = 0; i <= v.W; i += v.W / 2)
     for (int j = 0; j <= v.W; j += v.W / 2)
       for (int k = 0; k <= v.W; k += v.W / 2) VAT(&v, i, j, k) = 0.0f;
@@ -158,5 +183,12 @@ int rno_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, floa
     const int e = vol_halo(s / 2);
     vol_level(&v, s, i0 - e, i0 + ni - 1 + e);
   }
-  return RN_OK;
+  for (int i = 0; i < ni; i++)
+  {
+    if (v.plane[i0 + i]) memcpy(slab + (size_t)i * v.S * v.S, v.plane[i0 + i], v.S * v.S * sizeof(float));
+    else v.failed = 1; /* every plane of the slab is written by the last level */
+  }
+  for (int i = 0; i <= v.W; i++) free(v.plane[i]);
+  free(v.plane);
+  return v.failed ? RN_ERR_OOM : RN_OK;
 }

@@ -1,4 +1,4 @@
-"""Per-CTA trace of the streaming output kernel: which SM ran each CTA, when it started and ended (%globaltimer).
+"""Per-unit trace of the output kernel (k_march: one unit = one warp; algorithm 3, k_stream: one CTA): which SM ran each CTA, when it started and ended (%globaltimer).
 
 Needs an instrumented build of the library (the instrumentation is compiled out of the product):
     RN_NVCC_EXTRA=-DRN_STREAM_TRACE python -m rednoise_b200.build --force
@@ -17,6 +17,8 @@ sys.path.insert(0, '/root/repo')
 from rednoise_b200 import capi
 
 ctx = capi.Context(0)
+if len(sys.argv) > 1:
+    ctx.set_algorithm(int(sys.argv[1]))
 p = capi.default_params(seed=12345, depth=12, apply_volcano=1)
 S = capi.side(12)
 s = torch.cuda.Stream(); torch.cuda.set_stream(s)
@@ -45,3 +47,8 @@ for smid, e_ in zip(a[:, 0].tolist(), en.tolist()): last[smid] = max(last[smid],
 l = np.array(list(last.values())) / 1e3
 print("SM finish us: min %.1f p50 %.1f max %.1f" % (l.min(), np.median(l), l.max()))
 print("cta end us percentiles 1,10,50,90,99:", np.percentile(en, [1, 10, 50, 90, 99]) / 1e3)
+cnt = np.array([per[k] for k in sorted(per)])
+fin = np.array([last[k] for k in sorted(per)]) / 1e3
+for c in sorted(set(cnt.tolist())):
+    print("  SMs with %d units: %d, finish p50 %.1f max %.1f us" % (c, (cnt == c).sum(), np.median(fin[cnt == c]), fin[cnt == c].max()))
+print("start us percentiles 1,50,99,100:", np.percentile(st, [1, 50, 99, 100]) / 1e3)

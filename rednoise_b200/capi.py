@@ -22,7 +22,7 @@ SYMBOLS = [
     "rn_version", "rn_last_error_string", "rn_status_string", "rn_params_default", "rn_terrain2d_side",
     "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
     "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_set_pipelining", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device", "rn_selftest_math",
-    "rn_terrain2d_cell_count", "rn_terrain2d_cell_level_offset", "rn_terrain2d_cells", "rn_volume3d",
+    "rn_terrain2d_cell_count", "rn_terrain2d_cell_level_offset", "rn_terrain2d_cells", "rn_volume3d", "rn_volume3d_slab_elems",
     "rn_rock_draw_count", "rn_rock", "rn_cloud_draw_count", "rn_cloud",
     "rn_device_count", "rn_device_alloc", "rn_device_free", "rn_host_alloc", "rn_host_free", "rn_copy_to_host",
     "rn_create_multi", "rn_destroy_multi", "rn_multi_size", "rn_multi_context", "rn_slab_rows", "rn_slab_window",
@@ -112,6 +112,8 @@ def lib() -> C.CDLL:
     L.rn_terrain2d_cell_level_offset.argtypes = [i32]
     L.rn_terrain2d_cells.argtypes = [vp, C.POINTER(Params), vp, sz, i32, vp, i32, vp]
     L.rn_volume3d.argtypes = [vp, C.POINTER(VolumeParams), i32, i32, vp, vp]
+    L.rn_volume3d_slab_elems.restype = u64
+    L.rn_volume3d_slab_elems.argtypes = [i32, i32]
     L.rn_rock_draw_count.restype = C.c_uint64
     L.rn_rock_draw_count.argtypes = [i32]
     L.rn_rock.restype = i32
@@ -258,7 +260,8 @@ class Context:
         return out
 
     def volume3d_ptr(self, seed: int, depth: int, amplitude: float, ptr: int, *, i0: int = 0, ni: int | None = None, stream: int = 0):
-        """3D extension: planes [i0, i0+ni) of the (W+1)^3 float volume at device pointer `ptr` (full-volume layout)."""
+        """3D extension: planes [i0, i0+ni) of the (W+1)^3 float volume into the slab-sized device buffer at `ptr`
+        (ni x (W+1) x (W+1) floats)."""
         vp_ = VolumeParams(seed & 0xFFFFFFFF, depth, amplitude)
         side = (1 << depth) + 1
         _check(lib().rn_volume3d(self._h, C.byref(vp_), i0, side - i0 if ni is None else ni, C.c_void_p(ptr),

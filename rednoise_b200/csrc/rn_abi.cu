@@ -655,19 +655,30 @@ int rn_terrain2d_cells(rn_context* ctx, const rn_params* p, const rn_element* fi
   return RN_OK;
 }
 
-int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, float* vol, void* stream_v)
+int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, float* slab, void* stream_v)
 {
   if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
-  if (!p || !vol) return fail(RN_ERR_BAD_PARAM, "params/vol is NULL");
+  if (!p || !slab) return fail(RN_ERR_BAD_PARAM, "params/slab is NULL");
   if (p->depth < RN_VOLUME_MIN_DEPTH || p->depth > RN_VOLUME_MAX_DEPTH) return fail(RN_ERR_BAD_PARAM, "volume depth out of range [2,11]");
   const int side = (1 << p->depth) + 1;
   if (i0 < 0 || ni <= 0 || i0 > side - ni) return fail(RN_ERR_BAD_PARAM, "slab does not lie inside the volume");
   DeviceGuard guard(ctx->device);
   if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
-  RN_CUDA(volume_generate(vol, p->depth, p->seed, p->amplitude, i0, ni, stream, &ctx->launches));
+  // the coarser level grids of the slab's dependency cone (context-owned, grow-only; consecutive calls on one context are
+  // ordered by the stream they are given)
+  int st = ensure(&ctx->plane, &ctx->plane_bytes, volume_scratch_bytes(p->depth, i0, ni));
+  if (st != RN_OK) return st;
+  RN_CUDA(volume_generate(slab, ctx->plane, p->depth, p->seed, p->amplitude, i0, ni, stream, &ctx->launches));
   if (!stream_v) RN_CUDA(cudaStreamSynchronize(stream));
   return RN_OK;
+}
+
+uint64_t rn_volume3d_slab_elems(int depth, int ni)
+{
+  if (depth < RN_VOLUME_MIN_DEPTH || depth > RN_VOLUME_MAX_DEPTH || ni <= 0) return 0;
+  const uint64_t side = ((uint64_t)1 << depth) + 1;
+  return (uint64_t)ni * side * side;
 }
 
 uint64_t rn_rock_draw_count(int depth)

@@ -44,6 +44,10 @@ struct TlScope {
 #define RN_TL_SCOPE(slot)
 #endif
 
+#ifdef RN_STREAM_TRACE
+__device__ unsigned long long g_trace[4 * 8192];  // per unit: SM, start, end (%globaltimer), border flag
+#endif
+
 template <int L, int T, int NT>
 __global__ void __launch_bounds__(NT, T == kTileSmall ? 8 : ((TileGeo<L, T>::BYTES <= 113 * 1024) ? 2 : 1)) k_stage(const __grid_constant__ StageParams sp)
 {
@@ -123,10 +127,6 @@ __device__ __forceinline__ void stream_march(const StreamParams& sp, const Strea
   S::store_rows(sp, cx, sm, th, cx.a1e - 1, S::mod(S::step_of(cx, cx.a1e - 1), 2));
 }
 
-#ifdef RN_STREAM_TRACE
-__device__ unsigned long long g_trace[4 * 8192];
-#endif
-
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_stream(const __grid_constant__ StreamParams sp)
 {
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NT, MINB) k_stream(const __grid_constant__ Str
 #endif
 }
 
-// Warp-synchronous march (rn_march.cuh): every warp is an independent (strip, segment) unit; no shared memory, no barriers.
+// Warp-synchronous march (rn_march.cuh): every warp is an independent (strip, segment) unit; no block barriers.
 template <bool EDGE, int PH>
 __device__ __forceinline__ void march_step(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* ring, int u, int lane)
 {
@@ -161,7 +161,7 @@ __device__ __forceinline__ void march_step(const StreamParams& sp, const MarchCt
   M::template x1<PH>(L, nullptr, nullptr);
   M::template p2<PH>(sp, cx, L, ring, u, lane);
   M::template x2<PH>(L, nullptr, nullptr);
-  M::template p3<PH>(sp, cx, L, u);
+  M::template p3<PH>(sp, cx, L, ring, u);
   M::store(sp, cx, L, u, lane, nullptr);
 }
 
@@ -175,6 +175,14 @@ __global__ void __launch_bounds__(32 * WPB, MINB) k_march(const __grid_constant_
   __shared__ __align__(16) E4 ring_s[WPB * kRingE4];  // per warp: four input lattice rows in flight (cp.async)
   E4* ring = ring_s + ((int)threadIdx.x >> 5) * kRingE4 + 3 * lane;
   const MarchCtx cx = march_ctx(sp, id, blockIdx.z);
+#ifdef RN_STREAM_TRACE
+  if (lane == 0 && id < 8192) {
+    unsigned smid; unsigned long long t;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[4 * id] = smid; g_trace[4 * id + 1] = t; g_trace[4 * id + 3] = !cx.col_lean;
+  }
+#endif
   MarchLane L;
   March<true>::init(sp, cx, L, ring, lane, false);
   const int last = cx.a1e;
@@ -200,6 +208,13 @@ __global__ void __launch_bounds__(32 * WPB, MINB) k_march(const __grid_constant_
       u++;
     }
   }
+#ifdef RN_STREAM_TRACE
+  if (lane == 0 && id < 8192) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[4 * id + 2] = t;
+  }
+#endif
 }
 
 cudaError_t launch_march(const StreamParams& st, dim3 grid_units, cudaStream_t stream)

@@ -35,8 +35,10 @@ cudaError_t rock_generate(void* faces, void* cells, int* flag, int kind, int dep
                           cudaStream_t stream, uint64_t* launches);
 
 // 3D density-volume extension (rn_volume.cu; defined by the CPU specification of DESIGN.md section 5.8, no reference counterpart):
-// planes [i0, i0+ni) of the (W+1)^3 float volume d (full-volume layout).
-cudaError_t volume_generate(float* d, int depth, uint32_t seed, float amplitude, int i0, int ni, cudaStream_t stream, uint64_t* launches);
+// planes [i0, i0+ni) of the (W+1)^3 float volume into `slab` (ni x (W+1) x (W+1), dense); scratch: volume_scratch_bytes() bytes.
+size_t volume_scratch_bytes(int depth, int i0, int ni);
+cudaError_t volume_generate(float* slab, void* scratch, int depth, uint32_t seed, float amplitude, int i0, int ni, cudaStream_t stream,
+                            uint64_t* launches);
 
 // Epilogues / utilities (rn_util.cu).
 // addVolcano (Terrain.cpp:121-141) over the window [i0,i0+ni) x [j0,j0+nj) of a depth-`depth` field

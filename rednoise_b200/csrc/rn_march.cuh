@@ -6,8 +6,8 @@
 //   * ONE WARP owns a strip and nothing is shared between warps: no block barriers.  What a lane needs from its
 //     neighbours (one centre, two generateSquare losses, two generateDiamond losses per step) travels by warp
 //     shuffles; everything else a step hands to the next lives in registers.  Shared memory only holds the input
-//     lattice rows on their way in: every lane copies its own three lattice points of row u+3 with cp.async while step u
-//     runs (a private ring of four rows per warp), so the L2 latency of the input never reaches the issue stream.
+//     lattice rows: every lane copies its own three lattice points of row u+2 with cp.async while step u runs (a private
+//     ring of four rows per warp: u-1 .. u+2), so the L2 latency of the input never reaches the issue stream.
 //   * a lane owns TWO adjacent cell columns, so its two square centres, its two loop-1 midpoints and its two loop-2
 //     midpoints are each evaluated as ONE packed-FP32 instruction stream (rn_math.cuh: F2, displace2), the values the two
 //     cells share are loaded once, and the per-step bookkeeping is paid once per eight output samples;
@@ -29,8 +29,8 @@
 //        rows 2(u-1) and 2(u-1)+1
 // Values of step u-1 that step u needs sit in the other of two register banks; the march is unrolled by two with the bank
 // as a template argument, so no value is ever moved.  Steps that touch the first / last lattice rows, strips on a
-// lattice column border, strips cut by the window and the few warps inside the volcano's crater run the EDGE
-// instantiation (existence tests, border forms, the crater branch of addVolcano, per-sample stores).
+// lattice column border and strips cut by the window run the EDGE instantiation (existence tests, border forms,
+// per-sample stores).
 //
 // Compiles as plain C++ for tests/host_replay (a warp = 32 MarchLane structs, a shuffle = a read of the neighbour's struct).
 #pragma once
@@ -41,7 +41,7 @@ namespace rn {
 constexpr int kMarchCols = 60;  // cell columns a warp finishes
 
 struct MarchLane {
-  E4 kc[2][2];     // bank (t&1): K'(u, k0/k1) = corner with the shade generateSquare's scatter left (written in P2)
+  float sg[2][2];  // bank (t&1): shade of corner K(u, k0/k1) as generateSquare's scatter left it (written in P2; the position stays in the ring)
   E4 cen[2][3];    // bank (t&1): C(u, k0-1), C(u, k0), C(u, k1)
   E4 m1[2][2];     // bank (t&1): M1(u, k0/k1)
   float ts[2][4];  // bank (t&1): TS(u; k0-1, k0, k1, k1+1)
@@ -64,8 +64,8 @@ struct MarchCtx {
   E4* gout;
   int far;         // every sample of the warp lies outside the volcano's crater
   int lean_lo, lean_hi;  // steps that touch no lattice row border
-  int col_lean;    // all 65 lattice columns of the warp exist, it owns 60 whole cell columns inside the window (sector stores) and
-                   // lies outside the crater: its interior steps run the lean instantiation
+  int col_lean;    // all 65 lattice columns of the warp exist and it owns 60 whole cell columns inside the window (sector stores):
+                   // its interior steps run the lean instantiation
 };
 
 // The warp's ring of input lattice rows in shared memory: row r sits in slot r & 3, lane l's three points (columns k0, k0+1,
@@ -87,10 +87,10 @@ RN_HD void ring_commit()
   asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
 }
-RN_HD void ring_wait_all_but_2()  // everything but the two most recent groups has landed
+RN_HD void ring_wait_all_but_1()  // everything but the most recent group has landed
 {
 #if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.wait_group 2;" ::: "memory");
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
 #endif
 }
 
@@ -125,7 +125,7 @@ RN_HD MarchCtx march_ctx(const StreamParams& sp, int id, unsigned f)
   cx.gout = sp.gout + (size_t)f * sp.gout_field_stride;
   cx.far = stream_box_is_far(2 * cx.a0, 2 * cx.a1e - 1, 2 * cx.B0, 2 * (cx.B0 + cx.CWe) - 1, 1 << sp.dout);
   const bool fast = cx.CW == kMarchCols && cx.CWe == cx.CW && 2 * cx.B0 >= sp.win_j0 && 2 * (cx.B0 + cx.CW) <= sp.win_j0 + sp.win_nj;
-  cx.col_lean = cx.L0 >= 0 && cx.L0 + 64 <= n && fast && (!sp.volcano || cx.far);
+  cx.col_lean = cx.L0 >= 0 && cx.L0 + 64 <= n && fast;
   cx.lean_lo = imax_(cx.a0 - 1, 1);
   cx.lean_hi = cx.a1e <= n - 1 ? cx.a1e : n - 2;
   return cx;
@@ -218,6 +218,20 @@ RN_HD void centre_pair(const Law& law, const E4& a00, const E4& a10, const E4& a
   displaced_pair(law, a_xy, a_zw, b_xy, b_zw, dir1, dir2, blah, draw_a, draw_b, out_a, out_b, loss_a, loss_b);
 }
 
+// addVolcano (Terrain.cpp:129-137) for two samples at once, crater branch included: volcano_height_r2<false> lane by lane
+// (same operations in the same order; the sums after a packed product go through f2add_product, see rn_math.cuh).
+RN_HD F2 volcano_pair_general(F2 r2, float inv_w, float gain, float gain_w, float one)
+{
+  const float minRad = 0.02f;
+  const F2 s = sqrt_rn_normal2(r2);  // not a number for r2 == 0 (the centre sample): replaced below
+  const F2 far = f2mul(rcp_rn_normal2(s), f2s(gain_w));
+  F2 d = f2mul(s, f2s(inv_w));
+  d = f2(f2lo(r2) == 0.0f ? 0.0f : f2lo(d), f2hi(r2) == 0.0f ? 0.0f : f2hi(d));
+  const F2 t = f2add_product(f2mul(d, d), f2s(-(minRad * minRad)), one);
+  const F2 crater = f2mul(f2add_product(f2mul(f2s(60000.f), t), f2s(1.0f / minRad), one), f2s(gain));
+  return f2(!(f2lo(d) >= minRad) ? f2lo(crater) : f2lo(far), !(f2hi(d) >= minRad) ? f2hi(crater) : f2hi(far));
+}
+
 template <bool EDGE>
 struct March {
   // cp.async of lattice row r (the lane's columns k0 .. k0+2, from p = &gin[r][k0]) into the ring; always one commit group
@@ -246,7 +260,7 @@ struct March {
 #pragma unroll
       for (int q = 0; q < 3; q++) { L.cen[b][q] = z4; L.td1[b][q] = z; L.td2[b][q] = z; }
 #pragma unroll
-      for (int q = 0; q < 2; q++) { L.kc[b][q] = z4; L.m1[b][q] = z4; }
+      for (int q = 0; q < 2; q++) { L.sg[b][q] = z; L.m1[b][q] = z4; }
 #pragma unroll
       for (int q = 0; q < 4; q++) { L.ts[b][q] = z; L.out[b][q] = z4; }
     }
@@ -267,7 +281,7 @@ struct March {
     // (both pointers may start outside their grids; they are only dereferenced where the row / column exists)
     L.src = cx.gin + ((ptrdiff_t)u0 * (ptrdiff_t)sp.gin_pitch + (ptrdiff_t)k0);
     L.dst = cx.gout + ((ptrdiff_t)(2 * (u0 - 1) - sp.win_i0) * (ptrdiff_t)sp.gout_pitch + (ptrdiff_t)(2 * k0 - sp.win_j0));  // the first step finishes cell row u0 - 1
-    for (int b = 0; b < 3; b++) {  // rows u0, u0+1, u0+2: one commit group each; step u requests row u+3
+    for (int b = 0; b < 2; b++) {  // rows u0, u0+1: one commit group each; step u requests row u+2
       prefetch_row(sp, cx, ring, L.src, u0 + b, k0);
       L.src += sp.gin_pitch;
     }
@@ -277,10 +291,11 @@ struct March {
   template <int PH>
   static RN_HD void p1(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* ring, int u, int lane)
   {
-    // lattice row u+3 sets out now; rows u and u+1 have landed once at most two groups are still in flight
-    prefetch_row(sp, cx, ring, L.src, u + 3, cx.L0 + 2 * lane);
+    // lattice row u+2 sets out now (it lands in the slot row u-2 occupied; the ring keeps rows u-1 .. u+2); rows u and u+1
+    // have landed once at most this one group is still in flight
+    prefetch_row(sp, cx, ring, L.src, u + 2, cx.L0 + 2 * lane);
     L.src += sp.gin_pitch;
-    ring_wait_all_but_2();
+    ring_wait_all_but_1();
     const E4* ka = ring_row(ring, u);
     const E4* kb = ring_row(ring, u + 1);
     const uint32_t sB = kLcgA * L.sS + kLcgC;
@@ -324,7 +339,10 @@ struct March {
     const float* tsc = L.ts[PH];
     const E4* cenm = L.cen[PH ^ 1];
     const E4* cenc = L.cen[PH];
-    const E4* kcm = L.kc[PH ^ 1];
+    const E4* km = ring_row(const_cast<E4*>(ring), u - 1);
+    E4 kcm[2] = {km[0], km[1]};  // K'(u-1, k0/k1): position from the ring, shade as carried
+    kcm[0].w = L.sg[PH ^ 1][0];
+    kcm[1].w = L.sg[PH ^ 1][1];
     // corner shades as generateSquare left them (Terrain.cpp:252-255): minus the scatter of the 4 surrounding centres,
     // in call order (u-1, k-1), (u-1, k), (u, k-1), (u, k)
     E4 K0 = ka[0], K1 = ka[1], K2 = ka[2];
@@ -367,8 +385,8 @@ struct March {
         L.td2[PH][q] = loss2;
       }
     }
-    L.kc[PH][0] = K0;
-    L.kc[PH][1] = K1;
+    L.sg[PH][0] = K0.w;
+    L.sg[PH][1] = K1.w;
   }
   template <int PH>
   static RN_HD void x2(MarchLane& L, const MarchLane* left, const MarchLane* right)
@@ -379,14 +397,17 @@ struct March {
 
   // ------------------------------------------------------------------ P3: G(u-1), addVolcano ----
   template <int PH>
-  static RN_HD void p3(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, int u)
+  static RN_HD void p3(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, const E4* ring, int u)
   {
     const float* tdm = L.td1[PH ^ 1];
     const float* tdc = L.td1[PH];
     const float* t2mm = L.td2[PH ^ 1];
     const float* t2 = L.td2[PH];
     // corner K(u-1, k): generateSquare's scatter (carried), then loop 1 (same row: k-1, k), loop 2 (same column: u-2, u-1)
-    E4 c0 = L.kc[PH ^ 1][0], c1 = L.kc[PH ^ 1][1];
+    const E4* km = ring_row(const_cast<E4*>(ring), u - 1);
+    E4 c0 = km[0], c1 = km[1];
+    c0.w = L.sg[PH ^ 1][0];
+    c1.w = L.sg[PH ^ 1][1];
     c0.w = (((c0.w - tdm[0]) - tdm[1]) - t2mm[0]) - t2[0];
     c1.w = (((c1.w - tdm[1]) - tdm[2]) - t2mm[1]) - t2[1];
     // centre C(u-1, k): loop-1 mids above and below, loop-2 mids left and right
@@ -406,9 +427,17 @@ struct March {
       for (int r = 0; r < 2; r++) {
         const float fx = (float)(2 * (u - 1) + r - Wout / 2);
         const float fx2 = fx * fx;
-        if (!EDGE) {  // lean warps lie outside the crater: no branch, two columns at once (packed pair)
-          const F2 h01 = f2mul(rcp_rn_normal2(sqrt_rn_normal2(f2add(f2s(fx2), f2(L.fy2[0], L.fy2[1])))), f2s(gain_w));
-          const F2 h23 = f2mul(rcp_rn_normal2(sqrt_rn_normal2(f2add(f2s(fx2), f2(L.fy2[2], L.fy2[3])))), f2s(gain_w));
+        if (!EDGE) {  // two columns at once (packed pair); the few warps that touch the crater evaluate its branch as a select
+          const F2 r01 = f2add(f2s(fx2), f2(L.fy2[0], L.fy2[1])), r23 = f2add(f2s(fx2), f2(L.fy2[2], L.fy2[3]));
+          F2 h01, h23;
+          if (cx.far) {  // uniform
+            h01 = f2mul(rcp_rn_normal2(sqrt_rn_normal2(r01)), f2s(gain_w));
+            h23 = f2mul(rcp_rn_normal2(sqrt_rn_normal2(r23)), f2s(gain_w));
+          } else {
+            const float inv_w = 1.0f / (float)Wout;
+            h01 = volcano_pair_general(r01, inv_w, sp.volcano_gain, gain_w, sp.law.one);
+            h23 = volcano_pair_general(r23, inv_w, sp.volcano_gain, gain_w, sp.law.one);
+          }
           L.out[r][0].y = L.out[r][0].y + f2lo(h01);
           L.out[r][1].y = L.out[r][1].y + f2hi(h01);
           L.out[r][2].y = L.out[r][2].y + f2lo(h23);
@@ -430,7 +459,7 @@ struct March {
       RN_SWAP_(E4, L.cen[0][q], L.cen[1][q]) RN_SWAP_(float, L.td1[0][q], L.td1[1][q]) RN_SWAP_(float, L.td2[0][q], L.td2[1][q])
     }
 #pragma unroll
-    for (int q = 0; q < 2; q++) { RN_SWAP_(E4, L.kc[0][q], L.kc[1][q]) RN_SWAP_(E4, L.m1[0][q], L.m1[1][q]) }
+    for (int q = 0; q < 2; q++) { RN_SWAP_(float, L.sg[0][q], L.sg[1][q]) RN_SWAP_(E4, L.m1[0][q], L.m1[1][q]) }
 #pragma unroll
     for (int q = 0; q < 4; q++) RN_SWAP_(float, L.ts[0][q], L.ts[1][q])
 #undef RN_SWAP_

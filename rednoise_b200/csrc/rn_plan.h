@@ -62,10 +62,10 @@ constexpr int kStreamSmallCols = RN_STREAM_SMALL_COLS;    // levels with fewer c
 #define RN_MARCH_WPB 1          // independent warps per CTA
 #endif
 #ifndef RN_MARCH_FREE
-#define RN_MARCH_FREE 2         // warps per SM the output launch leaves to the next call's small coarse stages
+#define RN_MARCH_FREE 1         // warps per SM the output launch leaves to the next call's small coarse stages
 #endif
 #ifndef RN_MARCH_EDGE_COST
-#define RN_MARCH_EDGE_COST 2.0f // duration of a border-strip warp relative to an interior one with the same rows
+#define RN_MARCH_EDGE_COST 1.6f // duration of a border-strip warp relative to an interior one with the same rows
 #endif
 #ifndef RN_MARCH_MIN_SEG_ROWS
 #define RN_MARCH_MIN_SEG_ROWS 8

@@ -182,7 +182,7 @@ void march_step_host(const StreamParams& sp, const MarchCtx& cx, std::vector<Mar
   RN_LANES(M::template x1<PH>(L[l], l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
   RN_LANES(M::template p2<PH>(sp, cx, L[l], ringw + 3 * l, u, l))
   RN_LANES(M::template x2<PH>(L[l], l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
-  RN_LANES(M::template p3<PH>(sp, cx, L[l], u))
+  RN_LANES(M::template p3<PH>(sp, cx, L[l], ringw + 3 * l, u))
   RN_LANES(M::store(sp, cx, L[l], u, l, l > 0 ? &L[l - 1] : nullptr))
 #undef RN_LANES
 }

@@ -140,11 +140,12 @@ class Oracle:
             raise RuntimeError(f"oracle status {st}")
         return out
 
-    def volume3d(self, seed: int, depth: int, amplitude: float, i0: int = 0, ni=None, fill=np.nan) -> np.ndarray:
-        """3D extension (rn_oracle3d.c, no reference counterpart): planes [i0, i0+ni) final, the rest `fill` or partial."""
+    def volume3d(self, seed: int, depth: int, amplitude: float, i0: int = 0, ni=None) -> np.ndarray:
+        """3D extension (rn_oracle3d.c, no reference counterpart): planes [i0, i0+ni) of the (W+1)^3 volume, shape (ni, S, S)."""
         S = (1 << depth) + 1
-        v = np.full((S, S, S), fill, np.float32)
-        st = self.L.rno_volume3d(seed & 0xFFFFFFFF, depth, amplitude, i0, S - i0 if ni is None else ni, v.ctypes.data)
+        ni = S - i0 if ni is None else ni
+        v = np.full((ni, S, S), np.nan, np.float32)
+        st = self.L.rno_volume3d(seed & 0xFFFFFFFF, depth, amplitude, i0, ni, v.ctypes.data)
         if st != 0:
             raise RuntimeError(f"oracle status {st}")
         return v

@@ -290,6 +290,81 @@ def final_kernel_name(args):
     return f"k_stage<2,64,512> (fused tile kernel, last two levels -> {full}^2)"
 
 
+def strong_scaling_records(args, ctx, capi, sharding, torch, dist, rank, world, stream, barrier):
+    """north_star's scaling configs in front of the driver: ONE depth-14 field (16385^2) in row slabs and ONE 2049^3 density
+    volume in i-slabs over the ranks of this run -- fixed total work, no data-path collective (each rank recomputes its slab's
+    dependency cone) -- each beside the same job on rank 0 alone, measured in the same run, so that efficiency =
+    value / (n_gpus * one_gpu.value) can be computed from this line alone.  Timed like the main figure: barrier +
+    synchronize on both sides, CUDA events, max over ranks."""
+    out = {}
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0])
+
+    def alone(fn, steps, warm):  # rank 0 only; the other ranks wait at the barriers inside timed()
+        return timed(fn if rank == 0 else (lambda: None), steps, warm)
+
+    # (i) one depth-14 field in row slabs
+    depth = 14
+    side = (1 << depth) + 1
+    p = capi.default_params(seed=BASE_SEED, depth=depth, apply_volcano=1)
+    i0, j0, ni, nj = sharding.slab_window(side, rank, world)
+    dst = torch.empty((max(ni, 1), nj, 4), device="cuda", dtype=torch.float32)
+    win = capi.Window(i0, j0, max(ni, 1), nj)
+    ms = timed(lambda: ctx.terrain2d_ptr(p, dst.data_ptr(), window=win, dst_is_device=True, stream=stream) if ni else None, 5, 2)
+    rec = {"workload": f"ONE {side}x{side} field (depth 14) in {world} row slab(s), dependency cone recomputed per rank, no collective",
+           "samples": side * side, "n_gpus": world, "ms_per_step": ms, "value": side * side / (ms * 1e-3) / 1e9, "unit": "Gsamples/s"}
+    del dst
+    if world > 1:
+        full = torch.empty((side, side, 4), device="cuda", dtype=torch.float32) if rank == 0 else None
+        ms1 = alone(lambda: ctx.terrain2d_ptr(p, full.data_ptr(), dst_is_device=True, stream=stream), 5, 2)
+        rec["one_gpu"] = {"ms_per_step": ms1, "value": side * side / (ms1 * 1e-3) / 1e9}
+        del full
+    else:
+        rec["one_gpu"] = {"ms_per_step": ms, "value": rec["value"]}
+    rec["efficiency_inputs"] = "value / (n_gpus * one_gpu.value)"
+    out["field_depth14_row_slabs"] = rec
+    torch.cuda.empty_cache()
+
+    # (ii) one 2049^3 volume in i-slabs (3D extension, defined by oracle/rn_oracle3d.c; the reference has no volume generator)
+    vdepth = 11
+    S3 = (1 << vdepth) + 1
+    i0, _, ni, _ = sharding.slab_window(S3, rank, world)
+    try:
+        vol = torch.empty((max(ni, 1), S3, S3), device="cuda", dtype=torch.float32)
+        ms = timed(lambda: ctx.volume3d_ptr(BASE_SEED, vdepth, 0.3, vol.data_ptr(), i0=i0, ni=ni, stream=stream) if ni else None, 3, 1)
+        rec = {"workload": f"ONE {S3}^3 density volume (3D extension, 10 levels) in {world} i-slab(s) of {sharding.slab_rows(S3, world)} planes, "
+                           "slab-sized destinations, dependency cone recomputed per rank, no collective",
+               "samples": S3 ** 3, "n_gpus": world, "ms_per_step": ms, "value": S3 ** 3 / (ms * 1e-3) / 1e9, "unit": "Gsamples/s"}
+        del vol
+        torch.cuda.empty_cache()
+        if world > 1:
+            full = torch.empty((S3, S3, S3), device="cuda", dtype=torch.float32) if rank == 0 else None
+            ms1 = alone(lambda: ctx.volume3d_ptr(BASE_SEED, vdepth, 0.3, full.data_ptr(), stream=stream), 3, 1)
+            rec["one_gpu"] = {"ms_per_step": ms1, "value": S3 ** 3 / (ms1 * 1e-3) / 1e9}
+            del full
+        else:
+            rec["one_gpu"] = {"ms_per_step": ms, "value": rec["value"]}
+        rec["efficiency_inputs"] = "value / (n_gpus * one_gpu.value)"
+        out["volume_2049_i_slabs"] = rec
+    except Exception as e:  # e.g. not enough free HBM for the 34.4 GB single-GPU volume on a shared box
+        out["volume_2049_i_slabs"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------ our arm ---
 def run_ours(args):
     import torch
@@ -348,7 +423,7 @@ def run_ours(args):
         i0, _, ni, _ = sharding.slab_window(S3, rank, world)
         my_samples = ni * S3 * S3
         nj = S3
-        vol = torch.empty((S3, S3, S3), device="cuda", dtype=torch.float32)  # full-volume layout (the ABI's contract)
+        vol = torch.empty((max(ni, 1), S3, S3), device="cuda", dtype=torch.float32)  # slab-sized: only this rank's planes
         p = None
         win = None
         seeds = []
@@ -419,7 +494,7 @@ def run_ours(args):
         def e2e_step():
             if ni_e:
                 ctx.volume3d_ptr(BASE_SEED, depth, 0.3, vol.data_ptr(), i0=i0, ni=ni_e)  # blocking
-                host[:ni_e].copy_(vol[i0:i0 + ni_e])                                      # the slab's planes are contiguous
+                host[:ni_e].copy_(vol[:ni_e])                                             # the slab's planes are contiguous
                 return float(host[ni_e // 2, S3 // 2, S3 // 2])
             return 0.0
     elif args.workload == "batch":
@@ -448,6 +523,9 @@ def run_ours(args):
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    strong = None
+    if args.workload == "field" and not args.no_strong:
+        strong = strong_scaling_records(args, ctx, capi, sharding, torch, dist, rank, world, stream, barrier)
     t = torch.tensor([total_ms, e2e_s, float(my_samples), float(e2e_samples)], device="cuda", dtype=torch.float64)
     if world > 1:
         tmax = t.clone()
@@ -488,6 +566,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks, "algorithm": args.algo,
             "per_step_ms": {"min": min(per_step), "median": statistics.median(per_step), "max": max(per_step)},
         }
+        if strong:
+            line["strong"] = strong
         if stage_ms:
             line["stage_ms"] = stage_ms
             alu = alu_roofline(args, value, k_ms, my_samples, (clocks or {}).get("sm_mhz"))
@@ -540,6 +620,7 @@ def main():
     ap.add_argument("--algo", type=int, default=0)
     ap.add_argument("--cpu-procs", type=int, default=0, help="reference arm: concurrent single-threaded generators (0 = all host cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling records (one depth-14 field / one 2049^3 volume in slabs)")
     ap.add_argument("--no-pipelining", action="store_true", help="run the coarse stages on the caller's stream (no overlap between calls)")
     args = ap.parse_args()
     if args.depth is None:

@@ -153,27 +153,27 @@ __global__ void __launch_bounds__(NT, MINB) k_stream(const __grid_constant__ Str
 }
 
 // Warp-synchronous march (rn_march.cuh): every warp is an independent (strip, segment) unit; no block barriers.
-template <bool EDGE, int PH>
-__device__ __forceinline__ void march_step(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* ring, int u, int lane)
+template <bool EDGE>
+__device__ __forceinline__ void march_step(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* wsm, int u, int lane)
 {
   using M = March<EDGE>;
-  M::template p1<PH>(sp, cx, L, ring, u, lane);
-  M::template x1<PH>(L, nullptr, nullptr);
-  M::template p2<PH>(sp, cx, L, ring, u, lane);
-  M::template x2<PH>(L, nullptr, nullptr);
-  M::template p3<PH>(sp, cx, L, ring, u);
+  M::p1(sp, cx, L, wsm, u, lane);
+  M::x1(cx, L, wsm, u, lane, nullptr, nullptr);
+  M::p2(sp, cx, L, wsm, u, lane);
+  M::x2(cx, L, wsm, u, lane, nullptr, nullptr);
+  M::p3(sp, cx, L, wsm, u, lane);
   M::store(sp, cx, L, u, lane, nullptr);
 }
 
 template <int WPB, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB) k_march(const __grid_constant__ StreamParams sp, const int nunits)
 {
+  extern __shared__ __align__(16) float sm[];
   RN_TL_SCOPE(sp.tl_slot);
   const int lane = (int)threadIdx.x & 31;
   const int id = (int)blockIdx.x * WPB + ((int)threadIdx.x >> 5);
   if (id >= nunits) return;
-  __shared__ __align__(16) E4 ring_s[WPB * kRingE4];  // per warp: four input lattice rows in flight (cp.async)
-  E4* ring = ring_s + ((int)threadIdx.x >> 5) * kRingE4 + 3 * lane;
+  E4* wsm = reinterpret_cast<E4*>(sm) + ((int)threadIdx.x >> 5) * kWarpE4;  // this warp's ring, carried state and constants
   const MarchCtx cx = march_ctx(sp, id, blockIdx.z);
 #ifdef RN_STREAM_TRACE
   if (lane == 0 && id < 8192) {
@@ -184,29 +184,11 @@ __global__ void __launch_bounds__(32 * WPB, MINB) k_march(const __grid_constant_
   }
 #endif
   MarchLane L;
-  March<true>::init(sp, cx, L, ring, lane, false);
+  March<true>::init(sp, cx, L, wsm, lane, false);
   const int last = cx.a1e;
-  int u = cx.a0 - 1;
-  while (u <= last) {
-    if (march_step_is_lean(cx, u)) {
-      // two steps per trip: the register bank of every carried value is a compile-time constant
-      const int hi = cx.lean_hi;
-      for (;;) {
-        march_step<false, 0>(sp, cx, L, ring, u, lane);
-        if (u == hi) {
-          March<false>::swap_banks(L);  // an odd number of lean steps: the next (EDGE) step expects its row in bank 0
-          break;
-        }
-        march_step<false, 1>(sp, cx, L, ring, u + 1, lane);
-        if (u + 1 == hi) break;
-        u += 2;
-      }
-      u = hi + 1;
-    } else {
-      march_step<true, 0>(sp, cx, L, ring, u, lane);
-      March<true>::swap_banks(L);
-      u++;
-    }
+  for (int u = cx.a0 - 1; u <= last; u++) {
+    if (march_step_is_lean(cx, u)) march_step<false>(sp, cx, L, wsm, u, lane);  // uniform per warp
+    else march_step<true>(sp, cx, L, wsm, u, lane);
   }
 #ifdef RN_STREAM_TRACE
   if (lane == 0 && id < 8192) {
@@ -219,9 +201,19 @@ __global__ void __launch_bounds__(32 * WPB, MINB) k_march(const __grid_constant_
 
 cudaError_t launch_march(const StreamParams& st, dim3 grid_units, cudaStream_t stream)
 {
+  constexpr int kBytes = kMarchWPB * kWarpE4 * (int)sizeof(E4);
+  static std::atomic<bool> configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
+    e = cudaFuncSetAttribute(k_march<kMarchWPB, kMarchWarpsPerSM / kMarchWPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+    if (e != cudaSuccess) return e;
+    if (dev < 64) configured[dev].store(true, std::memory_order_release);
+  }
   const int nunits = (int)grid_units.x;
   const dim3 grid((unsigned)((nunits + kMarchWPB - 1) / kMarchWPB), 1, grid_units.z);
-  k_march<kMarchWPB, kMarchWarpsPerSM / kMarchWPB><<<grid, 32 * kMarchWPB, 0, stream>>>(st, nunits);
+  k_march<kMarchWPB, kMarchWarpsPerSM / kMarchWPB><<<grid, 32 * kMarchWPB, kBytes, stream>>>(st, nunits);
   return cudaGetLastError();
 }
 

@@ -4,10 +4,7 @@
 // Same march as rn_stream.cuh (a strip of cell columns walked row by row, nothing recomputed in the marching
 // direction, ordered shade gather), re-cut for the instruction-issue bound that kernel ran into:
 //   * ONE WARP owns a strip and nothing is shared between warps: no block barriers.  What a lane needs from its
-//     neighbours (one centre, two generateSquare losses, two generateDiamond losses per step) travels by warp
-//     shuffles; everything else a step hands to the next lives in registers.  Shared memory only holds the input
-//     lattice rows: every lane copies its own three lattice points of row u+2 with cp.async while step u runs (a private
-//     ring of four rows per warp: u-1 .. u+2), so the L2 latency of the input never reaches the issue stream.
+//     neighbours (one centre, two generateSquare losses, two generateDiamond losses per step) travels by warp shuffles.
 //   * a lane owns TWO adjacent cell columns, so its two square centres, its two loop-1 midpoints and its two loop-2
 //     midpoints are each evaluated as ONE packed-FP32 instruction stream (rn_math.cuh: F2, displace2), the values the two
 //     cells share are loaded once, and the per-step bookkeeping is paid once per eight output samples;
@@ -15,24 +12,29 @@
 //     32-byte sectors (st.global.v8.f32 -> STG.E.ENL2.256).  Rows whose first sample sits on an odd 16-byte slot (every
 //     other row of a (W+1)-pitched field) are shifted by one sample with four shuffles; the two samples at the warp's
 //     ends are stored as 16-byte halves.
+//   * registers hold a value only WITHIN a step.  What step u hands to step u+1 (centres, loop-1 mids, the loss terms) is
+//     parked in lane-private shared-memory slots (two banks, element e of lane l at [e][l]: every access is a
+//     conflict-free 128-bit one), and the input lattice arrives through a warp-private ring of four rows filled by
+//     cp.async one step ahead, so the L2 latency of the input never reaches the issue stream.  That keeps the kernel at
+//     128 registers -- 16 resident warps per SM, which is what the issue rate needs -- without spills.
 //
-// Lanes: lane l holds the lattice / cell columns k0 = L0 + 2l and k1 = k0 + 1 (L0 even) and reads column k1 + 1 as well.
-// Lanes 0 and 31 are halo: their samples are incomplete (they have no left / right neighbour) and are never stored, so a
-// warp finishes the 60 cell columns [L0 + 2, L0 + 62) = 120 output columns per row.
+// Lanes: lane l holds the lattice / cell columns k0 = L0 + 2l and k1 = k0 + 1 (L0 even) and reads column k1 + 1, its right
+// neighbour's k0, as well.  Lanes 0 and 31 are halo: their samples are incomplete (they have no left / right neighbour) and
+// are never stored, so a warp finishes the 60 cell columns [L0 + 2, L0 + 62) = 120 output columns per row.
 //
 // Step u (cell row u; vocabulary of rn_tile.cuh):
-//   P1   S(u): centres C(u, k0), C(u, k1) from lattice rows u, u+1        (averageSquare + generateSquare)
+//   P1   S(u): centres C(u, k0), C(u, k1) from lattice rows u, u+1        (averageSquare + generateSquare);
+//        lattice row u+2 is requested (cp.async) into the ring slot row u-2 occupied
 //   X1   losses TS(u, .) to both neighbours, C(u, k1) to the right neighbour
 //   P2   D(u): mids M1(u, k0), M1(u, k1) and M2(u-1, k0), M2(u-1, k1)       (averageDiamond + generateDiamond)
 //   X2   losses TD1(u, k1) to the right, TD2(u-1, k0) to the left neighbour
 //   P3   G(u-1): final shade of corners K(u-1, .) and centres C(u-1, .) (ordered gather), addVolcano, store of output
 //        rows 2(u-1) and 2(u-1)+1
-// Values of step u-1 that step u needs sit in the other of two register banks; the march is unrolled by two with the bank
-// as a template argument, so no value is ever moved.  Steps that touch the first / last lattice rows, strips on a
-// lattice column border and strips cut by the window run the EDGE instantiation (existence tests, border forms,
-// per-sample stores).
+// Steps that touch the first / last lattice rows, strips on a lattice column border and strips cut by the window run the
+// EDGE instantiation (existence tests, border forms, per-sample stores).
 //
-// Compiles as plain C++ for tests/host_replay (a warp = 32 MarchLane structs, a shuffle = a read of the neighbour's struct).
+// Compiles as plain C++ for tests/host_replay (a warp = 32 MarchLane structs + one block of "shared memory", a shuffle = a
+// read of the neighbour's struct).
 #pragma once
 #include "rn_stream.cuh"
 
@@ -40,19 +42,36 @@ namespace rn {
 
 constexpr int kMarchCols = 60;  // cell columns a warp finishes
 
+// Warp-private shared memory, in E4 (16-byte) units.
+//   ring    four input lattice rows (row r in slot r & 3): lane l's columns k0, k0+1 at [2l], [2l+1] -- so [2l+2] is its right
+//           neighbour's k0 --, lane 31's third column at [64]
+//   state   two banks (step parity) of the values a step hands to the next: element e of lane l at [e][l]
+//   const   per-lane constants: the squared column distances of the lane's four output columns from the volcano
+constexpr int kRingRowE4 = 66;
+constexpr int kRingE4 = 4 * kRingRowE4;
+enum { S_C0 = 0, S_C1, S_C2, S_M1A, S_M1B, S_TS, S_TD, S_TE, S_COUNT };  // C(u; k0-1, k0, k1), M1(u; k0, k1), TS(u; 4),
+                                                                          // {TD1(u; 3), sg(u, k0)}, {TD2(u-1; 3), sg(u, k1)}
+constexpr int kBankE4 = S_COUNT * 32;
+constexpr int kStateE4 = kRingE4;
+constexpr int kConstE4 = kStateE4 + 2 * kBankE4;
+constexpr int kWarpE4 = kConstE4 + 32;  // 808 E4 = 12.6 KB per warp
+RN_HD E4* ring_row(E4* wsm, int r) { return wsm + (r & 3) * kRingRowE4; }
+RN_HD E4* state_at(E4* wsm, int bank, int e, int lane) { return wsm + kStateE4 + bank * kBankE4 + e * 32 + lane; }
+
+// registers of a lane: what lives across steps, and what one phase of a step hands to the next
 struct MarchLane {
-  float sg[2][2];  // bank (t&1): shade of corner K(u, k0/k1) as generateSquare's scatter left it (written in P2; the position stays in the ring)
-  E4 cen[2][3];    // bank (t&1): C(u, k0-1), C(u, k0), C(u, k1)
-  E4 m1[2][2];     // bank (t&1): M1(u, k0/k1)
-  float ts[2][4];  // bank (t&1): TS(u; k0-1, k0, k1, k1+1)
-  float td1[2][3]; // bank (t&1): TD1(u; k0-1, k0, k1)
-  float td2[2][3]; // bank (t&1): TD2(u-1; k0, k1, k1+1)
   uint32_t sS, sD1, sD2;  // LCG states whose extraction is the draw of column k0's next S / loop-1 / loop-2 call
   const E4* src;   // lattice (row of the next cp.async, column k0)
   E4* dst;         // output (row 2(u-1), column 2*k0) of the step in progress, relative to the window
-  float fy2[4];    // squared column distance of the lane's four output columns from the volcano
   int ok;          // bit j: output column 2*k0 + j belongs to the strip and lies inside the stored window
-  E4 out[2][4];    // P3: the two finished output rows of the lane (transient)
+  // within a step
+  E4 cen[3];       // C(u; k0-1, k0, k1)
+  E4 m1[2];        // M1(u; k0, k1)
+  float ts[4];     // TS(u; k0-1, k0, k1, k1+1)
+  float td1[3];    // TD1(u; k0-1, k0, k1)
+  float td2[3];    // TD2(u-1; k0, k1, k1+1)
+  float sg[2];     // shade of corner K(u, k0/k1) as generateSquare's scatter left it
+  E4 out[2][4];    // the two finished output rows of the lane
 };
 
 struct MarchCtx {
@@ -66,13 +85,9 @@ struct MarchCtx {
   int lean_lo, lean_hi;  // steps that touch no lattice row border
   int col_lean;    // all 65 lattice columns of the warp exist and it owns 60 whole cell columns inside the window (sector stores):
                    // its interior steps run the lean instantiation
+  int ubase;       // bank of step u = (u - ubase) & 1
 };
 
-// The warp's ring of input lattice rows in shared memory: row r sits in slot r & 3, lane l's three points (columns k0, k0+1,
-// k0+2) at [slot][3*l + q] -- every lane reads only what it copied itself, so no synchronisation beyond cp.async.wait_group.
-constexpr int kRingRowE4 = 96;               // 32 lanes x 3 points
-constexpr int kRingE4 = 4 * kRingRowE4;      // per warp (6 KB)
-RN_HD E4* ring_row(E4* ring_lane, int r) { return ring_lane + (r & 3) * kRingRowE4; }
 RN_HD void ring_copy16(E4* dst_smem, const E4* src_global)
 {
 #if defined(__CUDA_ARCH__)
@@ -87,10 +102,12 @@ RN_HD void ring_commit()
   asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
 }
-RN_HD void ring_wait_all_but_1()  // everything but the most recent group has landed
+// everything but the most recent group of EVERY lane has landed and is visible to the whole warp
+RN_HD void ring_wait_all_but_1()
 {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.wait_group 1;" ::: "memory");
+  __syncwarp();
 #endif
 }
 
@@ -128,6 +145,7 @@ RN_HD MarchCtx march_ctx(const StreamParams& sp, int id, unsigned f)
   cx.col_lean = cx.L0 >= 0 && cx.L0 + 64 <= n && fast;
   cx.lean_lo = imax_(cx.a0 - 1, 1);
   cx.lean_hi = cx.a1e <= n - 1 ? cx.a1e : n - 2;
+  cx.ubase = cx.a0 - 1;
   return cx;
 }
 RN_HD bool march_step_is_lean(const MarchCtx& cx, int u) { return cx.col_lean && u >= cx.lean_lo && u <= cx.lean_hi; }
@@ -234,21 +252,25 @@ RN_HD F2 volcano_pair_general(F2 r2, float inv_w, float gain, float gain_w, floa
 
 template <bool EDGE>
 struct March {
-  // cp.async of lattice row r (the lane's columns k0 .. k0+2, from p = &gin[r][k0]) into the ring; always one commit group
-  static RN_HD void prefetch_row(const StreamParams& sp, const MarchCtx& cx, E4* ring, const E4* p, int r, int k0)
+  static RN_HD int bank_of(const MarchCtx& cx, int u) { return (u - cx.ubase) & 1; }
+
+  // cp.async of lattice row r into the ring (from p = &gin[r][k0]): the lane's own two columns, lane 31 its third as well;
+  // always exactly one commit group
+  static RN_HD void prefetch_row(const StreamParams& sp, const MarchCtx& cx, E4* wsm, const E4* p, int r, int lane)
   {
     if (r <= cx.a1e + 1 && r >= 0 && r <= sp.lev.n) {  // uniform: a later step reads the row, and it exists
-      E4* slot = ring_row(ring, r);
-#pragma unroll
-      for (int q = 0; q < 3; q++)
-        if (!EDGE || (k0 + q >= 0 && k0 + q <= sp.lev.n)) ring_copy16(slot + q, p + q);
+      E4* slot = ring_row(wsm, r) + 2 * lane;
+      const int k0 = cx.L0 + 2 * lane, n = sp.lev.n;
+      if (!EDGE || (k0 >= 0 && k0 <= n)) ring_copy16(slot, p);
+      if (!EDGE || (k0 + 1 >= 0 && k0 + 1 <= n)) ring_copy16(slot + 1, p + 1);
+      if (lane == 31 && (!EDGE || (k0 + 2 >= 0 && k0 + 2 <= n))) ring_copy16(slot + 2, p + 2);
     }
     ring_commit();
   }
 
   // ------------------------------------------------------------------ start-up ----
-  // ring: the lane's part of the warp's ring (ring_of_warp + 3 * lane)
-  static RN_HD void init(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* ring, int lane, bool poison)
+  // wsm: the warp's block of shared memory (kWarpE4 elements)
+  static RN_HD void init(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* wsm, int lane, bool poison)
   {
     const int u0 = cx.a0 - 1;
     const int k0 = cx.L0 + 2 * lane;
@@ -256,54 +278,56 @@ struct March {
     const float z = poison ? march_nan() : 0.0f;
     const E4 z4 = E4{z, z, z, z};
 #pragma unroll
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < 2; b++)
 #pragma unroll
-      for (int q = 0; q < 3; q++) { L.cen[b][q] = z4; L.td1[b][q] = z; L.td2[b][q] = z; }
+      for (int e = 0; e < S_COUNT; e++) *state_at(wsm, b, e, lane) = z4;
 #pragma unroll
-      for (int q = 0; q < 2; q++) { L.sg[b][q] = z; L.m1[b][q] = z4; }
+    for (int q = 0; q < 3; q++) { L.cen[q] = z4; L.td1[q] = z; L.td2[q] = z; }
 #pragma unroll
-      for (int q = 0; q < 4; q++) { L.ts[b][q] = z; L.out[b][q] = z4; }
-    }
+    for (int q = 0; q < 2; q++) { L.sg[q] = z; L.m1[q] = z4; }
+#pragma unroll
+    for (int q = 0; q < 4; q++) { L.ts[q] = z; L.out[0][q] = z4; L.out[1][q] = z4; }
     L.sS = lcg_skip(cx.seed, sp.lev.kS + (uint32_t)u0 * n + (uint32_t)k0);
     L.sD1 = lcg_skip(cx.seed, sp.lev.kD1 + (uint32_t)u0 * n + (uint32_t)k0);
     L.sD2 = lcg_skip(cx.seed, sp.lev.kD2 + (uint32_t)(u0 - 1) * (n + 1u) + (uint32_t)k0);
     const int Wout = 1 << sp.dout;
     L.ok = 0;
+    float fy2[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int gj = 2 * k0 + j;
       const int b = k0 + (j >> 1);  // owning cell column
       const float fy = (float)(gj - Wout / 2);
-      L.fy2[j] = fy * fy;
+      fy2[j] = fy * fy;
       const bool owned = (b >= cx.B0 && b < cx.B0 + cx.CW) || (gj == 2 * (cx.B0 + cx.CW) && cx.CWe != cx.CW);
       if (owned && (unsigned)(gj - sp.win_j0) < (unsigned)sp.win_nj) L.ok |= 1 << j;
     }
+    wsm[kConstE4 + lane] = E4{fy2[0], fy2[1], fy2[2], fy2[3]};
     // (both pointers may start outside their grids; they are only dereferenced where the row / column exists)
     L.src = cx.gin + ((ptrdiff_t)u0 * (ptrdiff_t)sp.gin_pitch + (ptrdiff_t)k0);
     L.dst = cx.gout + ((ptrdiff_t)(2 * (u0 - 1) - sp.win_i0) * (ptrdiff_t)sp.gout_pitch + (ptrdiff_t)(2 * k0 - sp.win_j0));  // the first step finishes cell row u0 - 1
     for (int b = 0; b < 2; b++) {  // rows u0, u0+1: one commit group each; step u requests row u+2
-      prefetch_row(sp, cx, ring, L.src, u0 + b, k0);
+      prefetch_row(sp, cx, wsm, L.src, u0 + b, lane);
       L.src += sp.gin_pitch;
     }
   }
 
   // ------------------------------------------------------------------ P1: S(u) ----
-  template <int PH>
-  static RN_HD void p1(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* ring, int u, int lane)
+  static RN_HD void p1(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* wsm, int u, int lane)
   {
-    // lattice row u+2 sets out now (it lands in the slot row u-2 occupied; the ring keeps rows u-1 .. u+2); rows u and u+1
-    // have landed once at most this one group is still in flight
-    prefetch_row(sp, cx, ring, L.src, u + 2, cx.L0 + 2 * lane);
+    // lattice row u+2 sets out now (into the slot row u-2 occupied; the ring keeps rows u-1 .. u+2); rows u and u+1 have
+    // landed once at most this one group is still in flight
+    prefetch_row(sp, cx, wsm, L.src, u + 2, lane);
     L.src += sp.gin_pitch;
     ring_wait_all_but_1();
-    const E4* ka = ring_row(ring, u);
-    const E4* kb = ring_row(ring, u + 1);
+    const E4* ka = ring_row(wsm, u) + 2 * lane;
+    const E4* kb = ring_row(wsm, u + 1) + 2 * lane;
     const uint32_t sB = kLcgA * L.sS + kLcgC;
     const uint32_t draw_a = lcg_draw_from_state(L.sS), draw_b = lcg_draw_from_state(sB);
     L.sS = jump_apply(sp.jn, L.sS);
     if (!EDGE) {
-      centre_pair(sp.law, ka[0], kb[0], ka[1], kb[1], ka[1], kb[1], ka[2], kb[2], sp.lev.blahS, draw_a, draw_b, &L.cen[PH][1], &L.cen[PH][2],
-                  &L.ts[PH][1], &L.ts[PH][2]);
+      const E4 a01 = ka[1], a11 = kb[1];  // shared by the lane's two cells
+      centre_pair(sp.law, ka[0], kb[0], a01, a11, a01, a11, ka[2], kb[2], sp.lev.blahS, draw_a, draw_b, &L.cen[1], &L.cen[2], &L.ts[1], &L.ts[2]);
     } else {
       const int n = sp.lev.n;
       const int k0 = cx.L0 + 2 * lane;
@@ -315,40 +339,46 @@ struct March {
           const E4 k00 = ka[q], k01 = ka[q + 1], k10 = kb[q], k11 = kb[q + 1];
           const E4 a4 = avg4_packed(k00, k10, k01, k11);
           const Displaced dp = displace<true>(sp.law, pos4(a4), vsub(pos4(k11), pos4(k00)), vsub(pos4(k10), pos4(k01)), sp.lev.blahS, q ? draw_b : draw_a);
-          L.cen[PH][1 + q] = e4_of(dp.pos, a4.w + shade_gain(sp.law, dp.offset));
+          L.cen[1 + q] = e4_of(dp.pos, a4.w + shade_gain(sp.law, dp.offset));
           loss = shade_loss(sp.law, dp.offset);
         }
-        L.ts[PH][1 + q] = loss;
+        L.ts[1 + q] = loss;
       }
     }
   }
-  template <int PH>
-  static RN_HD void x1(MarchLane& L, const MarchLane* left, const MarchLane* right)
+  // X1 + the step's centres and generateSquare losses go to the bank of step u
+  static RN_HD void x1(const MarchCtx& cx, MarchLane& L, E4* wsm, int u, int lane, const MarchLane* left, const MarchLane* right)
   {
-    L.ts[PH][0] = from_left(L.ts[PH][2], left ? &left->ts[PH][2] : nullptr);
-    L.ts[PH][3] = from_right(L.ts[PH][1], right ? &right->ts[PH][1] : nullptr);
-    L.cen[PH][0] = from_left4(L.cen[PH][2], left ? &left->cen[PH][2] : nullptr);
+    L.ts[0] = from_left(L.ts[2], left ? &left->ts[2] : nullptr);
+    L.ts[3] = from_right(L.ts[1], right ? &right->ts[1] : nullptr);
+    L.cen[0] = from_left4(L.cen[2], left ? &left->cen[2] : nullptr);
+    const int b = bank_of(cx, u);
+    *state_at(wsm, b, S_C0, lane) = L.cen[0];
+    *state_at(wsm, b, S_C1, lane) = L.cen[1];
+    *state_at(wsm, b, S_C2, lane) = L.cen[2];
+    *state_at(wsm, b, S_TS, lane) = E4{L.ts[0], L.ts[1], L.ts[2], L.ts[3]};
   }
 
   // ------------------------------------------------------------------ P2: D(u) ----
-  template <int PH>
-  static RN_HD void p2(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, const E4* ring, int u, int lane)
+  static RN_HD void p2(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* wsm, int u, int lane)
   {
-    const E4* ka = ring_row(const_cast<E4*>(ring), u);
-    const float* tsm = L.ts[PH ^ 1];
-    const float* tsc = L.ts[PH];
-    const E4* cenm = L.cen[PH ^ 1];
-    const E4* cenc = L.cen[PH];
-    const E4* km = ring_row(const_cast<E4*>(ring), u - 1);
-    E4 kcm[2] = {km[0], km[1]};  // K'(u-1, k0/k1): position from the ring, shade as carried
-    kcm[0].w = L.sg[PH ^ 1][0];
-    kcm[1].w = L.sg[PH ^ 1][1];
+    const int pb = bank_of(cx, u) ^ 1;  // what step u-1 left
+    const E4* ka = ring_row(wsm, u) + 2 * lane;
+    const E4* km = ring_row(wsm, u - 1) + 2 * lane;
+    const E4 tsm = *state_at(wsm, pb, S_TS, lane);
+    const E4 cenm[3] = {*state_at(wsm, pb, S_C0, lane), *state_at(wsm, pb, S_C1, lane), *state_at(wsm, pb, S_C2, lane)};
+    const float* tsc = L.ts;
+    const E4* cenc = L.cen;
     // corner shades as generateSquare left them (Terrain.cpp:252-255): minus the scatter of the 4 surrounding centres,
     // in call order (u-1, k-1), (u-1, k), (u, k-1), (u, k)
     E4 K0 = ka[0], K1 = ka[1], K2 = ka[2];
-    K0.w = (((K0.w - tsm[0]) - tsm[1]) - tsc[0]) - tsc[1];
-    K1.w = (((K1.w - tsm[1]) - tsm[2]) - tsc[1]) - tsc[2];
-    K2.w = (((K2.w - tsm[2]) - tsm[3]) - tsc[2]) - tsc[3];
+    K0.w = (((K0.w - tsm.x) - tsm.y) - tsc[0]) - tsc[1];
+    K1.w = (((K1.w - tsm.y) - tsm.z) - tsc[1]) - tsc[2];
+    K2.w = (((K2.w - tsm.z) - tsm.w) - tsc[2]) - tsc[3];
+    // K'(u-1, k0/k1): position from the ring, shade as step u-1 computed it
+    E4 kcm[2] = {km[0], km[1]};
+    kcm[0].w = state_at(wsm, pb, S_TD, lane)->w;
+    kcm[1].w = state_at(wsm, pb, S_TE, lane)->w;
     const uint32_t s1B = kLcgA * L.sD1 + kLcgC, s2B = kLcgA * L.sD2 + kLcgC;
     const uint32_t d1a = lcg_draw_from_state(L.sD1), d1b = lcg_draw_from_state(s1B);
     const uint32_t d2a = lcg_draw_from_state(L.sD2), d2b = lcg_draw_from_state(s2B);
@@ -356,11 +386,10 @@ struct March {
     L.sD2 = jump_apply(sp.jn1, L.sD2);
     if (!EDGE) {
       // loop 1: M1(u, k) at output (2u, 2k+1): x neighbours C(u-1, k), C(u, k); y neighbours K'(u, k), K'(u, k+1)
-      mid_interior2(sp.law, cenm[1], cenc[1], K0, K1, cenm[2], cenc[2], K1, K2, sp.lev.blahD, d1a, d1b, &L.m1[PH][0], &L.m1[PH][1], &L.td1[PH][1],
-                    &L.td1[PH][2]);
+      mid_interior2(sp.law, cenm[1], cenc[1], K0, K1, cenm[2], cenc[2], K1, K2, sp.lev.blahD, d1a, d1b, &L.m1[0], &L.m1[1], &L.td1[1], &L.td1[2]);
       // loop 2: M2(u-1, k) at output (2u-1, 2k): x neighbours K'(u-1, k), K'(u, k); y neighbours C(u-1, k-1), C(u-1, k)
-      mid_interior2(sp.law, kcm[0], K0, cenm[0], cenm[1], kcm[1], K1, cenm[1], cenm[2], sp.lev.blahD, d2a, d2b, &L.out[1][0], &L.out[1][2],
-                    &L.td2[PH][0], &L.td2[PH][1]);
+      mid_interior2(sp.law, kcm[0], K0, cenm[0], cenm[1], kcm[1], K1, cenm[1], cenm[2], sp.lev.blahD, d2a, d2b, &L.out[1][0], &L.out[1][2], &L.td2[0],
+                    &L.td2[1]);
     } else {
       const int n = sp.lev.n;
       const int k0 = cx.L0 + 2 * lane;
@@ -374,61 +403,65 @@ struct March {
         if (v1) {
           if (u == 0 || u == n) {
             const E4 dummy = k00;
-            L.m1[PH][q] = mid_border(sp.law, u == 0 ? dummy : cenm[1 + q], u == n ? dummy : cenc[1 + q], k00, k01, u == 0, u == n, false, false,
-                                     sp.lev.blahDh, q ? d1b : d1a, &loss1);
+            L.m1[q] = mid_border(sp.law, u == 0 ? dummy : cenm[1 + q], u == n ? dummy : cenc[1 + q], k00, k01, u == 0, u == n, false, false, sp.lev.blahDh,
+                                 q ? d1b : d1a, &loss1);
           } else {
-            L.m1[PH][q] = mid_interior(sp.law, cenm[1 + q], cenc[1 + q], k00, k01, sp.lev.blahD, q ? d1b : d1a, &loss1);
+            L.m1[q] = mid_interior(sp.law, cenm[1 + q], cenc[1 + q], k00, k01, sp.lev.blahD, q ? d1b : d1a, &loss1);
           }
         }
         if (v2) L.out[1][2 * q] = mid_select_y(sp.law, kcm[q], k00, cenm[q], cenm[1 + q], bg == 0, bg == n, sp.lev.blahD, q ? d2b : d2a, &loss2);
-        L.td1[PH][1 + q] = loss1;
-        L.td2[PH][q] = loss2;
+        L.td1[1 + q] = loss1;
+        L.td2[q] = loss2;
       }
     }
-    L.sg[PH][0] = K0.w;
-    L.sg[PH][1] = K1.w;
+    L.sg[0] = K0.w;
+    L.sg[1] = K1.w;
   }
-  template <int PH>
-  static RN_HD void x2(MarchLane& L, const MarchLane* left, const MarchLane* right)
+  // X2 + the step's loop-1 mids, generateDiamond losses and corner shades go to the bank of step u
+  static RN_HD void x2(const MarchCtx& cx, MarchLane& L, E4* wsm, int u, int lane, const MarchLane* left, const MarchLane* right)
   {
-    L.td1[PH][0] = from_left(L.td1[PH][2], left ? &left->td1[PH][2] : nullptr);
-    L.td2[PH][2] = from_right(L.td2[PH][0], right ? &right->td2[PH][0] : nullptr);
+    L.td1[0] = from_left(L.td1[2], left ? &left->td1[2] : nullptr);
+    L.td2[2] = from_right(L.td2[0], right ? &right->td2[0] : nullptr);
+    const int b = bank_of(cx, u);
+    *state_at(wsm, b, S_M1A, lane) = L.m1[0];
+    *state_at(wsm, b, S_M1B, lane) = L.m1[1];
+    *state_at(wsm, b, S_TD, lane) = E4{L.td1[0], L.td1[1], L.td1[2], L.sg[0]};
+    *state_at(wsm, b, S_TE, lane) = E4{L.td2[0], L.td2[1], L.td2[2], L.sg[1]};
   }
 
   // ------------------------------------------------------------------ P3: G(u-1), addVolcano ----
-  template <int PH>
-  static RN_HD void p3(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, const E4* ring, int u)
+  static RN_HD void p3(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* wsm, int u, int lane)
   {
-    const float* tdm = L.td1[PH ^ 1];
-    const float* tdc = L.td1[PH];
-    const float* t2mm = L.td2[PH ^ 1];
-    const float* t2 = L.td2[PH];
+    const int pb = bank_of(cx, u) ^ 1;
+    const E4 tdm = *state_at(wsm, pb, S_TD, lane);  // TD1(u-1; k0-1, k0, k1), sg(u-1, k0)
+    const E4 tem = *state_at(wsm, pb, S_TE, lane);  // TD2(u-2; k0, k1, .), sg(u-1, k1)
+    const float* tdc = L.td1;
+    const float* t2 = L.td2;
     // corner K(u-1, k): generateSquare's scatter (carried), then loop 1 (same row: k-1, k), loop 2 (same column: u-2, u-1)
-    const E4* km = ring_row(const_cast<E4*>(ring), u - 1);
+    const E4* km = ring_row(wsm, u - 1) + 2 * lane;
     E4 c0 = km[0], c1 = km[1];
-    c0.w = L.sg[PH ^ 1][0];
-    c1.w = L.sg[PH ^ 1][1];
-    c0.w = (((c0.w - tdm[0]) - tdm[1]) - t2mm[0]) - t2[0];
-    c1.w = (((c1.w - tdm[1]) - tdm[2]) - t2mm[1]) - t2[1];
+    c0.w = (((tdm.w - tdm.x) - tdm.y) - tem.x) - t2[0];
+    c1.w = (((tem.w - tdm.y) - tdm.z) - tem.y) - t2[1];
     // centre C(u-1, k): loop-1 mids above and below, loop-2 mids left and right
-    E4 e0 = L.cen[PH ^ 1][1], e1 = L.cen[PH ^ 1][2];
-    e0.w = (((e0.w - tdm[1]) - tdc[1]) - t2[0]) - t2[1];
-    e1.w = (((e1.w - tdm[2]) - tdc[2]) - t2[1]) - t2[2];
+    E4 e0 = *state_at(wsm, pb, S_C1, lane), e1 = *state_at(wsm, pb, S_C2, lane);
+    e0.w = (((e0.w - tdm.y) - tdc[1]) - t2[0]) - t2[1];
+    e1.w = (((e1.w - tdm.z) - tdc[2]) - t2[1]) - t2[2];
     L.out[0][0] = c0;
-    L.out[0][1] = L.m1[PH ^ 1][0];
+    L.out[0][1] = *state_at(wsm, pb, S_M1A, lane);
     L.out[0][2] = c1;
-    L.out[0][3] = L.m1[PH ^ 1][1];
+    L.out[0][3] = *state_at(wsm, pb, S_M1B, lane);
     L.out[1][1] = e0;
     L.out[1][3] = e1;
     if (sp.volcano) {  // uniform
       const int Wout = 1 << sp.dout;
       const float gain_w = sp.volcano_gain * (float)Wout;
+      const E4 fy2 = wsm[kConstE4 + lane];
 #pragma unroll
       for (int r = 0; r < 2; r++) {
         const float fx = (float)(2 * (u - 1) + r - Wout / 2);
         const float fx2 = fx * fx;
         if (!EDGE) {  // two columns at once (packed pair); the few warps that touch the crater evaluate its branch as a select
-          const F2 r01 = f2add(f2s(fx2), f2(L.fy2[0], L.fy2[1])), r23 = f2add(f2s(fx2), f2(L.fy2[2], L.fy2[3]));
+          const F2 r01 = f2add(f2s(fx2), f2(fy2.x, fy2.y)), r23 = f2add(f2s(fx2), f2(fy2.z, fy2.w));
           F2 h01, h23;
           if (cx.far) {  // uniform
             h01 = f2mul(rcp_rn_normal2(sqrt_rn_normal2(r01)), f2s(gain_w));
@@ -444,25 +477,13 @@ struct March {
           L.out[r][3].y = L.out[r][3].y + f2hi(h23);
         } else {
           const float inv_w = 1.0f / (float)Wout;
-#pragma unroll
-          for (int j = 0; j < 4; j++) L.out[r][j].y = L.out[r][j].y + volcano_height_r2<false>(fx2 + L.fy2[j], inv_w, sp.volcano_gain, gain_w);
+          L.out[r][0].y = L.out[r][0].y + volcano_height_r2<false>(fx2 + fy2.x, inv_w, sp.volcano_gain, gain_w);
+          L.out[r][1].y = L.out[r][1].y + volcano_height_r2<false>(fx2 + fy2.y, inv_w, sp.volcano_gain, gain_w);
+          L.out[r][2].y = L.out[r][2].y + volcano_height_r2<false>(fx2 + fy2.z, inv_w, sp.volcano_gain, gain_w);
+          L.out[r][3].y = L.out[r][3].y + volcano_height_r2<false>(fx2 + fy2.w, inv_w, sp.volcano_gain, gain_w);
         }
       }
     }
-  }
-
-  static RN_HD void swap_banks(MarchLane& L)
-  {
-#define RN_SWAP_(T, a, b) { const T t__ = a; a = b; b = t__; }
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-      RN_SWAP_(E4, L.cen[0][q], L.cen[1][q]) RN_SWAP_(float, L.td1[0][q], L.td1[1][q]) RN_SWAP_(float, L.td2[0][q], L.td2[1][q])
-    }
-#pragma unroll
-    for (int q = 0; q < 2; q++) { RN_SWAP_(float, L.sg[0][q], L.sg[1][q]) RN_SWAP_(E4, L.m1[0][q], L.m1[1][q]) }
-#pragma unroll
-    for (int q = 0; q < 4; q++) RN_SWAP_(float, L.ts[0][q], L.ts[1][q])
-#undef RN_SWAP_
   }
 
   // ------------------------------------------------------------------ store of cell row a = u-1 ----

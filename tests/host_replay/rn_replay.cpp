@@ -12,9 +12,11 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <vector>
 #include "../../include/rednoise.h"
 #include "../../rednoise_b200/csrc/rn_plan.h"
+#include "../../rednoise_b200/csrc/rn_volume.cuh"
 
 using namespace rn;
 
@@ -171,18 +173,19 @@ int run_stream_t(const StageLaunch& sl, int nfields, const uint32_t* seeds, int 
 }
 
 // The warp-synchronous march (rn_march.cuh): the 32 lanes of a warp are replayed phase by phase in lockstep; a shuffle is a read
-// of the neighbouring lane's struct after every lane has finished the phase before it.  With `poison` all lane state starts as
-// NaN and the values the device shuffles in from outside the warp (lane 0's left, lane 31's right) are NaN too.
-template <bool EDGE, int PH>
-void march_step_host(const StreamParams& sp, const MarchCtx& cx, std::vector<MarchLane>& L, E4* ringw, int u)
+// of the neighbouring lane's struct after every lane has finished the phase before it.  With `poison` the lane state and the
+// warp's block of "shared memory" start as NaN and the values the device shuffles in from outside the warp (lane 0's left,
+// lane 31's right) are NaN too; guard zones around the block are verified untouched.
+template <bool EDGE>
+void march_step_host(const StreamParams& sp, const MarchCtx& cx, std::vector<MarchLane>& L, E4* wsm, int u)
 {
   using M = March<EDGE>;
 #define RN_LANES(call) for (int q = 0; q < 32; q++) { const int l = g_reverse ? 31 - q : q; call; }
-  RN_LANES(M::template p1<PH>(sp, cx, L[l], ringw + 3 * l, u, l))
-  RN_LANES(M::template x1<PH>(L[l], l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
-  RN_LANES(M::template p2<PH>(sp, cx, L[l], ringw + 3 * l, u, l))
-  RN_LANES(M::template x2<PH>(L[l], l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
-  RN_LANES(M::template p3<PH>(sp, cx, L[l], ringw + 3 * l, u))
+  RN_LANES(M::p1(sp, cx, L[l], wsm, u, l))
+  RN_LANES(M::x1(cx, L[l], wsm, u, l, l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
+  RN_LANES(M::p2(sp, cx, L[l], wsm, u, l))
+  RN_LANES(M::x2(cx, L[l], wsm, u, l, l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
+  RN_LANES(M::p3(sp, cx, L[l], wsm, u, l))
   RN_LANES(M::store(sp, cx, L[l], u, l, l > 0 ? &L[l - 1] : nullptr))
 #undef RN_LANES
 }
@@ -190,8 +193,10 @@ void march_step_host(const StreamParams& sp, const MarchCtx& cx, std::vector<Mar
 int run_march(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
 {
   std::vector<MarchLane> L(32);
-  std::vector<E4> ringv(kRingE4 + 1);
-  E4* ringw = ringv.data();
+  constexpr int G4 = 64;  // guard, in E4
+  std::vector<E4> buf(kWarpE4 + 2 * G4 + 1);
+  E4* wsm = buf.data() + G4;
+  int bad = 0;
   for (int f = 0; f < nfields; f++)
     for (unsigned id = 0; id < sl.gx; id++) {
       StreamParams sp = sl.st;
@@ -199,33 +204,21 @@ int run_march(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poi
       MarchCtx cx = march_ctx(sp, (int)id, (unsigned)f);
       if (force_edge) cx.col_lean = 0;
       memset(L.data(), poison ? 0xff : 0, sizeof(MarchLane) * L.size());
-      memset(ringw, poison ? 0xff : 0, sizeof(E4) * kRingE4);
-      for (int l = 0; l < 32; l++) March<true>::init(sp, cx, L[l], ringw + 3 * l, l, poison != 0);
-      // the kernel's loop (rn_fused.cu: k_march), including its bank bookkeeping
-      const int last = cx.a1e;
-      int u = cx.a0 - 1;
-      while (u <= last) {
-        if (march_step_is_lean(cx, u)) {
-          const int hi = cx.lean_hi;
-          for (;;) {
-            march_step_host<false, 0>(sp, cx, L, ringw, u);
-            if (u == hi) {
-              for (int l = 0; l < 32; l++) March<false>::swap_banks(L[l]);
-              break;
-            }
-            march_step_host<false, 1>(sp, cx, L, ringw, u + 1);
-            if (u + 1 == hi) break;
-            u += 2;
-          }
-          u = hi + 1;
-        } else {
-          march_step_host<true, 0>(sp, cx, L, ringw, u);
-          for (int l = 0; l < 32; l++) March<true>::swap_banks(L[l]);
-          u++;
-        }
+      memset(buf.data(), poison ? 0xff : 0, sizeof(E4) * buf.size());
+      for (int l = 0; l < 32; l++) March<true>::init(sp, cx, L[l], wsm, l, poison != 0);
+      // the kernel's loop (rn_fused.cu: k_march)
+      for (int u = cx.a0 - 1; u <= cx.a1e; u++) {
+        if (march_step_is_lean(cx, u)) march_step_host<false>(sp, cx, L, wsm, u);
+        else march_step_host<true>(sp, cx, L, wsm, u);
+      }
+      if (poison) {
+        const unsigned char* g0 = reinterpret_cast<const unsigned char*>(buf.data());
+        const unsigned char* g1 = reinterpret_cast<const unsigned char*>(wsm + kWarpE4);
+        for (size_t i = 0; i < sizeof(E4) * G4; i++)
+          if (g0[i] != 0xff || g1[i] != 0xff) bad = 1;  // a write outside the warp's shared memory
       }
     }
-  return 0;
+  return bad;
 }
 
 int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int poison, int force_edge)
@@ -235,6 +228,28 @@ int run_stream(const StageLaunch& sl, int nfields, const uint32_t* seeds, int po
 }
 
 }  // namespace
+
+// The 3D volume path (rn_volume.cuh): the kernels' own tile routine, one "thread" per tile, over the same level chain and plane
+// ranges as volume_generate (rn_volume.cu).  poison: NaN-fill the level grids and every tile's shared-memory image.
+template <int TI, int TJ, int TK>
+void vol_level_host(const VolLevel& L, int tiles_i, int poison)
+{
+  using G = VolGeo<TI, TJ, TK>;
+  std::vector<float> sm(G::WORDS);
+  uint32_t nanbits = 0x7fc0dead;
+  float nanv;
+  memcpy(&nanv, &nanbits, 4);
+  const int tj = (L.n + TJ - 1) / TJ, tk = (L.n + TK - 1) / TK;
+  for (int z = 0; z < tiles_i; z++)
+    for (int y = 0; y < tj; y++)
+      for (int x = 0; x < tk; x++) {
+        for (auto& w : sm) w = poison ? nanv : 0.0f;
+        const int A0 = (L.tile_i0 + z) * TI, B0 = y * TJ, C0 = x * TK;
+        const bool edge = A0 < 1 || B0 < 1 || C0 < 1 || A0 + TI >= L.n || B0 + TJ >= L.n || C0 + TK >= L.n;
+        if (edge) vol_tile<TI, TJ, TK, 1, true>(L, sm.data(), A0, B0, C0);
+        else vol_tile<TI, TJ, TK, 1, false>(L, sm.data(), A0, B0, C0);
+      }
+}
 
 extern "C" {
 
@@ -257,6 +272,36 @@ int replay_plan(int depth, int* din, int* L)
     L[k] = plan[k].L;
   }
   return ns;
+}
+
+int replay_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, float* slab, int poison)
+{
+  if (!slab || depth < 2 || depth > 11) return RN_ERR_BAD_PARAM;
+  const int side = (1 << depth) + 1;
+  if (i0 < 0 || ni <= 0 || i0 > side - ni) return RN_ERR_BAD_PARAM;
+  int lo[32], hi[32];
+  volume_ranges(depth, i0, ni, lo, hi);
+  std::vector<std::vector<float>> grids(depth + 1);
+  float* grid[32] = {};
+  for (int l = 1; l < depth; l++) {
+    const size_t m = ((size_t)1 << l) + 1;
+    grids[l].assign((size_t)(hi[l] - lo[l] + 1) * m * m, poison ? NAN : 0.0f);
+    grid[l] = grids[l].data();
+  }
+  grid[depth] = slab;
+  for (size_t q = 0; q < grids[1].size(); q++) grids[1][q] = 0.0f;  // the 27 undisplaced points
+  for (int l = 1; l < depth; l++) {
+    const int n = 1 << l;
+    int tiles_i = 0;
+    const VolLevel L = vol_level_make(depth, l, lo, hi, grid[l], grid[l + 1], seed, amplitude, &tiles_i);
+    switch (n) {
+      case 2: vol_level_host<2, 2, 2>(L, tiles_i, poison); break;
+      case 4: vol_level_host<4, 4, 4>(L, tiles_i, poison); break;
+      case 8: vol_level_host<8, 8, 8>(L, tiles_i, poison); break;
+      default: vol_level_host<kVolTI, kVolTJ, kVolTK>(L, tiles_i, poison); break;
+    }
+  }
+  return 0;
 }
 
 // kinds[k] of the launches that synthesize a whole depth-`depth` field (0 tile stage, 1 block streaming, 2 warp march).

@@ -25,7 +25,7 @@ class Win(C.Structure):
 
 @pytest.fixture(scope="module")
 def replay():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rn_tile.cuh", "rn_stream.cuh", "rn_march.cuh", "rn_plan.h", "rn_math.cuh")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("rn_tile.cuh", "rn_stream.cuh", "rn_march.cuh", "rn_plan.h", "rn_math.cuh", "rn_volume.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", SO, SRC], check=True)
     L = C.CDLL(SO)

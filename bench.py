@@ -523,6 +523,16 @@ def run_ours(args):
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # the same call with a PAGEABLE destination (what `new TerrainElement[]`, Terrain.cpp:45-49, gives an unmodified caller)
+    e2e_pageable_s = None
+    if args.workload == "field" and ni:
+        pageable = torch.empty((ni, nj, 4), dtype=torch.float32)
+        ctx.terrain2d_ptr(p, pageable.data_ptr(), window=win, dst_is_device=False)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            ctx.terrain2d_ptr(p, pageable.data_ptr(), window=win, dst_is_device=False)
+        e2e_pageable_s = (time.perf_counter() - t0) / 2
+        del pageable
     strong = None
     if args.workload == "field" and not args.no_strong:
         strong = strong_scaling_records(args, ctx, capi, sharding, torch, dist, rank, world, stream, barrier)
@@ -562,7 +572,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": 48 + (4 * len(seeds[:32]) if args.workload == "batch" else 0),
                     "d2h_bytes_per_step": e2e_samples * (4 if args.workload == "volume" else ELEM_BYTES), "ms_per_step": e2e_s * 1e3,
                     "note": "rn_terrain2d()/rn_terrain2d_batch() with a pinned HOST destination: synthesis + D2H of the samples + host read; "
-                            "the only inputs are the 48-byte rn_params (and the seeds of a batch)"},
+                            "the only inputs are the 48-byte rn_params (and the seeds of a batch)",
+                    "pageable_destination": None if e2e_pageable_s is None else
+                    {"value_rank0": my_samples / e2e_pageable_s / 1e9, "ms_per_step": e2e_pageable_s * 1e3,
+                     "note": "same call, destination from plain malloc (rank 0's own figure)"}},
             "gpu_launches": int(launches), "clocks": clocks, "algorithm": args.algo,
             "per_step_ms": {"min": min(per_step), "median": statistics.median(per_step), "max": max(per_step)},
         }

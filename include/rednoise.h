@@ -208,6 +208,21 @@ uint64_t rn_rock_draw_count(int depth);
 int rn_rock(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, rn_cell* cells, int dst_is_device, void* stream,
             uint32_t* lcg_state_after);
 
+/* The app's rock loop in one call (Core.cpp:69-79): `nrocks` rocks continue ONE rand() stream that starts in state `lcg_state`.
+ * With depths == NULL the loop is the reference's: before each rock one rand() call gives
+ * exponent = random(-5.0f, 0.0f) (basics.h:20-23) and detail = (int)(exponent + 7) (Core.cpp:72-75), then Rock(detail, amplitude, .)
+ * consumes its calls; with depths != NULL rock i has depth depths[i] and no call is made in between.  Rocks of depth <= 7 (all of the
+ * app's) are generated by ONE kernel launch for the whole batch (a CTA per face, the face in shared memory through all levels);
+ * deeper ones and the rare value-dependent inputs (see rn_rock) go through rn_rock's path one by one.  Blocking.
+ *   faces / cells   nrocks pointers (device or host memory by dst_is_device), each sized like rn_rock's; either array may be NULL
+ *   depths_out, exponents_out, states_out   optional, nrocks entries: detail, exponent (rockRadius = 10 * powf(2, exponent),
+ *                   Core.cpp:73-74) and the generator state at the entry of every rock
+ *   lcg_state_after the state after the last rock */
+#define RN_ROCK_BATCH_MAX 4096
+int rn_rock_batch(rn_context* ctx, uint32_t lcg_state, int nrocks, const int32_t* depths, float amplitude, rn_rock_element* const* faces,
+                  rn_cell* const* cells, int dst_is_device, void* stream, int32_t* depths_out, float* exponents_out, uint32_t* states_out,
+                  uint32_t* lcg_state_after);
+
 /* ---- Cloud generator --------------------------------------------
  * Cloud::Cloud (renderEngine/source/Cloud.cpp:14-105; the app never instantiates one, Core.cpp:80-82): the two-face
  * variant of Rock.  Same calling convention as rn_rock with 2 faces instead of 6: faces[(f*(W+1) + x)*(W+1) + y] is what

@@ -1,4 +1,4 @@
-/* oracle/ref_shim.h -- TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+/* oracle/ref_shim.h -- TEST INFRASTRUCTURE ONLY (see oracle/Makefile and DESIGN.md section 2).
  *
  * Force-included (g++ -include) in front of every UNMODIFIED reference
  * translation unit so that the Win32/MSVC-2008 sources under

@@ -23,7 +23,7 @@ SYMBOLS = [
     "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
     "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_set_pipelining", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device", "rn_selftest_math",
     "rn_terrain2d_cell_count", "rn_terrain2d_cell_level_offset", "rn_terrain2d_cells", "rn_volume3d", "rn_volume3d_slab_elems",
-    "rn_rock_draw_count", "rn_rock", "rn_cloud_draw_count", "rn_cloud",
+    "rn_rock_draw_count", "rn_rock", "rn_rock_batch", "rn_cloud_draw_count", "rn_cloud",
     "rn_device_count", "rn_device_alloc", "rn_device_free", "rn_host_alloc", "rn_host_free", "rn_copy_to_host",
     "rn_create_multi", "rn_destroy_multi", "rn_multi_size", "rn_multi_context", "rn_slab_rows", "rn_slab_window",
     "rn_terrain2d_sharded", "rn_terrain2d_batch_sharded", "rn_gather",
@@ -118,6 +118,9 @@ def lib() -> C.CDLL:
     L.rn_rock_draw_count.argtypes = [i32]
     L.rn_rock.restype = i32
     L.rn_rock.argtypes = [vp, C.POINTER(RockParams), vp, vp, i32, vp, C.POINTER(C.c_uint32)]
+    L.rn_rock_batch.restype = i32
+    L.rn_rock_batch.argtypes = [vp, u32, i32, C.POINTER(C.c_int32), C.c_float, C.POINTER(vp), C.POINTER(vp), i32, vp, C.POINTER(C.c_int32),
+                                C.POINTER(C.c_float), C.POINTER(u32), C.POINTER(u32)]
     L.rn_cloud_draw_count.restype = C.c_uint64
     L.rn_cloud_draw_count.argtypes = [i32]
     L.rn_cloud.restype = i32
@@ -286,6 +289,33 @@ class Context:
         cells = np.zeros((nf, int(lib().rn_terrain2d_cell_count(depth))), CELL_DTYPE) if want_cells else None
         after = self.rock_ptr(state, depth, amplitude, faces.ctypes.data, cells.ctypes.data if want_cells else 0, dst_is_device=False, cloud=cloud)
         return faces, cells, after
+
+    def rock_batch_host(self, state: int, nrocks: int, depths=None, amplitude: float = 0.3):
+        """rn_rock_batch with host destinations: ([faces_i], [cells_i], depths, exponents, states_at_entry, state_after)."""
+        nd = (C.c_int32 * nrocks)()
+        ex = (C.c_float * nrocks)()
+        st = (C.c_uint32 * nrocks)()
+        after = C.c_uint32(0)
+        if depths is None:
+            # depths are decided by the stream: ask for them first (no destinations needed for the dry walk: use depth 12 sized? no --
+            # the walk is host-only, so run it through the library's own helper by generating cells only on a second call)
+            s = state & 0xFFFFFFFF
+            dl = []
+            for _ in range(nrocks):
+                s = (s * 214013 + 2531011) & 0xFFFFFFFF
+                r = (s >> 16) & 0x7FFF
+                e = np.float32(-5.0) + np.float32(5.0) * (np.float32(r) / np.float32(32767.0))
+                dl.append(int(np.float32(e + np.float32(7.0))))
+                s = int(lib().rn_lcg_state_after(s, int(lib().rn_rock_draw_count(dl[-1]))))
+        else:
+            dl = [int(x) for x in depths]
+        faces = [np.empty((6, (1 << d) + 1, (1 << d) + 1, 2), np.float32) for d in dl]
+        cells = [np.zeros((6, int(lib().rn_terrain2d_cell_count(d))), CELL_DTYPE) for d in dl]
+        fp = (C.c_void_p * nrocks)(*[f.ctypes.data for f in faces])
+        cp = (C.c_void_p * nrocks)(*[c.ctypes.data for c in cells])
+        darr = (C.c_int32 * nrocks)(*dl) if depths is not None else None
+        _check(lib().rn_rock_batch(self._h, state & 0xFFFFFFFF, nrocks, darr, amplitude, fp, cp, 0, None, nd, ex, st, C.byref(after)))
+        return faces, cells, list(nd), [float(x) for x in ex], [int(x) for x in st], int(after.value)
 
     def selftest_math(self):
         buf = (C.c_uint64 * 3)()

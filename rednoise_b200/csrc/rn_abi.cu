@@ -11,6 +11,7 @@
 #include <string>
 #include <new>
 #include <vector>
+#include <algorithm>
 
 using namespace rn;
 
@@ -744,6 +745,137 @@ int rn_rock(rn_context* ctx, const rn_rock_params* p, rn_rock_element* faces, rn
             uint32_t* lcg_state_after)
 {
   return rock_or_cloud(ctx, 0, p, faces, cells, dst_is_device, stream_v, lcg_state_after);
+}
+
+int rn_rock_batch(rn_context* ctx, uint32_t lcg_state, int nrocks, const int32_t* depths, float amplitude, rn_rock_element* const* faces,
+                  rn_cell* const* cells, int dst_is_device, void* stream_v, int32_t* depths_out, float* exponents_out, uint32_t* states_out,
+                  uint32_t* lcg_state_after)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  if (nrocks < 0 || nrocks > RN_ROCK_BATCH_MAX) return fail(RN_ERR_BAD_PARAM, "nrocks outside [0, RN_ROCK_BATCH_MAX]");
+  if (!faces && !cells) return fail(RN_ERR_BAD_PARAM, "faces and cells are both NULL");
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+  // 1. the host walks the rand() stream: one call decides a rock's depth (Core.cpp:72-75), the rock then consumes
+  //    rn_rock_draw_count(depth) calls -- a closed form, so every rock's entry state is known before anything is generated
+  std::vector<int> d((size_t)nrocks);
+  std::vector<uint32_t> st((size_t)nrocks + 1);
+  uint32_t s = lcg_state;
+  for (int i = 0; i < nrocks; i++) {
+    float exponent = 0.0f;
+    if (depths) {
+      d[i] = depths[i];
+    } else {
+      s = s * kLcgA + kLcgC;
+      const int r = (int)((s >> 16) & 0x7fffu);
+      exponent = -5.0f + (0.0f - -5.0f) * ((float)r / 32767.0f);  // random(-5.0f, 0.0f), basics.h:20-23
+      d[i] = (int)(exponent + 7);                                   // Core.cpp:75
+    }
+    if (d[i] < RN_ROCK_MIN_DEPTH || d[i] > RN_ROCK_MAX_DEPTH) return fail(RN_ERR_BAD_PARAM, "rock depth out of range [1,12]");
+    if (exponents_out) exponents_out[i] = exponent;
+    if (depths_out) depths_out[i] = d[i];
+    st[i] = s;
+    s = rn::lcg_state_after(s, rock_draw_count(d[i]));
+  }
+  st[nrocks] = s;
+  if (nrocks == 0) {
+    if (lcg_state_after) *lcg_state_after = s;
+    return RN_OK;
+  }
+  // 2. destinations: the caller's device buffers, or device staging for host destinations
+  std::vector<void*> df((size_t)nrocks, nullptr), dc((size_t)nrocks, nullptr);
+  std::vector<size_t> fbytes((size_t)nrocks), cbytes((size_t)nrocks);
+  size_t ftotal = 0, ctotal = 0;
+  for (int i = 0; i < nrocks; i++) {
+    const size_t side = ((size_t)1 << d[i]) + 1;
+    fbytes[i] = ((6 * side * side * sizeof(rn_rock_element) + 255) / 256) * 256;
+    cbytes[i] = ((6 * (size_t)rn_terrain2d_cell_count(d[i]) * sizeof(rn_cell) + 255) / 256) * 256;
+    ftotal += fbytes[i];
+    ctotal += cbytes[i];
+  }
+  const bool stage_f = faces && !dst_is_device, stage_c = cells && !dst_is_device;
+  int stt = RN_OK;
+  if (stage_f && (stt = ensure(&ctx->field, &ctx->field_bytes, ftotal)) != RN_OK) return stt;
+  if (stage_c && (stt = ensure(&ctx->cells, &ctx->cells_bytes, ctotal)) != RN_OK) return stt;
+  {
+    size_t fo = 0, co = 0;
+    for (int i = 0; i < nrocks; i++) {
+      if (faces) {
+        if (!faces[i]) return fail(RN_ERR_BAD_PARAM, "faces[i] is NULL");
+        df[i] = stage_f ? static_cast<char*>(ctx->field) + fo : (void*)faces[i];
+      }
+      if (cells) {
+        if (!cells[i]) return fail(RN_ERR_BAD_PARAM, "cells[i] is NULL");
+        dc[i] = stage_c ? static_cast<char*>(ctx->cells) + co : (void*)cells[i];
+      }
+      fo += fbytes[i];
+      co += cbytes[i];
+    }
+  }
+  // 3. rocks of depth <= 7 (all of the app's): one launch for the lot; deeper ones through the level kernels
+  const size_t item = rock_small_item_bytes();
+  if ((stt = ensure(&ctx->small, &ctx->small_bytes, 256 + (size_t)nrocks * (item + 16))) != RN_OK) return stt;
+  int* flags = static_cast<int*>(ctx->small);
+  void* items_dev = static_cast<char*>(ctx->small) + ((sizeof(int) * (size_t)nrocks + 255) / 256) * 256;
+  std::vector<char> items_host((size_t)nrocks * item);
+  std::vector<int> small_idx, sd;
+  std::vector<uint32_t> ss;
+  std::vector<void*> sf, sc;
+  for (int i = 0; i < nrocks; i++)
+    if (d[i] <= 7 && (!df[i] || reinterpret_cast<uintptr_t>(df[i]) % 8 == 0) && (!dc[i] || reinterpret_cast<uintptr_t>(dc[i]) % 16 == 0)) {
+      small_idx.push_back(i); sd.push_back(d[i]); ss.push_back(st[i]); sf.push_back(df[i]); sc.push_back(dc[i]);
+    }
+  if (!small_idx.empty())
+    RN_CUDA(rock_small_batch((int)small_idx.size(), sd.data(), ss.data(), amplitude, faces ? sf.data() : nullptr, cells ? sc.data() : nullptr, flags, items_dev,
+                             items_host.data(), stream, &ctx->launches));
+  std::vector<int> collided(small_idx.size(), 0);
+  if (!small_idx.empty()) {
+    RN_CUDA(cudaMemcpyAsync(collided.data(), flags, sizeof(int) * small_idx.size(), cudaMemcpyDeviceToHost, stream));
+    RN_CUDA(cudaStreamSynchronize(stream));  // (also makes items_host reusable)
+  }
+  // 4. a displaced height of exactly 0.0f makes the reference's call sequence value-dependent (about 1 rock in 500): from the
+  //    first such rock on, the rocks are generated one by one (rn_rock regenerates it literally and reports the state after it)
+  int first_bad = nrocks;
+  for (size_t q = 0; q < small_idx.size(); q++)
+    if (collided[q] && small_idx[q] < first_bad) first_bad = small_idx[q];
+  for (int i = 0; i < nrocks; i++) {
+    const bool was_small = d[i] <= 7 && std::find(small_idx.begin(), small_idx.end(), i) != small_idx.end();
+    if (was_small && i < first_bad) continue;
+    if (i >= first_bad && states_out) states_out[i] = st[i];
+    rn_rock_params rp{st[i], d[i], amplitude};
+    uint32_t after = 0;
+    stt = rock_or_cloud(ctx, 0, &rp, reinterpret_cast<rn_rock_element*>(df[i]), reinterpret_cast<rn_cell*>(dc[i]), 1, stream, &after);
+    if (stt != RN_OK) return stt;
+    if (i >= first_bad && after != st[i + 1]) {  // the stream moved: re-derive everything behind this rock
+      uint32_t s2 = after;
+      for (int j = i + 1; j < nrocks; j++) {
+        float exponent = 0.0f;
+        if (!depths) {
+          s2 = s2 * kLcgA + kLcgC;
+          const int r = (int)((s2 >> 16) & 0x7fffu);
+          exponent = -5.0f + (0.0f - -5.0f) * ((float)r / 32767.0f);
+          const int nd = (int)(exponent + 7);
+          if (nd != d[j]) return fail(RN_ERR_UNSUPPORTED, "a colliding rock changed the depth of a later rock: generate the rocks one by one with rn_rock");
+          if (exponents_out) exponents_out[j] = exponent;
+        }
+        st[j] = s2;
+        s2 = rn::lcg_state_after(s2, rock_draw_count(d[j]));
+      }
+      st[nrocks] = s2;
+    }
+  }
+  if (states_out)
+    for (int i = 0; i < nrocks; i++) states_out[i] = st[i];
+  // 5. host destinations
+  for (int i = 0; i < nrocks; i++) {
+    const size_t side = ((size_t)1 << d[i]) + 1;
+    if (stage_f) RN_CUDA(cudaMemcpyAsync(faces[i], df[i], 6 * side * side * sizeof(rn_rock_element), cudaMemcpyDeviceToHost, stream));
+    if (stage_c) RN_CUDA(cudaMemcpyAsync(cells[i], dc[i], 6 * (size_t)rn_terrain2d_cell_count(d[i]) * sizeof(rn_cell), cudaMemcpyDeviceToHost, stream));
+  }
+  RN_CUDA(cudaStreamSynchronize(stream));
+  if (lcg_state_after) *lcg_state_after = st[nrocks];
+  return RN_OK;
 }
 
 uint64_t rn_cloud_draw_count(int depth)

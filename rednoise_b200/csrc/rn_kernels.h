@@ -34,6 +34,11 @@ uint64_t cloud_draw_count(int depth);
 cudaError_t rock_generate(void* faces, void* cells, int* flag, int kind, int depth, uint32_t state, float amplitude, int sequential,
                           cudaStream_t stream, uint64_t* launches);
 
+// n rocks of depth <= 7 in one launch (one CTA per face, the face in shared memory through all levels): see rn_rock.cu
+size_t rock_small_item_bytes();
+cudaError_t rock_small_batch(int n, const int* depths, const uint32_t* states, float amplitude, void* const* faces, void* const* cells, int* flags,
+                             void* items_dev, void* items_host, cudaStream_t stream, uint64_t* launches);
+
 // 3D density-volume extension (rn_volume.cu; defined by the CPU specification of DESIGN.md section 5.8, no reference counterpart):
 // planes [i0, i0+ni) of the (W+1)^3 float volume into `slab` (ni x (W+1) x (W+1), dense); scratch: volume_scratch_bytes() bytes.
 size_t volume_scratch_bytes(int depth, int i0, int ni);

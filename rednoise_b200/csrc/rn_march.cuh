@@ -41,12 +41,18 @@
 namespace rn {
 
 constexpr int kMarchCols = 60;  // cell columns a warp finishes
+#ifndef RN_MARCH_CARRY
+#define RN_MARCH_CARRY 0   // values kept in registers from phase to phase instead of being re-read from shared memory (lean
+                           // instantiation): bit 0 K(u-1, k0/k1) P2 -> P3, bit 1 C(u-1, k0/k1) P2 -> P3, bit 2 K(u, .) P1 -> P2
+#endif
 
 // Warp-private shared memory, in E4 (16-byte) units.
-//   ring    four input lattice rows (row r in slot r & 3): lane l's columns k0, k0+1 at [2l], [2l+1] -- so [2l+2] is its right
-//           neighbour's k0 --, lane 31's third column at [64]
+//   ring    four input lattice rows (row r in slot r & 3), even and odd columns apart so that every access of a warp is one
+//           contiguous run: lane l's column k0 at [l] -- so [l+1] is its right neighbour's k0, [32] lane 31's third
+//           column -- and its column k0+1 at [kRingOdd + l]
 //   state   two banks (step parity) of the values a step hands to the next: element e of lane l at [e][l]
 //   const   per-lane constants: the squared column distances of the lane's four output columns from the volcano
+constexpr int kRingOdd = 34;     // (33 even-column entries, padded to an even count)
 constexpr int kRingRowE4 = 66;
 constexpr int kRingE4 = 4 * kRingRowE4;
 enum { S_C0 = 0, S_C1, S_C2, S_M1A, S_M1B, S_TS, S_TD, S_TE, S_COUNT };  // C(u; k0-1, k0, k1), M1(u; k0, k1), TS(u; 4),
@@ -56,6 +62,7 @@ constexpr int kStateE4 = kRingE4;
 constexpr int kConstE4 = kStateE4 + 2 * kBankE4;
 constexpr int kWarpE4 = kConstE4 + 32;  // 808 E4 = 12.6 KB per warp
 RN_HD E4* ring_row(E4* wsm, int r) { return wsm + (r & 3) * kRingRowE4; }
+RN_HD const E4& ring_at(const E4* row_lane, int q) { return row_lane[q == 1 ? kRingOdd : (q >> 1)]; }  // row_lane = ring_row(wsm, r) + lane
 RN_HD E4* state_at(E4* wsm, int bank, int e, int lane) { return wsm + kStateE4 + bank * kBankE4 + e * 32 + lane; }
 
 // registers of a lane: what lives across steps, and what one phase of a step hands to the next
@@ -71,6 +78,8 @@ struct MarchLane {
   float td1[3];    // TD1(u; k0-1, k0, k1)
   float td2[3];    // TD2(u-1; k0, k1, k1+1)
   float sg[2];     // shade of corner K(u, k0/k1) as generateSquare's scatter left it
+  E4 tdm, tem;     // what step u-1 left in its S_TD / S_TE slots (read in P2, used again in P3)
+  E4 c_km[2], c_cm[2], c_ka[3];  // RN_MARCH_CARRY
   E4 out[2][4];    // the two finished output rows of the lane
 };
 
@@ -259,11 +268,11 @@ struct March {
   static RN_HD void prefetch_row(const StreamParams& sp, const MarchCtx& cx, E4* wsm, const E4* p, int r, int lane)
   {
     if (r <= cx.a1e + 1 && r >= 0 && r <= sp.lev.n) {  // uniform: a later step reads the row, and it exists
-      E4* slot = ring_row(wsm, r) + 2 * lane;
+      E4* slot = ring_row(wsm, r) + lane;
       const int k0 = cx.L0 + 2 * lane, n = sp.lev.n;
       if (!EDGE || (k0 >= 0 && k0 <= n)) ring_copy16(slot, p);
-      if (!EDGE || (k0 + 1 >= 0 && k0 + 1 <= n)) ring_copy16(slot + 1, p + 1);
-      if (lane == 31 && (!EDGE || (k0 + 2 >= 0 && k0 + 2 <= n))) ring_copy16(slot + 2, p + 2);
+      if (!EDGE || (k0 + 1 >= 0 && k0 + 1 <= n)) ring_copy16(slot + kRingOdd, p + 1);
+      if (lane == 31 && (!EDGE || (k0 + 2 >= 0 && k0 + 2 <= n))) ring_copy16(slot + 1, p + 2);
     }
     ring_commit();
   }
@@ -320,14 +329,15 @@ struct March {
     prefetch_row(sp, cx, wsm, L.src, u + 2, lane);
     L.src += sp.gin_pitch;
     ring_wait_all_but_1();
-    const E4* ka = ring_row(wsm, u) + 2 * lane;
-    const E4* kb = ring_row(wsm, u + 1) + 2 * lane;
+    const E4* ra = ring_row(wsm, u) + lane;
+    const E4* rb = ring_row(wsm, u + 1) + lane;
+    const E4 ka[3] = {ring_at(ra, 0), ring_at(ra, 1), ring_at(ra, 2)}, kb[3] = {ring_at(rb, 0), ring_at(rb, 1), ring_at(rb, 2)};
     const uint32_t sB = kLcgA * L.sS + kLcgC;
     const uint32_t draw_a = lcg_draw_from_state(L.sS), draw_b = lcg_draw_from_state(sB);
     L.sS = jump_apply(sp.jn, L.sS);
     if (!EDGE) {
-      const E4 a01 = ka[1], a11 = kb[1];  // shared by the lane's two cells
-      centre_pair(sp.law, ka[0], kb[0], a01, a11, a01, a11, ka[2], kb[2], sp.lev.blahS, draw_a, draw_b, &L.cen[1], &L.cen[2], &L.ts[1], &L.ts[2]);
+      if (RN_MARCH_CARRY & 4) { L.c_ka[0] = ka[0]; L.c_ka[1] = ka[1]; L.c_ka[2] = ka[2]; }
+      centre_pair(sp.law, ka[0], kb[0], ka[1], kb[1], ka[1], kb[1], ka[2], kb[2], sp.lev.blahS, draw_a, draw_b, &L.cen[1], &L.cen[2], &L.ts[1], &L.ts[2]);
     } else {
       const int n = sp.lev.n;
       const int k0 = cx.L0 + 2 * lane;
@@ -363,22 +373,27 @@ struct March {
   static RN_HD void p2(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* wsm, int u, int lane)
   {
     const int pb = bank_of(cx, u) ^ 1;  // what step u-1 left
-    const E4* ka = ring_row(wsm, u) + 2 * lane;
-    const E4* km = ring_row(wsm, u - 1) + 2 * lane;
+    const E4* ra = ring_row(wsm, u) + lane;
+    const E4* rm = ring_row(wsm, u - 1) + lane;
     const E4 tsm = *state_at(wsm, pb, S_TS, lane);
+    L.tdm = *state_at(wsm, pb, S_TD, lane);  // kept for P3
+    L.tem = *state_at(wsm, pb, S_TE, lane);
     const E4 cenm[3] = {*state_at(wsm, pb, S_C0, lane), *state_at(wsm, pb, S_C1, lane), *state_at(wsm, pb, S_C2, lane)};
     const float* tsc = L.ts;
     const E4* cenc = L.cen;
     // corner shades as generateSquare left them (Terrain.cpp:252-255): minus the scatter of the 4 surrounding centres,
     // in call order (u-1, k-1), (u-1, k), (u, k-1), (u, k)
-    E4 K0 = ka[0], K1 = ka[1], K2 = ka[2];
+    const bool cka = !EDGE && (RN_MARCH_CARRY & 4);
+    E4 K0 = cka ? L.c_ka[0] : ring_at(ra, 0), K1 = cka ? L.c_ka[1] : ring_at(ra, 1), K2 = cka ? L.c_ka[2] : ring_at(ra, 2);
     K0.w = (((K0.w - tsm.x) - tsm.y) - tsc[0]) - tsc[1];
     K1.w = (((K1.w - tsm.y) - tsm.z) - tsc[1]) - tsc[2];
     K2.w = (((K2.w - tsm.z) - tsm.w) - tsc[2]) - tsc[3];
     // K'(u-1, k0/k1): position from the ring, shade as step u-1 computed it
-    E4 kcm[2] = {km[0], km[1]};
-    kcm[0].w = state_at(wsm, pb, S_TD, lane)->w;
-    kcm[1].w = state_at(wsm, pb, S_TE, lane)->w;
+    E4 kcm[2] = {ring_at(rm, 0), ring_at(rm, 1)};
+    if (!EDGE && (RN_MARCH_CARRY & 1)) { L.c_km[0] = kcm[0]; L.c_km[1] = kcm[1]; }
+    if (!EDGE && (RN_MARCH_CARRY & 2)) { L.c_cm[0] = cenm[1]; L.c_cm[1] = cenm[2]; }
+    kcm[0].w = L.tdm.w;
+    kcm[1].w = L.tem.w;
     const uint32_t s1B = kLcgA * L.sD1 + kLcgC, s2B = kLcgA * L.sD2 + kLcgC;
     const uint32_t d1a = lcg_draw_from_state(L.sD1), d1b = lcg_draw_from_state(s1B);
     const uint32_t d2a = lcg_draw_from_state(L.sD2), d2b = lcg_draw_from_state(s2B);
@@ -433,17 +448,18 @@ struct March {
   static RN_HD void p3(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* wsm, int u, int lane)
   {
     const int pb = bank_of(cx, u) ^ 1;
-    const E4 tdm = *state_at(wsm, pb, S_TD, lane);  // TD1(u-1; k0-1, k0, k1), sg(u-1, k0)
-    const E4 tem = *state_at(wsm, pb, S_TE, lane);  // TD2(u-2; k0, k1, .), sg(u-1, k1)
+    const E4 tdm = L.tdm;  // TD1(u-1; k0-1, k0, k1), sg(u-1, k0)
+    const E4 tem = L.tem;  // TD2(u-2; k0, k1, .), sg(u-1, k1)
     const float* tdc = L.td1;
     const float* t2 = L.td2;
     // corner K(u-1, k): generateSquare's scatter (carried), then loop 1 (same row: k-1, k), loop 2 (same column: u-2, u-1)
-    const E4* km = ring_row(wsm, u - 1) + 2 * lane;
-    E4 c0 = km[0], c1 = km[1];
+    const E4* rm = ring_row(wsm, u - 1) + lane;
+    const bool ckm = !EDGE && (RN_MARCH_CARRY & 1), ccm = !EDGE && (RN_MARCH_CARRY & 2);
+    E4 c0 = ckm ? L.c_km[0] : ring_at(rm, 0), c1 = ckm ? L.c_km[1] : ring_at(rm, 1);
     c0.w = (((tdm.w - tdm.x) - tdm.y) - tem.x) - t2[0];
     c1.w = (((tem.w - tdm.y) - tdm.z) - tem.y) - t2[1];
     // centre C(u-1, k): loop-1 mids above and below, loop-2 mids left and right
-    E4 e0 = *state_at(wsm, pb, S_C1, lane), e1 = *state_at(wsm, pb, S_C2, lane);
+    E4 e0 = ccm ? L.c_cm[0] : *state_at(wsm, pb, S_C1, lane), e1 = ccm ? L.c_cm[1] : *state_at(wsm, pb, S_C2, lane);
     e0.w = (((e0.w - tdm.y) - tdc[1]) - t2[0]) - t2[1];
     e1.w = (((e1.w - tdm.z) - tdc[2]) - t2[1]) - t2[2];
     L.out[0][0] = c0;

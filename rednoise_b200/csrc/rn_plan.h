@@ -56,7 +56,7 @@ constexpr int kStreamSmallCols = RN_STREAM_SMALL_COLS;    // levels with fewer c
 #define RN_MARCH 1              // 0: streamed levels run the round-1 block kernel (rn_stream.cuh)
 #endif
 #ifndef RN_MARCH_WARPS
-#define RN_MARCH_WARPS 16       // resident warps per SM the kernel is compiled for (register cap 65536 / 32 / this)
+#define RN_MARCH_WARPS 14       // resident warps per SM the kernel is compiled for (register cap 65536 / 32 / this)
 #endif
 #ifndef RN_MARCH_WPB
 #define RN_MARCH_WPB 1          // independent warps per CTA
@@ -65,7 +65,7 @@ constexpr int kStreamSmallCols = RN_STREAM_SMALL_COLS;    // levels with fewer c
 #define RN_MARCH_FREE 2         // warps per SM the output launch leaves to the next call's small coarse stages
 #endif
 #ifndef RN_MARCH_EDGE_COST
-#define RN_MARCH_EDGE_COST 1.6f // duration of a border-strip warp relative to an interior one with the same rows
+#define RN_MARCH_EDGE_COST 1.3f // duration of a border-strip warp relative to an interior one with the same rows
 #endif
 #ifndef RN_MARCH_MIN_SEG_ROWS
 #define RN_MARCH_MIN_SEG_ROWS 8

@@ -14,7 +14,8 @@
 // With the index known, the LCG state is reached by skip-ahead and the levels are evaluated breadth-first, one launch
 // per level, each face on its own: a sample on a cube edge is computed by both faces that see it, from the same call
 // index, so the faces never exchange data.  A displaced height of exactly 0.0f would make the reference draw again
-// (value-dependent); the kernels flag it and the call fails loudly instead of returning different samples.
+// (value-dependent); the kernels flag it and rn_rock / rn_cloud then regenerate the input with the literal recursion on one
+// device thread (k_rock_sequential below): slower, but the samples and the rand() call count are the reference's.
 //
 // KIND 1 is the Cloud generator (Cloud.cpp), the two-face variant: a lower and an upper sheet that share their whole border
 // (Cloud::element, Cloud.cpp:116-121: face 1 finds all four sides set by face 0), ten preset control heights (:64-73) that the
@@ -22,6 +23,7 @@
 // the upper sheet (:199-200).
 #include "rn_kernels.h"
 #include "rn_tile.cuh"
+#include <atomic>
 
 namespace rn {
 
@@ -33,6 +35,7 @@ struct RockTopo {
 };
 
 constexpr int kRock = 0, kCloud = 1;
+constexpr int kRockSmallMaxDepth = 7;  // rocks up to this depth fit one CTA per face in shared memory (k_rock_small)
 constexpr int kRockNodeLevel = 7;  // levels from this one on use the node-major kernel (measured: depth 7 77 vs 92 us, depth 11 0.89 vs 2.1 ms)
 
 struct RockParams {
@@ -127,19 +130,15 @@ __device__ inline uint32_t rock_point_call_index(const RockTopo& t, int depth, i
 // half-step lattice of that level ((2n+1)^2 points per face; those with two even coordinates are older).
 // One level, one thread per SAMPLE (used for the coarse levels, where a level is a handful of warps and latency counts): the centres (Rock.cpp:179) and edge midpoints (:181-212) of all nodes of width W >> l, on the
 // half-step lattice of that level ((2n+1)^2 points per face; those with two even coordinates are older).
+// the sample (px, py) of the half-step lattice of level l on face f, whose (W+1)^2 samples start at g (global or shared memory)
 template <int KIND>
-__global__ void k_rock_level_points(const __grid_constant__ RockParams rp, int l)
+__device__ __forceinline__ void rock_point(const RockParams& rp, float2* g, int f, int l, int px, int py)
 {
   const int depth = rp.depth, W = 1 << depth, P = W + 1;
-  const int n2 = (2 << l) + 1;  // points per side of the half-step lattice
-  const int f = blockIdx.z;
-  const int px = blockIdx.y * blockDim.y + threadIdx.y, py = blockIdx.x * blockDim.x + threadIdx.x;
-  if (px >= n2 || py >= n2) return;
   const int ox = px & 1, oy = py & 1;
   if (!ox && !oy) return;
   const int hsh = depth - l - 1, h = 1 << hsh;  // half step
   const int x = px << hsh, y = py << hsh;
-  float2* g = rp.faces + (size_t)f * P * P;
   float2 e;
   if (ox && oy) {
     if (KIND == kCloud && g[(size_t)x * P + y].x != 0.0f) return;  // a preset control height (Cloud.cpp:64-73,131)
@@ -157,6 +156,17 @@ __global__ void k_rock_level_points(const __grid_constant__ RockParams rp, int l
     if (e.x == 0.0f) atomicExch(rp.collision, 1);
   }
   g[(size_t)x * P + y] = e;
+}
+
+template <int KIND>
+__global__ void k_rock_level_points(const __grid_constant__ RockParams rp, int l)
+{
+  const int P = (1 << rp.depth) + 1;
+  const int n2 = (2 << l) + 1;  // points per side of the half-step lattice
+  const int f = blockIdx.z;
+  const int px = blockIdx.y * blockDim.y + threadIdx.y, py = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= n2 || py >= n2) return;
+  rock_point<KIND>(rp, rp.faces + (size_t)f * P * P, f, l, px, py);
 }
 
 // One level, one thread per quadtree NODE (f, qx, qy) of width W >> l: its centre (Rock.cpp:179) and the edge midpoints it is
@@ -342,14 +352,11 @@ struct RockCell {  // rn_cell (include/rednoise.h)
   uint8_t level;
 };
 
+// node e_all (level-major) of face f, whose samples start at g (global or shared memory), into out[e_all]
 template <int KIND>
-__global__ void k_rock_cells(RockCell* __restrict__ out, const float2* __restrict__ faces, int depth, uint32_t count, float radius0)
+__device__ __forceinline__ void rock_cell(RockCell* __restrict__ out, const float2* g, int depth, int f, uint32_t e_all, float radius0)
 {
-  const uint32_t e_all = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e_all >= count) return;
-  const int f = blockIdx.y;
   const int W = 1 << depth, P = W + 1;
-  const float2* g = faces + (size_t)f * P * P;
   // level-major index -> (level, entry); entry = Morton code of the node, x in the low bit (children order of :266-269)
   int l = 0;
   uint32_t off = 0;
@@ -390,12 +397,91 @@ __global__ void k_rock_cells(RockCell* __restrict__ out, const float2* __restric
   c.radius = radius;
   c.level = (uint8_t)l;
   const float4* src = reinterpret_cast<const float4*>(&c);
-  float4* dst = reinterpret_cast<float4*>(out + (size_t)f * count + e_all);
+  float4* dst = reinterpret_cast<float4*>(out + e_all);
   dst[0] = src[0];
   dst[1] = src[1];
 }
 
+template <int KIND>
+__global__ void k_rock_cells(RockCell* __restrict__ out, const float2* __restrict__ faces, int depth, uint32_t count, float radius0)
+{
+  const uint32_t e_all = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e_all >= count) return;
+  const int f = blockIdx.y;
+  const size_t P = ((size_t)1 << depth) + 1;
+  rock_cell<KIND>(out + (size_t)f * count, faces + (size_t)f * P * P, depth, f, e_all, radius0);
+}
+
+// ---- small rocks, ONE launch for a whole batch (the app builds 20 rocks of depth 2..7 back to back, Core.cpp:69-79) ----
+// A CTA owns one face of one rock: the face lives in shared memory ((W+1)^2 x 8 B <= 133 KB at depth 7) through all levels
+// (one barrier per level: a level's centres and edge midpoints read older samples only), is then written out, and the Cell
+// attributes of its quadtree are evaluated from the same shared image.  Same per-sample code as the level kernels.
+struct RockBatchItem {
+  RockParams rp;     // rp.faces: device destination of the rock's faces, or nullptr
+  RockCell* cells;   // device destination of the rock's nfaces x count cells, or nullptr
+  float radius0;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_rock_small(const RockBatchItem* __restrict__ items)
+{
+  extern __shared__ __align__(16) float2 gs[];
+  const RockBatchItem& it = items[blockIdx.y];
+  const RockParams rp = it.rp;
+  const int f = blockIdx.x, depth = rp.depth, W = 1 << depth, P = W + 1, tid = threadIdx.x;
+  const int q = W / 4;
+  for (int i = tid; i < P * P; i += 256) {
+    float2 v = make_float2(0.0f, 1.0f);  // Rock.cpp:57-60, Cloud.cpp:59-60
+    if (KIND == kCloud) {                // Cloud.cpp:64-73: centre and quarter points of both sheets
+      const int x = i / P, y = i - x * P;
+      const bool preset = (x == 2 * q && y == 2 * q) || ((x == q || x == 3 * q) && (y == q || y == 3 * q));
+      if (preset) v.x = f ? 0.5f : -0.5f;
+    }
+    gs[i] = v;
+  }
+  __syncthreads();
+  for (int l = 0; l < depth; l++) {
+    const int n2 = (2 << l) + 1;
+    for (int i = tid; i < n2 * n2; i += 256) {
+      const int px = i / n2, py = i - px * n2;
+      rock_point<KIND>(rp, gs, f, l, px, py);
+    }
+    __syncthreads();
+  }
+  if (rp.faces) {
+    float2* dst = rp.faces + (size_t)f * P * P;
+    for (int i = tid; i < P * P; i += 256) dst[i] = gs[i];
+  }
+  if (it.cells) {
+    uint32_t count = 0;
+    for (int l = 0; l < depth; l++) count += 1u << (2 * l);
+    for (uint32_t e = tid; e < count; e += 256) rock_cell<KIND>(it.cells + (size_t)f * count, gs, depth, f, e, it.radius0);
+  }
+}
+
+
 }  // namespace
+
+// which sides of a face were drawn by an earlier face (cube topology of Rock::element / shared border of Cloud::element), and
+// the faces' first call
+static void rock_topo(int kind, int depth, RockTopo& topo)
+{
+  const int W = 1 << depth;
+  const int sx[4] = {0, W, W / 2, W / 2}, sy[4] = {W / 2, W / 2, 0, W};
+  uint32_t acc = 0;
+  for (int f = 0; f < 6; f++) {
+    for (int s = 0; s < 4; s++) {
+      topo.pre[f][s] = 0;
+      if (kind == kCloud) { topo.pre[f][s] = f == 1; continue; }
+      int X, Y, Z, x, y;
+      cube_of(W, f, sx[s], sy[s], X, Y, Z);
+      for (int g = 0; g < f; g++)
+        if (face_local(W, g, X, Y, Z, x, y)) topo.pre[f][s] = 1;
+    }
+    topo.base[f] = acc;
+    acc += rock_E(depth) - (uint32_t)(W - 1) * (uint32_t)(topo.pre[f][0] + topo.pre[f][1] + topo.pre[f][2] + topo.pre[f][3]);
+  }
+}
 
 uint64_t rock_draw_count(int depth)
 {
@@ -414,23 +500,7 @@ cudaError_t rock_generate(void* faces_v, void* cells_v, int* flag, int kind, int
   const size_t P = (size_t)W + 1, nall = (size_t)nfaces * P * P;
   RockParams rp;
   rp.faces = faces; rp.depth = depth; rp.state = state; rp.amplitude = amplitude; rp.collision = flag;
-  {  // which sides of a face were drawn by an earlier face (cube topology of Rock::element / shared border of Cloud::element),
-     // and the faces' first call
-    const int sx[4] = {0, W, W / 2, W / 2}, sy[4] = {W / 2, W / 2, 0, W};
-    uint32_t acc = 0;
-    for (int f = 0; f < 6; f++) {
-      for (int s = 0; s < 4; s++) {
-        rp.topo.pre[f][s] = 0;
-        if (kind == kCloud) { rp.topo.pre[f][s] = f == 1; continue; }
-        int X, Y, Z, x, y;
-        cube_of(W, f, sx[s], sy[s], X, Y, Z);
-        for (int g = 0; g < f; g++)
-          if (face_local(W, g, X, Y, Z, x, y)) rp.topo.pre[f][s] = 1;
-      }
-      rp.topo.base[f] = acc;
-      acc += rock_E(depth) - (uint32_t)(W - 1) * (uint32_t)(rp.topo.pre[f][0] + rp.topo.pre[f][1] + rp.topo.pre[f][2] + rp.topo.pre[f][3]);
-    }
-  }
+  rock_topo(kind, depth, rp.topo);
   cudaError_t e = cudaMemsetAsync(flag, 0, 2 * sizeof(unsigned long long), stream);
   if (e != cudaSuccess) return e;
   k_rock_init<<<(unsigned)((nall + 255) / 256), 256, 0, stream>>>(faces, nall, kind == kCloud ? W : 0);
@@ -470,6 +540,47 @@ cudaError_t rock_generate(void* faces_v, void* cells_v, int* flag, int kind, int
     nl++;
   }
   if (launches) *launches += nl;
+  return cudaGetLastError();
+}
+
+// `n` rocks of depth <= kRockSmallMaxDepth in ONE launch (k_rock_small): states[i] = generator state when rock i is entered,
+// faces[i] / cells[i] = device destinations (or nullptr), flags = n device ints (collision per rock), items_dev = device scratch of
+// rock_small_item_bytes() * n bytes, items_host = pinned or pageable host scratch of the same size.
+size_t rock_small_item_bytes() { return sizeof(RockBatchItem); }
+cudaError_t rock_small_batch(int n, const int* depths, const uint32_t* states, float amplitude, void* const* faces, void* const* cells, int* flags,
+                             void* items_dev, void* items_host, cudaStream_t stream, uint64_t* launches)
+{
+  RockBatchItem* h = static_cast<RockBatchItem*>(items_host);
+  int maxd = 1;
+  for (int i = 0; i < n; i++) {
+    if (depths[i] < 1 || depths[i] > kRockSmallMaxDepth) return cudaErrorInvalidValue;
+    RockBatchItem& it = h[i];
+    it.rp.faces = static_cast<float2*>(faces ? faces[i] : nullptr);
+    it.rp.depth = depths[i];
+    it.rp.state = states[i];
+    it.rp.amplitude = amplitude;
+    it.rp.collision = flags + i;
+    rock_topo(kRock, depths[i], it.rp.topo);
+    it.cells = static_cast<RockCell*>(cells ? cells[i] : nullptr);
+    it.radius0 = 1.4f * sqrtf((1.0f + 0.5f * amplitude) * 0.5f);  // Rock.cpp:76
+    if (depths[i] > maxd) maxd = depths[i];
+  }
+  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)n, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(items_dev, h, sizeof(RockBatchItem) * (size_t)n, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  const size_t P = ((size_t)1 << maxd) + 1, bytes = P * P * sizeof(float2);
+  static std::atomic<size_t> configured[64] = {};
+  int dev = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 64 || configured[dev].load(std::memory_order_acquire) < bytes) {
+    e = cudaFuncSetAttribute(k_rock_small<kRock>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)1 << kRockSmallMaxDepth) + 1) * (int)(((size_t)1 << kRockSmallMaxDepth) + 1) * (int)sizeof(float2));
+    if (e != cudaSuccess) return e;
+    if (dev < 64) configured[dev].store((size_t)1 << 30, std::memory_order_release);
+  }
+  k_rock_small<kRock><<<dim3(6, (unsigned)n), 256, bytes, stream>>>(static_cast<const RockBatchItem*>(items_dev));
+  if (launches) *launches += 1;
   return cudaGetLastError();
 }
 

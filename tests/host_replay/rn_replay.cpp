@@ -253,6 +253,9 @@ void vol_level_host(const VolLevel& L, int tiles_i, int poison)
 
 extern "C" {
 
+// random() of basics.h:16-19 as the kernels evaluate it (rn_math.cuh: the /32767 as a multiplication + one FMA correction)
+float replay_random_from_draw(unsigned r) { return random_from_draw(r); }
+
 int replay_smem_bytes(int L)
 {
   switch (L) {

@@ -130,3 +130,71 @@ def test_cloud_seed_scan_including_collisions(ctx, oracle):
         assert co.tobytes() == cg.tobytes(), (depth, hex(state))
         odd += draws != lib.rn_cloud_draw_count(depth)
     print("clouds with value-dependent draws:", odd)
+
+
+def _core_loop_oracle(oracle, state, nrocks, depths=None):
+    """Core.cpp:69-79 on the CPU: per rock one rand() call decides the depth (unless depths are given), then the rock's own calls."""
+    out = []
+    s = state & 0xFFFFFFFF
+    for i in range(nrocks):
+        e = np.float32(0.0)
+        if depths is None:
+            s = (s * 214013 + 2531011) & 0xFFFFFFFF
+            r = (s >> 16) & 0x7FFF
+            e = np.float32(-5.0) + np.float32(5.0) * (np.float32(r) / np.float32(32767.0))   # random(-5.0f, 0.0f), basics.h:20-23
+            d = int(np.float32(e + np.float32(7.0)))                                          # Core.cpp:75
+        else:
+            d = depths[i]
+        fo, co, draws, so = oracle.rock(s, d, 0.3)
+        out.append((d, float(e), s, fo, co))
+        s = so
+    return out, s
+
+
+@pytest.mark.parametrize("state", [12345, 2024, 0xC0FFEE])
+def test_rock_batch_is_the_apps_rock_loop(ctx, oracle, state):
+    """rn_rock_batch: the 20 rocks of Core.cpp:69-79 in one call (one kernel launch for all rocks of depth <= 7), continuing one
+    rand() stream whose draws also decide the depths -- against the CPU restatement rock by rock."""
+    want, s_after = _core_loop_oracle(oracle, state, 20)
+    faces, cells, depths, exps, states, after = ctx.rock_batch_host(state, 20)
+    assert depths == [w[0] for w in want] and all(2 <= d <= 7 for d in depths)
+    assert states == [w[2] for w in want] and after == s_after
+    assert np.array_equal(np.array(exps, np.float32).view(np.uint32), np.array([w[1] for w in want], np.float32).view(np.uint32))
+    for i, (d, e, s, fo, co) in enumerate(want):
+        assert np.array_equal(fo.view(np.uint32), faces[i].view(np.uint32)), i
+        assert co.tobytes() == cells[i].tobytes(), i
+
+
+def test_rock_batch_given_depths_and_deep_rocks(ctx, oracle):
+    depths = [1, 7, 3, 9, 2, 8, 7, 5]   # 8 and 9 take the level kernels, the rest the one-launch kernel
+    want, s_after = _core_loop_oracle(oracle, 31337, len(depths), depths)
+    faces, cells, dout, exps, states, after = ctx.rock_batch_host(31337, len(depths), depths=depths)
+    assert dout == depths and after == s_after and states == [w[2] for w in want]
+    for i, (d, e, s, fo, co) in enumerate(want):
+        assert np.array_equal(fo.view(np.uint32), faces[i].view(np.uint32)), i
+        assert co.tobytes() == cells[i].tobytes(), i
+
+
+def test_rock_batch_with_a_colliding_rock(ctx, oracle):
+    """A batch that contains a value-dependent rock (a displaced height of exactly 0.0f, found by scanning with the oracle's
+    index-addressed form): from that rock on the batch falls back to rock-by-rock generation and still equals the reference."""
+    import ctypes as C
+    L = oracle.L
+    found = None
+    for s in range(1, 6000):
+        fo, co, draws, so = oracle.rock(s, 5, 0.3, want_cells=False)
+        if draws != 4 * 32 * 32 - 4:
+            found = s
+            break
+    if found is None:
+        pytest.skip("no colliding depth-5 rock among the first 6000 states")
+    depths = [3, 5, 4, 2]
+    # make rock 1 start exactly in the colliding state: walk back is impossible, so start the batch AT a state whose rock 0 (depth 3)
+    # ends in `found` -- simply put the colliding rock first instead
+    depths = [5, 3, 4, 2]
+    want, s_after = _core_loop_oracle(oracle, found, len(depths), depths)
+    faces, cells, dout, exps, states, after = ctx.rock_batch_host(found, len(depths), depths=depths)
+    assert after == s_after and states == [w[2] for w in want]
+    for i, (d, e, s, fo, co) in enumerate(want):
+        assert np.array_equal(fo.view(np.uint32), faces[i].view(np.uint32)), i
+        assert co.tobytes() == cells[i].tobytes(), i

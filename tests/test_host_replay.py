@@ -174,3 +174,13 @@ def test_replay_march_deep_slab(replay, oracle):
     for (i0, j0, ni, nj) in [(4000, 0, 200, 8193), (0, 4090, 8193, 70)]:
         got = run(replay, p, Win(i0, j0, ni, nj))
         assert np.array_equal(got.view(np.uint32), full[i0:i0 + ni, j0:j0 + nj].view(np.uint32)), (i0, j0, ni, nj)
+
+
+def test_random_division_shortcut_is_exact(replay, oracle):
+    """rn_math.cuh evaluates random()'s (2*r)/32767 as q = t*rc; q += fma(-q, 32767, t)*rc: the correctly rounded quotient, i.e. the
+    oracle's (and the reference's) division, for EVERY one of the 32768 draws."""
+    replay.replay_random_from_draw.restype = C.c_float
+    replay.replay_random_from_draw.argtypes = [C.c_uint]
+    for r in range(32768):
+        a, b = replay.replay_random_from_draw(r), oracle.L.rno_random_from_draw(r)
+        assert np.float32(a).view(np.uint32) == np.float32(b).view(np.uint32), r

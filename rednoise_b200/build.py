@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librednoise_b200.so")
 SOURCES = ["rn_abi.cu", "rn_levelsync.cu", "rn_util.cu", "rn_fused.cu", "rn_cells.cu", "rn_volume.cu", "rn_rock.cu"]
-HEADERS = ["rn_math.cuh", "rn_kernels.h", "rn_tile.cuh", "rn_stream.cuh", "rn_march.cuh", "rn_volume.cuh", "rn_plan.h", os.path.join("..", "..", "include", "rednoise.h")]
+HEADERS = ["rn_math.cuh", "rn_kernels.h", "rn_tile.cuh", "rn_stream.cuh", "rn_march.cuh", "rn_volume.cuh", "rn_volrow.cuh", "rn_plan.h", os.path.join("..", "..", "include", "rednoise.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

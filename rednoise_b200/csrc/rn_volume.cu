@@ -18,6 +18,7 @@
 // planes the slab needs only.  Bit-exact against the oracle.
 #include "rn_kernels.h"
 #include "rn_volume.cuh"
+#include "rn_volrow.cuh"
 #include <atomic>
 
 namespace rn {
@@ -50,6 +51,67 @@ cudaError_t launch_level(const VolLevel& L, int tiles_i, cudaStream_t stream)
   }
   const dim3 grid((unsigned)((L.n + TK - 1) / TK), (unsigned)((L.n + TJ - 1) / TJ), (unsigned)tiles_i);
   k_vol_level<TI, TJ, TK, NT><<<grid, NT, G::BYTES, stream>>>(L);
+  return cudaGetLastError();
+}
+
+// The warp-row kernel (rn_volrow.cuh): levels with n >= kRowMinN cells per axis.  NW warps; the phases of a level are separated
+// by block barriers, the row jobs of a phase go round-robin over the warps.  The job tables are compile-time constants in
+// global memory.
+__device__ constexpr RowJobs<kRowTI, kRowTJ, false> g_jobs_lean = make_row_jobs<kRowTI, kRowTJ, false>();
+__device__ constexpr RowJobs<kRowTI, kRowTJ, true> g_jobs_edge = make_row_jobs<kRowTI, kRowTJ, true>();
+
+template <int TI, int TJ, int NW>
+__global__ void __launch_bounds__(NW * 32) k_vol_rows(const __grid_constant__ VolLevel L)
+{
+  static_assert(TI == kRowTI && TJ == kRowTJ, "one job table per tile shape");
+  extern __shared__ __align__(16) float sm[];
+  const int A0 = (L.tile_i0 + (int)blockIdx.z) * TI, B0 = (int)blockIdx.y * TJ, C0 = (int)blockIdx.x * kRowTK;
+  const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool edge = A0 < 1 || B0 < 1 || A0 + TI >= L.n || B0 + TJ >= L.n;  // block-uniform: an i or j face of the volume
+  if (edge) {
+    using V = VolRows<TI, TJ, true>;
+    const typename V::Tile t = V::tile(L, A0, B0, C0);
+    V::zero(sm, tid, NW * 32);
+    __syncthreads();
+    V::load(L, t, sm, warp, lane, NW, tid);
+    __syncthreads();
+    V::cubes(L, t, sm, g_jobs_edge, warp, lane, NW, tid);
+    __syncthreads();
+    V::faces(L, t, sm, g_jobs_edge, warp, lane, NW, tid);
+    __syncthreads();
+    V::edges(L, t, sm, g_jobs_edge, warp, lane, NW, tid);
+    __syncthreads();
+    V::store(L, t, sm, warp, lane, NW);
+  } else {
+    using V = VolRows<TI, TJ, false>;
+    const typename V::Tile t = V::tile(L, A0, B0, C0);
+    V::load(L, t, sm, warp, lane, NW, tid);
+    __syncthreads();
+    V::cubes(L, t, sm, g_jobs_lean, warp, lane, NW, tid);
+    __syncthreads();
+    V::faces(L, t, sm, g_jobs_lean, warp, lane, NW, tid);
+    __syncthreads();
+    V::edges(L, t, sm, g_jobs_lean, warp, lane, NW, tid);
+    __syncthreads();
+    V::store(L, t, sm, warp, lane, NW);
+  }
+}
+
+template <int TI, int TJ, int NW>
+cudaError_t launch_rows(const VolLevel& L, int tiles_i, cudaStream_t stream)
+{
+  constexpr size_t BYTES = VolRows<TI, TJ, true>::BYTES;  // the EDGE table is the longer one
+  static std::atomic<bool> configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
+    e = cudaFuncSetAttribute(k_vol_rows<TI, TJ, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BYTES);
+    if (e != cudaSuccess) return e;
+    if (dev < 64) configured[dev].store(true, std::memory_order_release);
+  }
+  const dim3 grid((unsigned)(L.n / kRowTK), (unsigned)(L.n / TJ), (unsigned)tiles_i);
+  k_vol_rows<TI, TJ, NW><<<grid, NW * 32, BYTES, stream>>>(L);
   return cudaGetLastError();
 }
 
@@ -89,7 +151,8 @@ cudaError_t volume_generate(float* slab, void* scratch, int depth, uint32_t seed
     const int n = 1 << l;
     int tiles_i = 0;
     const VolLevel L = vol_level_make(depth, l, lo, hi, grid[l], grid[l + 1], seed, amplitude, &tiles_i);
-    switch (n) {
+    if (n >= kRowMinN) e = launch_rows<kRowTI, kRowTJ, kRowWarps>(L, tiles_i, stream);
+    else switch (n) {
       case 2: e = launch_level<2, 2, 2, 64>(L, tiles_i, stream); break;
       case 4: e = launch_level<4, 4, 4, 128>(L, tiles_i, stream); break;
       case 8: e = launch_level<8, 8, 8, kVolThreads>(L, tiles_i, stream); break;

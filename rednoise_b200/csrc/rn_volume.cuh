@@ -26,6 +26,7 @@ struct VolLevel {
   uint32_t seed;
   uint32_t ci, cj, ck; // hash multipliers of one fine step of this level: (coordinate << sh) * C == coordinate * (C << sh)
   float amplitude, scale;  // scale = s / W: ((amplitude * r) * s) / W == (amplitude * r) * scale exactly (powers of two)
+  float one;               // 1.0f the compiler cannot see (rn_volrow.cuh: a sum of packed products written as an FMA)
 };
 
 template <int TI, int TJ, int TK>
@@ -255,9 +256,12 @@ RN_HD void vol_tile(const VolLevel& L, float* sm, int A0, int B0, int C0)
 }
 
 constexpr int kVolTI = 8, kVolTJ = 8, kVolTK = 16, kVolThreads = 256;
+// the warp-row kernel (rn_volrow.cuh): levels with at least kRowMinN cells per axis
+constexpr int kRowTI = 4, kRowTJ = 4, kRowTK = 64, kRowWarps = 8;
+constexpr int kRowMinN = 64;
 
 // tile extent along i of the level whose input grid has n cells per axis
-inline int vol_tile_i(int n) { return n >= 16 ? kVolTI : n; }
+inline int vol_tile_i(int n) { return n >= kRowMinN ? kRowTI : (n >= 16 ? kVolTI : n); }
 
 
 // Plane ranges: lo[l], hi[l] = the planes (lattice index along i) of the level-l grid (side 2^l + 1) that the slab
@@ -301,6 +305,7 @@ inline VolLevel vol_level_make(int depth, int l, const int* lo, const int* hi, c
   L.ck = kHashK << sh;
   L.amplitude = amplitude;
   L.scale = (float)(W >> l) / (float)W;  // s / W with s = W / n
+  L.one = 1.0f;
   *tiles_i = t_hi - t_lo + 1;
   return L;
 }

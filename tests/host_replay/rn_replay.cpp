@@ -17,6 +17,7 @@
 #include "../../include/rednoise.h"
 #include "../../rednoise_b200/csrc/rn_plan.h"
 #include "../../rednoise_b200/csrc/rn_volume.cuh"
+#include "../../rednoise_b200/csrc/rn_volrow.cuh"
 
 using namespace rn;
 
@@ -251,7 +252,57 @@ void vol_level_host(const VolLevel& L, int tiles_i, int poison)
       }
 }
 
+// The warp-row form (rn_volrow.cuh): every phase for every warp and lane in turn (g_reverse: in descending order), the barrier
+// between phases modelled by finishing a phase for all of them first.
+template <int TI, int TJ, int NW, bool EDGE>
+void vol_rows_tile_host(const VolLevel& L, float* sm, int A0, int B0, int C0)
+{
+  using V = VolRows<TI, TJ, EDGE>;
+  static const RowJobs<TI, TJ, EDGE> jobs = make_row_jobs<TI, TJ, EDGE>();
+  const typename V::Tile t = V::tile(L, A0, B0, C0);
+  constexpr int NT = NW * 32;
+  auto each = [&](auto&& f) {
+    for (int q = 0; q < NT; q++) {
+      const int tid = g_reverse ? NT - 1 - q : q;
+      f(tid, tid >> 5, tid & 31);
+    }
+  };
+  if (EDGE) each([&](int tid, int, int) { V::zero(sm, tid, NT); });
+  each([&](int tid, int w, int l) { V::load(L, t, sm, w, l, NW, tid); });
+  each([&](int tid, int w, int l) { V::cubes(L, t, sm, jobs, w, l, NW, tid); });
+  each([&](int tid, int w, int l) { V::faces(L, t, sm, jobs, w, l, NW, tid); });
+  each([&](int tid, int w, int l) { V::edges(L, t, sm, jobs, w, l, NW, tid); });
+  each([&](int, int w, int l) { V::store(L, t, sm, w, l, NW); });
+}
+
+template <int TI, int TJ, int NW>
+void vol_rows_host(const VolLevel& L, int tiles_i, int poison)
+{
+  std::vector<float> sm(VolRows<TI, TJ, true>::BYTES / sizeof(float));
+  uint32_t nanbits = 0x7fc0dead;
+  float nanv;
+  memcpy(&nanv, &nanbits, 4);
+  for (int z = 0; z < tiles_i; z++)
+    for (int y = 0; y < L.n / TJ; y++)
+      for (int x = 0; x < L.n / kRowTK; x++) {
+        for (auto& w : sm) w = poison ? nanv : 0.0f;
+        const int A0 = (L.tile_i0 + z) * TI, B0 = y * TJ, C0 = x * kRowTK;
+        const bool edge = A0 < 1 || B0 < 1 || A0 + TI >= L.n || B0 + TJ >= L.n;
+        if (edge) vol_rows_tile_host<TI, TJ, NW, true>(L, sm.data(), A0, B0, C0);
+        else vol_rows_tile_host<TI, TJ, NW, false>(L, sm.data(), A0, B0, C0);
+      }
+}
+
 extern "C" {
+
+// random_from_draw2h (rn_volrow.cuh) against random_from_draw for one draw
+int replay_random_pair_matches(unsigned r)
+{
+  const F2 p = random_from_draw2h(r, 32767u - r);
+  const float a = random_from_draw(r), b = random_from_draw(32767u - r);
+  return memcmp(&p.a, &a, 4) == 0 && memcmp(&p.b, &b, 4) == 0;
+}
+void replay_set_reverse(int r) { g_reverse = r; }
 
 // random() of basics.h:16-19 as the kernels evaluate it (rn_math.cuh: the /32767 as a multiplication + one FMA correction)
 float replay_random_from_draw(unsigned r) { return random_from_draw(r); }
@@ -297,7 +348,8 @@ int replay_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, f
     const int n = 1 << l;
     int tiles_i = 0;
     const VolLevel L = vol_level_make(depth, l, lo, hi, grid[l], grid[l + 1], seed, amplitude, &tiles_i);
-    switch (n) {
+    if (n >= kRowMinN) vol_rows_host<kRowTI, kRowTJ, kRowWarps>(L, tiles_i, poison);
+    else switch (n) {
       case 2: vol_level_host<2, 2, 2>(L, tiles_i, poison); break;
       case 4: vol_level_host<4, 4, 4>(L, tiles_i, poison); break;
       case 8: vol_level_host<8, 8, 8>(L, tiles_i, poison); break;

@@ -42,39 +42,68 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", {}
 
 
+NCU_METRICS = os.path.join("profiles", "r02_march_kernel_ncu_metrics.json")  # written by profiles/micro/ncu_export.py from the
+# `ncu --set full` capture of THIS command's output kernel (k_march, 2049^2 -> 4097^2); refreshed whenever the kernel changes
+
+
+NCU_METRICS_VOLUME = os.path.join("profiles", "r02_vol_rows_kernel_ncu_metrics.json")  # the same for `--workload volume` (k_vol_rows, 257^3 -> 513^3)
+
+
+def _ncu_file(args):
+    if args.workload == "field" and args.depth == 12 and args.algo in (0, 2):
+        return NCU_METRICS
+    if args.workload == "volume" and args.depth == 9:
+        return NCU_METRICS_VOLUME
+    return None
+
+
+def _ncu_metrics(args):
+    try:
+        return json.load(open(os.path.join(ROOT, _ncu_file(args))))
+    except Exception:
+        return None
+
+
+def _mbytes(entry):
+    v, unit = float(entry[0]), entry[1].lower()
+    return v * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+
+
 def alu_roofline(args, value_gs, kernel_ms, my_samples, sm_mhz):
     """The instruction-issue ("ALU") bound of the output kernel: thread instructions per sample counted by ncu on the
-    committed capture (profiles/r01zz_stream_kernel_ncu_metrics.json) against 148 SMs x 4 schedulers x 32 lanes x the SM clock
-    seen during this run.  The bit-exact contract forbids FMA contraction, so this bound sits below the HBM-write bound."""
+    committed capture of this command (NCU_METRICS) against 148 SMs x 4 schedulers x 32 lanes x the SM clock seen during this
+    run.  The bit-exact contract forbids FMA contraction, so this bound sits near the HBM-write bound."""
+    d = _ncu_metrics(args)
+    if not d:
+        return None
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01zz_stream_kernel_ncu_metrics.json")))
-        if args.workload != "field" or args.depth != 12:
-            return None
         warp_inst = float(d["smsp__inst_executed.sum"][0])
         lanes = float(d["smsp__thread_inst_executed_per_inst_executed.ratio"][0])
         side = (1 << args.depth) + 1
-        inst_per_sample = warp_inst * lanes / (side * side)
+        inst_per_sample = warp_inst * lanes / (side ** 3 if args.workload == "volume" else side * side)
         mhz = float(sm_mhz or 1965.0)
         peak = 148 * 4 * 32 * mhz * 1e6           # thread instructions / s
         bound = peak / inst_per_sample / 1e9      # Gsamples/s of the output kernel at 100 % issue
         achieved = my_samples / (kernel_ms * 1e-3) / 1e9
         return {"bound": "issue", "thread_inst_per_sample": inst_per_sample, "peak_thread_inst_per_s": peak,
                 "gsamples_bound": bound, "achieved_gsamples_kernel": achieved, "frac": achieved / bound,
-                "source": "profiles/r01zz_stream_kernel_ncu_metrics.json (ncu --set full, k_stream<128,8>)"}
+                "ncu": {"issue_active_pct": float(d["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+                        "l1tex_lsu_wavefronts_pct": float(d["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"][0]),
+                        "pipe_fma_pct": float(d["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"][0]),
+                        "pipe_alu_pct": float(d["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"][0])},
+                "source": _ncu_file(args) + " (ncu --set full, " + d["kernel"][0] + ")"}
     except Exception:
         return None
 
 
 def ncu_traffic(args):
     """dram__bytes_read.sum + dram__bytes_write.sum of the output-stage kernel per launch, from the committed
-    `ncu --set full` capture of this command (profiles/roofline_traffic.json); None for other workloads."""
+    `ncu --set full` capture of this command (NCU_METRICS); None for other workloads."""
+    d = _ncu_metrics(args)
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        if args.workload == "field" and args.depth == d.get("depth"):
-            return d.get("dram_bytes_per_launch")
+        return int(_mbytes(d["dram__bytes_read.sum"]) + _mbytes(d["dram__bytes_write.sum"])) if d else None
     except Exception:
-        pass
-    return None
+        return None
 
 
 # --------------------------------------------------------------------------- clocks ---
@@ -278,9 +307,13 @@ def workload_config(args):
 
 def final_kernel_name(args):
     """The kernel that writes the output of this workload (rn_plan.h: plan_stages)."""
-    if args.workload == "volume":
-        return "rn_volume.cu (3D extension)"
     d = args.depth
+    if args.workload == "volume":
+        half, full = (1 << (d - 1)) + 1, (1 << d) + 1
+        if d >= 7:
+            return (f"k_vol_rows<4,4,8> (3D extension, warp-row tile kernel, last level {half}^3 -> {full}^3: cube centres, face centres, edge "
+                    "midpoints of a 4 x 4 x 64-cell tile in shared memory, 32-bit lattice hash, packed FP32 pairs, full-row stores)")
+        return f"k_vol_level (3D extension, thread-per-cell tile kernel, last level {half}^3 -> {full}^3)"
     half, full = (1 << (d - 1)) + 1, (1 << d) + 1
     if d >= 10:
         if args.algo == 3:
@@ -459,12 +492,15 @@ def run_ours(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     ev[0].record()
+    t_host0 = time.perf_counter()
     for k in range(args.steps):
         step()
         ev[k + 1].record()
+    host_enqueue_us = (time.perf_counter() - t_host0) / args.steps * 1e6  # host time per step of the asynchronous calls
     barrier()
     clocks = sampler.stop() if rank == 0 else None  # sampled during the timed region only
     total_ms = ev[0].elapsed_time(ev[-1])
+    own_total_ms = total_ms
     per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     launches = ctx.launches - launches0
     # per-launch device time of the stage chain (CUDA events on the launching stream), measured
@@ -482,6 +518,20 @@ def run_ours(args):
             mean = [statistics.mean(a[k] for a in acc) for k in range(ns)]
             stage_ms = {"launch_ms": mean, "final_ms": mean[-1], "final_name": final_kernel_name(args),
                         "share_of_chain": mean[-1] / sum(mean)}
+
+    # ---- one call at a time (what Core::init does, Core.cpp:65): no call in flight underneath, so nothing of the stage chain is hidden ----
+    single_ms = None
+    if args.workload in ("field", "volume"):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lat = []
+        for _ in range(10):
+            torch.cuda.synchronize()
+            e0.record()
+            step()
+            e1.record()
+            torch.cuda.synchronize()
+            lat.append(e0.elapsed_time(e1))
+        single_ms = statistics.median(lat)
 
     # ---- e2e: the same C-ABI call with a HOST destination (pinned), D2H inside the timed region ----
     e2e_steps = max(2, min(args.steps, 5))
@@ -543,7 +593,12 @@ def run_ours(args):
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         total_ms, e2e_s, all_samples, all_e2e_samples = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tsum[3])
+        mine = torch.tensor([own_total_ms / args.steps, host_enqueue_us], device="cuda", dtype=torch.float64)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = {"ms_per_step": [round(float(x[0]), 5) for x in every], "host_enqueue_us_per_step": [round(float(x[1]), 1) for x in every]}
     else:
+        per_rank = {"ms_per_step": [round(own_total_ms / args.steps, 5)], "host_enqueue_us_per_step": [round(host_enqueue_us, 1)]}
         all_samples, all_e2e_samples = float(my_samples), float(e2e_samples)
 
     if rank == 0:
@@ -578,7 +633,12 @@ def run_ours(args):
                      "note": "same call, destination from plain malloc (rank 0's own figure)"}},
             "gpu_launches": int(launches), "clocks": clocks, "algorithm": args.algo,
             "per_step_ms": {"min": min(per_step), "median": statistics.median(per_step), "max": max(per_step)},
+            "per_rank": per_rank,  # each rank's own device time per step (value uses the max) and the host time of one asynchronous call
         }
+        if single_ms:
+            line["single_call"] = {"ms": single_ms, "value": my_samples / (single_ms * 1e-3) / 1e9, "unit": "Gsamples/s",
+                                   "note": "one asynchronous call between two device synchronisations (rank 0): the latency of an isolated call; "
+                                           "`value` above is the steady state of back-to-back calls, whose coarse stages overlap the previous call's output kernel"}
         if strong:
             line["strong"] = strong
         if stage_ms:

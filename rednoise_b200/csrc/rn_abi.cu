@@ -670,7 +670,11 @@ int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, floa
   // ordered by the stream they are given)
   int st = ensure(&ctx->plane, &ctx->plane_bytes, volume_scratch_bytes(p->depth, i0, ni));
   if (st != RN_OK) return st;
-  RN_CUDA(volume_generate(slab, ctx->plane, p->depth, p->seed, p->amplitude, i0, ni, stream, &ctx->launches));
+  if (ctx->profiling && !ctx->ev[0])
+    for (int k = 0; k < 17; k++) RN_CUDA(cudaEventCreate(&ctx->ev[k]));
+  ctx->ev_stages = 0;
+  RN_CUDA(volume_generate(slab, ctx->plane, p->depth, p->seed, p->amplitude, i0, ni, stream, &ctx->launches, ctx->profiling ? ctx->ev : nullptr,
+                          ctx->profiling ? &ctx->ev_stages : nullptr));
   if (!stream_v) RN_CUDA(cudaStreamSynchronize(stream));
   return RN_OK;
 }

@@ -52,8 +52,9 @@ constexpr int kMarchCols = 60;  // cell columns a warp finishes
 //           column -- and its column k0+1 at [kRingOdd + l]
 //   state   two banks (step parity) of the values a step hands to the next: element e of lane l at [e][l]
 //   const   per-lane constants: the squared column distances of the lane's four output columns from the volcano
-constexpr int kRingOdd = 34;     // (33 even-column entries, padded to an even count)
-constexpr int kRingRowE4 = 66;
+constexpr int kRingOdd = 36;     // 33 even-column entries; 36 = 4 (mod 8): the even and the odd columns a quarter-warp's coalesced
+                                 // cp.async writes (4 + 4 elements) fall on disjoint banks
+constexpr int kRingRowE4 = 68;
 constexpr int kRingE4 = 4 * kRingRowE4;
 enum { S_C0 = 0, S_C1, S_C2, S_M1A, S_M1B, S_TS, S_TD, S_TE, S_COUNT };  // C(u; k0-1, k0, k1), M1(u; k0, k1), TS(u; 4),
                                                                           // {TD1(u; 3), sg(u, k0)}, {TD2(u-1; 3), sg(u, k1)}
@@ -63,12 +64,13 @@ constexpr int kConstE4 = kStateE4 + 2 * kBankE4;
 constexpr int kWarpE4 = kConstE4 + 32;  // 808 E4 = 12.6 KB per warp
 RN_HD E4* ring_row(E4* wsm, int r) { return wsm + (r & 3) * kRingRowE4; }
 RN_HD const E4& ring_at(const E4* row_lane, int q) { return row_lane[q == 1 ? kRingOdd : (q >> 1)]; }  // row_lane = ring_row(wsm, r) + lane
+RN_HD int ring_slot(int e) { return (e & 1) ? kRingOdd + (e >> 1) : (e >> 1); }  // ring entry of the warp's lattice column L0 + e, e = 0 .. 64
 RN_HD E4* state_at(E4* wsm, int bank, int e, int lane) { return wsm + kStateE4 + bank * kBankE4 + e * 32 + lane; }
 
 // registers of a lane: what lives across steps, and what one phase of a step hands to the next
 struct MarchLane {
   uint32_t sS, sD1, sD2;  // LCG states whose extraction is the draw of column k0's next S / loop-1 / loop-2 call
-  const E4* src;   // lattice (row of the next cp.async, column k0)
+  const E4* src;   // lattice (row of the next cp.async, column L0 + lane)
   E4* dst;         // output (row 2(u-1), column 2*k0) of the step in progress, relative to the window
   int ok;          // bit j: output column 2*k0 + j belongs to the strip and lies inside the stored window
   // within a step
@@ -263,16 +265,17 @@ template <bool EDGE>
 struct March {
   static RN_HD int bank_of(const MarchCtx& cx, int u) { return (u - cx.ubase) & 1; }
 
-  // cp.async of lattice row r into the ring (from p = &gin[r][k0]): the lane's own two columns, lane 31 its third as well;
-  // always exactly one commit group
+  // cp.async of lattice row r into the ring (from p = &gin[r][L0 + lane]): the warp's 65 lattice columns as two coalesced
+  // runs of 32 elements (lane l copies columns L0 + l and L0 + 32 + l) and column L0 + 64 by lane 0; always exactly one
+  // commit group
   static RN_HD void prefetch_row(const StreamParams& sp, const MarchCtx& cx, E4* wsm, const E4* p, int r, int lane)
   {
     if (r <= cx.a1e + 1 && r >= 0 && r <= sp.lev.n) {  // uniform: a later step reads the row, and it exists
-      E4* slot = ring_row(wsm, r) + lane;
-      const int k0 = cx.L0 + 2 * lane, n = sp.lev.n;
-      if (!EDGE || (k0 >= 0 && k0 <= n)) ring_copy16(slot, p);
-      if (!EDGE || (k0 + 1 >= 0 && k0 + 1 <= n)) ring_copy16(slot + kRingOdd, p + 1);
-      if (lane == 31 && (!EDGE || (k0 + 2 >= 0 && k0 + 2 <= n))) ring_copy16(slot + 1, p + 2);
+      E4* row = ring_row(wsm, r);
+      const int k = cx.L0 + lane, n = sp.lev.n;
+      if (!EDGE || (k >= 0 && k <= n)) ring_copy16(row + ring_slot(lane), p);
+      if (!EDGE || (k + 32 >= 0 && k + 32 <= n)) ring_copy16(row + ring_slot(lane + 32), p + 32);
+      if (lane == 0 && (!EDGE || (k + 64 >= 0 && k + 64 <= n))) ring_copy16(row + ring_slot(64), p + 64);
     }
     ring_commit();
   }
@@ -313,7 +316,7 @@ struct March {
     }
     wsm[kConstE4 + lane] = E4{fy2[0], fy2[1], fy2[2], fy2[3]};
     // (both pointers may start outside their grids; they are only dereferenced where the row / column exists)
-    L.src = cx.gin + ((ptrdiff_t)u0 * (ptrdiff_t)sp.gin_pitch + (ptrdiff_t)k0);
+    L.src = cx.gin + ((ptrdiff_t)u0 * (ptrdiff_t)sp.gin_pitch + (ptrdiff_t)(cx.L0 + lane));
     L.dst = cx.gout + ((ptrdiff_t)(2 * (u0 - 1) - sp.win_i0) * (ptrdiff_t)sp.gout_pitch + (ptrdiff_t)(2 * k0 - sp.win_j0));  // the first step finishes cell row u0 - 1
     for (int b = 0; b < 2; b++) {  // rows u0, u0+1: one commit group each; step u requests row u+2
       prefetch_row(sp, cx, wsm, L.src, u0 + b, lane);

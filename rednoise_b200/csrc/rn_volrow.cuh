@@ -98,20 +98,19 @@ RN_HD void vol_copy_wait()
 }
 
 // ---- the static job tables ----
-// One row job = one fine (i, j) row of one sample class for the 64 cells of the tile along k.
+// One row job = one fine (i, j) row of one sample class for the 64 cells of the tile along k.  The table lives in constant
+// memory (rn_volume.cu): a warp reads its job with a warp-uniform index, i.e. through the constant cache.
 enum { J_CUBE = 0, J_FK, J_FI, J_FJ, J_EI, J_EJ, J_EK };
 struct RowJob {
-  int base;  // G::row(2a, 2b): the image row of the cell row's low corner
-  int fiw;   // word offset of the hash table entry of the job's fine i (FI[fi])
-  int fjw;   // ... of its fine j (FJ[fj])
-  int ab;    // (a + 1) | (b + 1) << 8 | class << 16
+  int where;  // G::row(2a, 2b), the image row of the cell row's low corner, | word offset of the FH entry of the job's own fine row << 16
+  int ab;     // (a + 1) | (b + 1) << 8 | class << 16
 };
 template <int TI, int TJ, bool EDGE>
 struct RowJobs {
   static constexpr int X = EDGE ? 1 : 0;
   static constexpr int MAX = 7 * (TI + 1) * (TJ + 1);
   RowJob j[MAX];
-  int n_cubes, n_faces, n_all;  // cubes [0, n_cubes), faces [n_cubes, n_faces), edges [n_faces, n_all)
+  int c0[8];  // the jobs of class c: [c0[c], c0[c + 1]); cubes first, then the faces, then the edges
 };
 template <int TI, int TJ, bool EDGE>
 constexpr RowJobs<TI, TJ, EDGE> make_row_jobs()
@@ -125,19 +124,16 @@ constexpr RowJobs<TI, TJ, EDGE> make_row_jobs()
   const int a0[7] = {-1, -1, 0, -1, 0, 0, 0}, a1[7] = {TI, TI, TI + X, TI, TI, TI + X, TI + X};
   const int b0[7] = {-1, -1, -1, 0, 0, 0, 0}, b1[7] = {TJ, TJ, TJ, TJ + X, TJ + X, TJ, TJ + X};
   for (int cls = 0; cls < 7; cls++) {
+    t.c0[cls] = n;
     for (int a = a0[cls]; a < a1[cls]; a++)
       for (int b = b0[cls]; b < b1[cls]; b++) {
         if (!EDGE && cls == J_FK && a < 0 && b < 0) continue;  // no edge of the tile reads that face row
-        t.j[n].base = G::row(2 * a, 2 * b);
-        t.j[n].fiw = G::WORDS + (2 * a + pi[cls] + 2);
-        t.j[n].fjw = G::WORDS + G::NI + (2 * b + pj[cls] + 2);
+        t.j[n].where = G::row(2 * a, 2 * b) | ((G::WORDS + (2 * a + pi[cls] + 2) * G::NJ + (2 * b + pj[cls] + 2)) << 16);
         t.j[n].ab = (a + 1) | ((b + 1) << 8) | (cls << 16);
         n++;
       }
-    if (cls == J_CUBE) t.n_cubes = n;
-    if (cls == J_FJ) t.n_faces = n;
   }
-  t.n_all = n;
+  t.c0[7] = n;
   return t;
 }
 
@@ -146,8 +142,9 @@ struct VolRows {
   using G = RowGeo<TI, TJ>;
   using Jobs = RowJobs<TI, TJ, EDGE>;
   static constexpr int X = EDGE ? 1 : 0;  // closing rows (fine index 2T) may be owned
-  static constexpr int HASH = G::WORDS;   // FI[NI], FJ[NJ]: xs16 of the i / j term of the lattice hash of every fine row of the image
-  static constexpr size_t BYTES = (size_t)(G::WORDS + G::NI + G::NJ) * sizeof(float);
+  static constexpr int HASH = G::WORDS;   // FH[NI][NJ]: xs16(seed ^ i term) ^ xs16(j term) of the lattice hash of every fine row of the image
+  static constexpr size_t BYTES = (size_t)(G::WORDS + G::NI * G::NJ) * sizeof(float);
+  static_assert(G::WORDS + G::NI * G::NJ < 65536, "RowJob::where packs two 16-bit word offsets");
 
   struct Tile {
     int A0, B0, C0, n;
@@ -244,18 +241,25 @@ struct VolRows {
   static RN_HD void load(const VolLevel& L, const Tile& t, float* sm, int warp, int lane, int nw, int tid)
   {
     uint32_t* hash = reinterpret_cast<uint32_t*>(sm + HASH);
-    if (tid < G::NI) hash[tid] = xs16(L.seed ^ ((uint32_t)(2 * t.A0 + tid - 2) * L.ci));
-    else if (tid >= 32 && tid < 32 + G::NJ) hash[G::NI + tid - 32] = xs16((uint32_t)(2 * t.B0 + tid - 34) * L.cj);
+    for (int q = tid; q < G::NI * G::NJ; q += nw * 32) {
+      const int fi = q / G::NJ, fj = q - fi * G::NJ;
+      hash[q] = xs16(L.seed ^ ((uint32_t)(2 * t.A0 + fi - 2) * L.ci)) ^ xs16((uint32_t)(2 * t.B0 + fj - 2) * L.cj);
+    }
+    // lattice rows (a, b), a = -1 .. TI, b = -1 .. TJ, round-robin over the warps; columns c = -1 .. 64 of a row: lane - 1, lane + 31
+    // and (lanes 0, 1) 63, 64.  Row addresses advance from one base pointer (never dereferenced where the row does not exist).
     const size_t m = (size_t)t.n + 1;
+    const float* src0 = L.gin + (((size_t)(t.A0 - L.in_lo) * m + (size_t)t.B0) * m + (size_t)t.C0 + (size_t)lane);
+    const ptrdiff_t sa = (ptrdiff_t)(m * m), sb = (ptrdiff_t)m;
+    float* dst0 = sm + G::EOFF + lane;
+    const bool c_lo = !(t.k_first && lane == 0);
     for (int r = warp; r < (TI + 2) * (TJ + 2); r += nw) {
-      const int a = r / (TJ + 2) - 1, b = r % (TJ + 2) - 1;
-      const int ga = t.A0 + a, gb = t.B0 + b;
-      if (EDGE && (ga < 0 || gb < 0)) continue;
-      const float* src = L.gin + ((size_t)(ga - L.in_lo) * m + (size_t)gb) * m + (size_t)t.C0 + lane;
-      float* dst = sm + G::row(2 * a, 2 * b) + G::EOFF + lane;
-      if (!(t.k_first && lane == 0)) vol_copy4(dst - 1, src - 1);  // c = lane - 1: -1 .. 30
-      vol_copy4(dst + 31, src + 31);                                // c = lane + 31: 31 .. 62
-      if (lane < 2) vol_copy4(dst + 63, src + 63);                  // c = 63, 64
+      const int a = r / (TJ + 2) - 1, b = r - (a + 1) * (TJ + 2) - 1;
+      if (EDGE && (t.A0 + a < 0 || t.B0 + b < 0)) continue;
+      const float* src = src0 + ((ptrdiff_t)a * sa + (ptrdiff_t)b * sb);
+      float* dst = dst0 + G::row(2 * a, 2 * b);
+      if (c_lo) vol_copy4(dst - 1, src - 1);            // c = lane - 1: -1 .. 30
+      vol_copy4(dst + 31, src + 31);                    // c = lane + 31: 31 .. 62
+      if (lane < 2) vol_copy4(dst + 63, src + 63);      // c = 63, 64
     }
     vol_copy_wait();
   }
@@ -314,24 +318,17 @@ struct VolRows {
   }
   static RN_HD F2 rc_o(const Row& r) { return EDGE ? f2s(rcp_of(r.cnt)) : f2s(1.0f / 6.0f); }
 
-  // job q of the table -> Row; false: the row does not exist or nothing reads it (EDGE only)
-  static RN_HD bool row_of(const Tile& t, const float* sm, const RowJob* jobs, int q, Row* r, int* cls)
+  // table entry -> Row; false: the row does not exist or nothing reads it (EDGE only)
+  static RN_HD bool row_of(const Tile& t, const float* sm, const RowJob& j, Row* r)
   {
-#if defined(__CUDA_ARCH__)
-    const int4 v = __ldg(reinterpret_cast<const int4*>(jobs + q));
-    const RowJob j{v.x, v.y, v.z, v.w};
-#else
-    const RowJob j = jobs[q];
-#endif
     const uint32_t* w = reinterpret_cast<const uint32_t*>(sm);
-    r->base = j.base;
-    r->fh = w[j.fiw] ^ w[j.fjw];
-    *cls = j.ab >> 16;
+    r->base = j.where & 0xffff;
+    r->fh = w[j.where >> 16];
     r->cnt = 6;
     r->hi_i = false;
     r->hi_j = false;
     if (!EDGE) return true;
-    const int a = (j.ab & 0xff) - 1, b = ((j.ab >> 8) & 0xff) - 1, c = *cls;
+    const int a = (j.ab & 0xff) - 1, b = ((j.ab >> 8) & 0xff) - 1, c = j.ab >> 16;
     const int ga = t.A0 + a, gb = t.B0 + b, N2 = 2 * t.n;
     r->hi_i = a == TI;
     r->hi_j = b == TJ;
@@ -341,6 +338,17 @@ struct VolRows {
     const int ti = (ga > 0 ? 1 : 0) + (2 * ga < N2 ? 1 : 0), tj = (gb > 0 ? 1 : 0) + (2 * gb < N2 ? 1 : 0);  // neighbours at fine i -+ 1 / j -+ 1 of an even row
     r->cnt = c == J_FI || c == J_EJ ? 4 + ti : (c == J_FJ || c == J_EI ? 4 + tj : (c == J_EK ? 2 + ti + tj : 6));
     return true;
+  }
+  // the jobs of class `cls` that fall to this warp: the round-robin runs on across the class boundaries (job q goes to warp
+  // q mod nw, nw a power of two), so that every phase stays balanced without a per-job switch on the class
+  template <class F>
+  static RN_HD void for_jobs(const Tile& t, const float* sm, const Jobs& jobs, int cls, int warp, int nw, F&& f)
+  {
+    const int b = jobs.c0[cls], e = jobs.c0[cls + 1];
+    for (int q = b + ((warp - b) & (nw - 1)); q < e; q += nw) {
+      Row r;
+      if (row_of(t, sm, jobs.j[q], &r)) f(r);
+    }
   }
 
   // ------------------------------------------------------------------ the seven row routines ----
@@ -442,57 +450,46 @@ struct VolRows {
   static constexpr int NFI = (TI + X) * (TJ + 1), NFJ = (TI + 1) * (TJ + X);
   static constexpr int NEI = TI * (TJ + X), NEJ = (TI + X) * TJ;
 
+  // (the column jobs go to the LAST threads of the block: with 8 warps the first warps carry one row job more)
   static RN_HD void cubes(const VolLevel& L, const Tile& t, float* sm, const Jobs& jobs, int warp, int lane, int nw, int tid)
   {
     const LaneK k = lane_k(L, t, lane);
-    for (int q = warp; q < jobs.n_cubes; q += nw) {
-      Row r;
-      int cls;
-      if (!row_of(t, sm, jobs.j, q, &r, &cls)) continue;
-      cube_row(L, sm, k, r);
-    }
-    if (tid < NC) halo_column<1, 1>(L, t, sm, 2 * (tid / (TJ + 1) - 1) + 1, 2 * (tid % (TJ + 1) - 1) + 1);
+    for_jobs(t, sm, jobs, J_CUBE, warp, nw, [&](const Row& r) { cube_row(L, sm, k, r); });
+    const int ct = nw * 32 - 1 - tid;
+    if (ct < NC) halo_column<1, 1>(L, t, sm, 2 * (ct / (TJ + 1) - 1) + 1, 2 * (ct % (TJ + 1) - 1) + 1);
   }
   static RN_HD void faces(const VolLevel& L, const Tile& t, float* sm, const Jobs& jobs, int warp, int lane, int nw, int tid)
   {
     const LaneK k = lane_k(L, t, lane);
-    for (int q = jobs.n_cubes + warp; q < jobs.n_faces; q += nw) {
-      Row r;
-      int cls;
-      if (!row_of(t, sm, jobs.j, q, &r, &cls)) continue;
-      if (cls == J_FK) face_k_row(L, sm, k, r);
-      else if (cls == J_FI) face_i_row(L, sm, k, r);
-      else face_j_row(L, sm, k, r);
-    }
+    for_jobs(t, sm, jobs, J_FK, warp, nw, [&](const Row& r) { face_k_row(L, sm, k, r); });
+    for_jobs(t, sm, jobs, J_FI, warp, nw, [&](const Row& r) { face_i_row(L, sm, k, r); });
+    for_jobs(t, sm, jobs, J_FJ, warp, nw, [&](const Row& r) { face_j_row(L, sm, k, r); });
     // column jobs: O(-1) of the normal-i and normal-j faces, E(64) of the normal-k faces on the closing plane
-    if (tid < NFI) {
-      const int a = tid / (TJ + 1), b = tid % (TJ + 1) - 1;
+    const int ct = nw * 32 - 1 - tid;
+    if (ct < NFI) {
+      const int a = ct / (TJ + 1), b = ct % (TJ + 1) - 1;
       if (!(EDGE && a == TI && !t.close_i)) halo_column<0, 1>(L, t, sm, 2 * a, 2 * b + 1);
-    } else if (tid < NFI + NFJ) {
-      const int q = tid - NFI, a = q / (TJ + X) - 1, b = q % (TJ + X);
+    } else if (ct < NFI + NFJ) {
+      const int q = ct - NFI, a = q / (TJ + X) - 1, b = q % (TJ + X);
       if (!(EDGE && b == TJ && !t.close_j)) halo_column<1, 0>(L, t, sm, 2 * a + 1, 2 * b);
-    } else if (tid < NFI + NFJ + NC) {
-      const int q = tid - NFI - NFJ;
+    } else if (ct < NFI + NFJ + NC) {
+      const int q = ct - NFI - NFJ;
       if (t.k_last) generic_sample<1, 1, 0>(L, t, sm, 2 * (q / (TJ + 1) - 1) + 1, 2 * (q % (TJ + 1) - 1) + 1, 2 * G::TK);
     }
   }
   static RN_HD void edges(const VolLevel& L, const Tile& t, float* sm, const Jobs& jobs, int warp, int lane, int nw, int tid)
   {
     const LaneK k = lane_k(L, t, lane);
-    for (int q = jobs.n_faces + warp; q < jobs.n_all; q += nw) {
-      Row r;
-      int cls;
-      if (!row_of(t, sm, jobs.j, q, &r, &cls)) continue;
-      if (cls == J_EI) edge_i_row(L, sm, k, r);
-      else if (cls == J_EJ) edge_j_row(L, sm, k, r);
-      else edge_k_row(L, sm, k, r);
-    }
+    for_jobs(t, sm, jobs, J_EI, warp, nw, [&](const Row& r) { edge_i_row(L, sm, k, r); });
+    for_jobs(t, sm, jobs, J_EJ, warp, nw, [&](const Row& r) { edge_j_row(L, sm, k, r); });
+    for_jobs(t, sm, jobs, J_EK, warp, nw, [&](const Row& r) { edge_k_row(L, sm, k, r); });
     if (t.k_last) {  // E(64) of the edges along i and along j on the closing plane
-      if (tid < NEI) {
-        const int a = tid / (TJ + X), b = tid % (TJ + X);
+      const int ct = nw * 32 - 1 - tid;
+      if (ct < NEI) {
+        const int a = ct / (TJ + X), b = ct % (TJ + X);
         if (!(EDGE && b == TJ && !t.close_j)) generic_sample<1, 0, 0>(L, t, sm, 2 * a + 1, 2 * b, 2 * G::TK);
-      } else if (tid < NEI + NEJ) {
-        const int q = tid - NEI, a = q / TJ, b = q % TJ;
+      } else if (ct < NEI + NEJ) {
+        const int q = ct - NEI, a = q / TJ, b = q % TJ;
         if (!(EDGE && a == TI && !t.close_i)) generic_sample<0, 1, 0>(L, t, sm, 2 * a, 2 * b + 1, 2 * G::TK);
       }
     }
@@ -513,9 +510,12 @@ struct VolRows {
       for (int fi = lo; fi <= hi; fi++) {
 #pragma unroll
         for (int q = 0; q < 4; q++) dst[32 * q] = src[16 * q];
-        if (t.k_last && lane == 0) dst[2 * G::TK] = src[G::EOFF + G::TK - src0];
         src += G::NJ * G::PK;
         dst += plane;
+      }
+      if (t.k_last && lane <= hi - lo) {  // the closing column k = W: lane q stores it for fine row lo + q
+        const float* cs = sm + G::row(lo + lane, warp) + G::EOFF + G::TK;
+        L.gout[(size_t)(2 * t.A0 + lo + lane - L.out_lo) * plane + (size_t)(2 * t.B0 + warp) * M + (size_t)(2 * t.C0) + (size_t)(2 * G::TK)] = *cs;
       }
       return;
     }

@@ -56,9 +56,9 @@ cudaError_t launch_level(const VolLevel& L, int tiles_i, cudaStream_t stream)
 
 // The warp-row kernel (rn_volrow.cuh): levels with n >= kRowMinN cells per axis.  NW warps; the phases of a level are separated
 // by block barriers, the row jobs of a phase go round-robin over the warps.  The job tables are compile-time constants in
-// global memory.
-__device__ constexpr RowJobs<kRowTI, kRowTJ, false> g_jobs_lean = make_row_jobs<kRowTI, kRowTJ, false>();
-__device__ constexpr RowJobs<kRowTI, kRowTJ, true> g_jobs_edge = make_row_jobs<kRowTI, kRowTJ, true>();
+// constant memory (a warp reads its job with a warp-uniform index).
+__constant__ constexpr RowJobs<kRowTI, kRowTJ, false> g_jobs_lean = make_row_jobs<kRowTI, kRowTJ, false>();
+__constant__ constexpr RowJobs<kRowTI, kRowTJ, true> g_jobs_edge = make_row_jobs<kRowTI, kRowTJ, true>();
 
 template <int TI, int TJ, int NW>
 __global__ void __launch_bounds__(NW * 32) k_vol_rows(const __grid_constant__ VolLevel L)
@@ -131,8 +131,9 @@ size_t volume_scratch_bytes(int depth, int i0, int ni)
 
 // Planes [i0, i0+ni) of the (W+1)^3 volume into `slab` (device memory, ni x (W+1) x (W+1) floats, dense); scratch:
 // volume_scratch_bytes(depth, i0, ni) bytes of device memory.
+// events (optional, depth entries): events[0] is recorded before the first level, events[l] after level l; *nstages = depth - 1.
 cudaError_t volume_generate(float* slab, void* scratch, int depth, uint32_t seed, float amplitude, int i0, int ni, cudaStream_t stream,
-                            uint64_t* launches)
+                            uint64_t* launches, cudaEvent_t* events, int* nstages)
 {
   int lo[32], hi[32];
   volume_ranges(depth, i0, ni, lo, hi);
@@ -147,6 +148,8 @@ cudaError_t volume_generate(float* slab, void* scratch, int depth, uint32_t seed
   // level 1: the 27 points at multiples of W/2 start at 0
   cudaError_t e = cudaMemsetAsync(grid[1], 0, (size_t)(hi[1] - lo[1] + 1) * 9 * sizeof(float), stream);
   if (e != cudaSuccess) return e;
+  if (events && (e = cudaEventRecord(events[0], stream)) != cudaSuccess) return e;
+  if (nstages) *nstages = depth - 1;
   for (int l = 1; l < depth; l++) {
     const int n = 1 << l;
     int tiles_i = 0;
@@ -155,10 +158,15 @@ cudaError_t volume_generate(float* slab, void* scratch, int depth, uint32_t seed
     else switch (n) {
       case 2: e = launch_level<2, 2, 2, 64>(L, tiles_i, stream); break;
       case 4: e = launch_level<4, 4, 4, 128>(L, tiles_i, stream); break;
+#if RN_VOL_COARSE_TILE == 4
+      default: e = launch_level<4, 4, 4, 128>(L, tiles_i, stream); break;
+#else
       case 8: e = launch_level<8, 8, 8, kVolThreads>(L, tiles_i, stream); break;
       default: e = launch_level<kVolTI, kVolTJ, kVolTK, kVolThreads>(L, tiles_i, stream); break;
+#endif
     }
     if (e != cudaSuccess) return e;
+    if (events && (e = cudaEventRecord(events[l], stream)) != cudaSuccess) return e;
     if (launches) *launches += 1;
   }
   return cudaSuccess;

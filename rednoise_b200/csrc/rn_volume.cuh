@@ -261,7 +261,12 @@ constexpr int kRowTI = 4, kRowTJ = 4, kRowTK = 64, kRowWarps = 8;
 constexpr int kRowMinN = 64;
 
 // tile extent along i of the level whose input grid has n cells per axis
-inline int vol_tile_i(int n) { return n >= kRowMinN ? kRowTI : (n >= 16 ? kVolTI : n); }
+// the coarse levels (8 <= n < kRowMinN) are latency-bound -- a handful of CTAs, each walking its tile phase by phase: 4 x 4 x 4-cell tiles
+// with 128 threads give 8x more, 8x shorter CTAs than the 8 x 8 x 16 tile (RN_VOL_COARSE_TILE 8, the first form)
+#ifndef RN_VOL_COARSE_TILE
+#define RN_VOL_COARSE_TILE 4
+#endif
+inline int vol_tile_i(int n) { return n >= kRowMinN ? kRowTI : (n <= 4 ? n : (RN_VOL_COARSE_TILE == 4 ? 4 : (n >= 16 ? kVolTI : n))); }
 
 
 // Plane ranges: lo[l], hi[l] = the planes (lattice index along i) of the level-l grid (side 2^l + 1) that the slab

@@ -352,8 +352,12 @@ int replay_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, f
     else switch (n) {
       case 2: vol_level_host<2, 2, 2>(L, tiles_i, poison); break;
       case 4: vol_level_host<4, 4, 4>(L, tiles_i, poison); break;
+#if RN_VOL_COARSE_TILE == 4
+      default: vol_level_host<4, 4, 4>(L, tiles_i, poison); break;
+#else
       case 8: vol_level_host<8, 8, 8>(L, tiles_i, poison); break;
       default: vol_level_host<kVolTI, kVolTJ, kVolTK>(L, tiles_i, poison); break;
+#endif
     }
   }
   return 0;

@@ -249,13 +249,13 @@ struct VolRows {
     // and (lanes 0, 1) 63, 64.  Row addresses advance from one base pointer (never dereferenced where the row does not exist).
     const size_t m = (size_t)t.n + 1;
     const float* src0 = L.gin + (((size_t)(t.A0 - L.in_lo) * m + (size_t)t.B0) * m + (size_t)t.C0 + (size_t)lane);
-    const ptrdiff_t sa = (ptrdiff_t)(m * m), sb = (ptrdiff_t)m;
+    const int sa = (int)(m * m), sb = (int)m;  // 32-bit row offsets: (TI + 1) * (n + 1)^2 < 2^31 for every level (n <= 1024)
     float* dst0 = sm + G::EOFF + lane;
     const bool c_lo = !(t.k_first && lane == 0);
     for (int r = warp; r < (TI + 2) * (TJ + 2); r += nw) {
       const int a = r / (TJ + 2) - 1, b = r - (a + 1) * (TJ + 2) - 1;
       if (EDGE && (t.A0 + a < 0 || t.B0 + b < 0)) continue;
-      const float* src = src0 + ((ptrdiff_t)a * sa + (ptrdiff_t)b * sb);
+      const float* src = src0 + (a * sa + b * sb);
       float* dst = dst0 + G::row(2 * a, 2 * b);
       if (c_lo) vol_copy4(dst - 1, src - 1);            // c = lane - 1: -1 .. 30
       vol_copy4(dst + 31, src + 31);                    // c = lane + 31: 31 .. 62
@@ -339,109 +339,112 @@ struct VolRows {
     r->cnt = c == J_FI || c == J_EJ ? 4 + ti : (c == J_FJ || c == J_EI ? 4 + tj : (c == J_EK ? 2 + ti + tj : 6));
     return true;
   }
-  // the jobs of class `cls` that fall to this warp: the round-robin runs on across the class boundaries (job q goes to warp
-  // q mod nw, nw a power of two), so that every phase stays balanced without a per-job switch on the class
-  template <class F>
-  static RN_HD void for_jobs(const Tile& t, const float* sm, const Jobs& jobs, int cls, int warp, int nw, F&& f)
+  // the jobs of class CLS that fall to this warp: the round-robin runs on across the class boundaries (job q goes to warp
+  // q mod nw, nw a power of two), so that every phase stays balanced without a per-job switch on the class; two jobs at a time
+  template <int CLS>
+  static RN_HD void run_jobs(const VolLevel& L, const Tile& t, float* sm, const Jobs& jobs, const LaneK& k, int warp, int nw)
   {
-    const int b = jobs.c0[cls], e = jobs.c0[cls + 1];
-    for (int q = b + ((warp - b) & (nw - 1)); q < e; q += nw) {
+    const int b = jobs.c0[CLS], e = jobs.c0[CLS + 1];
+    int q = b + ((warp - b) & (nw - 1));
+    for (; q + nw < e; q += 2 * nw) {
+      Row r0, r1;
+      const bool ok0 = row_of(t, sm, jobs.j[q], &r0), ok1 = row_of(t, sm, jobs.j[q + nw], &r1);
+      F2 s0 = f2s(0.0f), s1 = f2s(0.0f);
+      if (ok0) s0 = row_sum<CLS>(sm, k, r0);
+      if (ok1) s1 = row_sum<CLS>(sm, k, r1);
+      if (ok0) row_put<CLS>(L, sm, k, r0, s0);
+      if (ok1) row_put<CLS>(L, sm, k, r1, s1);
+    }
+    if (q < e) {
       Row r;
-      if (row_of(t, sm, jobs.j[q], &r)) f(r);
+      if (row_of(t, sm, jobs.j[q], &r)) row_put<CLS>(L, sm, k, r, row_sum<CLS>(sm, k, r));
     }
   }
 
   // ------------------------------------------------------------------ the seven row routines ----
-  // cube centres of cell row (a, b): fine row (2a+1, 2b+1), O(c)
-  static RN_HD void cube_row(const VolLevel& L, float* sm, const LaneK& k, const Row& r)
+  // Each in two halves, so that a warp can have the shared-memory loads of TWO jobs in flight before it stores either result
+  // (the compiler cannot move a load across a store to the same image): row_sum = the neighbours in the specification's order,
+  // row_put = mean + displacement, stored to the row's own slots.
+  //   J_CUBE cube centres of cell row (a, b): fine row (2a+1, 2b+1), O(c)      J_FK face centres, normal k: (2a+1, 2b+1), E(c)
+  //   J_FI   face centres, normal i: (2a, 2b+1), O(c)                           J_FJ face centres, normal j: (2a+1, 2b), O(c)
+  //   J_EI   edge midpoints along i: (2a+1, 2b), E(c)    J_EJ along j: (2a, 2b+1), E(c)    J_EK along k: (2a, 2b), O(c)
+  template <int CLS>
+  static RN_HD F2 row_sum(const float* sm, const LaneK& k, const Row& r)
   {
-    const float* r00 = rp(sm, r, 0, 0) + G::EOFF + k.l2;
-    const float* r01 = rp(sm, r, 0, 2) + G::EOFF + k.l2;
-    const float* r10 = rp(sm, r, 2, 0) + G::EOFF + k.l2;
-    const float* r11 = rp(sm, r, 2, 2) + G::EOFF + k.l2;
-    F2 s = ld2(r00);
-    s = f2add(s, ldu(r00 + 1));
-    s = f2add(s, ld2(r01));
-    s = f2add(s, ldu(r01 + 1));
-    s = f2add(s, ld2(r10));
-    s = f2add(s, ldu(r10 + 1));
-    s = f2add(s, ld2(r11));
-    s = f2add(s, ldu(r11 + 1));
-    st2(rw(sm, r, 1, 1) + G::OOFF + k.l2, finish(L, s, f2s(0.125f), r.fh ^ k.fO0, r.fh ^ k.fO1));
+    if constexpr (CLS == J_CUBE) {
+      const float* r00 = rp(sm, r, 0, 0) + G::EOFF + k.l2;
+      const float* r01 = rp(sm, r, 0, 2) + G::EOFF + k.l2;
+      const float* r10 = rp(sm, r, 2, 0) + G::EOFF + k.l2;
+      const float* r11 = rp(sm, r, 2, 2) + G::EOFF + k.l2;
+      F2 s = ld2(r00);
+      s = f2add(s, ldu(r00 + 1));
+      s = f2add(s, ld2(r01));
+      s = f2add(s, ldu(r01 + 1));
+      s = f2add(s, ld2(r10));
+      s = f2add(s, ldu(r10 + 1));
+      s = f2add(s, ld2(r11));
+      return f2add(s, ldu(r11 + 1));
+    } else if constexpr (CLS == J_FK) {
+      const float* own = rp(sm, r, 1, 1);
+      F2 s = ld2(rp(sm, r, 0, 0) + G::EOFF + k.l2);
+      s = f2add(s, ld2(rp(sm, r, 0, 2) + G::EOFF + k.l2));
+      s = f2add(s, ld2(rp(sm, r, 2, 0) + G::EOFF + k.l2));
+      s = f2add(s, ld2(rp(sm, r, 2, 2) + G::EOFF + k.l2));
+      s = f2add(s, ldu(own + G::OOFF + k.l2 - 1));
+      return f2add(s, ld2(own + G::OOFF + k.l2));
+    } else if constexpr (CLS == J_FI) {
+      const float* r0 = rp(sm, r, 0, 0) + G::EOFF + k.l2;
+      const float* r1 = rp(sm, r, 0, 2) + G::EOFF + k.l2;
+      F2 s = ld2(r0);
+      s = f2add(s, ldu(r0 + 1));
+      s = f2add(s, ld2(r1));
+      s = f2add(s, ldu(r1 + 1));
+      s = f2add(s, ld2(rp(sm, r, -1, 1) + G::OOFF + k.l2));
+      return f2add(s, ld2(rp(sm, r, 1, 1) + G::OOFF + k.l2));
+    } else if constexpr (CLS == J_FJ) {
+      const float* r0 = rp(sm, r, 0, 0) + G::EOFF + k.l2;
+      const float* r1 = rp(sm, r, 2, 0) + G::EOFF + k.l2;
+      F2 s = ld2(r0);
+      s = f2add(s, ldu(r0 + 1));
+      s = f2add(s, ld2(r1));
+      s = f2add(s, ldu(r1 + 1));
+      s = f2add(s, ld2(rp(sm, r, 1, -1) + G::OOFF + k.l2));
+      return f2add(s, ld2(rp(sm, r, 1, 1) + G::OOFF + k.l2));
+    } else if constexpr (CLS == J_EI) {
+      const float* own = rp(sm, r, 1, 0);
+      F2 s = ld2(rp(sm, r, 0, 0) + G::EOFF + k.l2);
+      s = f2add(s, ld2(rp(sm, r, 2, 0) + G::EOFF + k.l2));
+      s = f2add(s, ld2(rp(sm, r, 1, -1) + G::EOFF + k.l2));
+      s = f2add(s, ld2(rp(sm, r, 1, 1) + G::EOFF + k.l2));
+      s = f2add(s, ldu(own + G::OOFF + k.l2 - 1));
+      return f2add(s, ld2(own + G::OOFF + k.l2));
+    } else if constexpr (CLS == J_EJ) {
+      const float* own = rp(sm, r, 0, 1);
+      F2 s = ld2(rp(sm, r, 0, 0) + G::EOFF + k.l2);
+      s = f2add(s, ld2(rp(sm, r, 0, 2) + G::EOFF + k.l2));
+      s = f2add(s, ld2(rp(sm, r, -1, 1) + G::EOFF + k.l2));
+      s = f2add(s, ld2(rp(sm, r, 1, 1) + G::EOFF + k.l2));
+      s = f2add(s, ldu(own + G::OOFF + k.l2 - 1));
+      return f2add(s, ld2(own + G::OOFF + k.l2));
+    } else {
+      const float* own = rp(sm, r, 0, 0);
+      F2 s = ld2(own + G::EOFF + k.l2);
+      s = f2add(s, ldu(own + G::EOFF + k.l2 + 1));
+      s = f2add(s, ld2(rp(sm, r, -1, 0) + G::OOFF + k.l2));
+      s = f2add(s, ld2(rp(sm, r, 1, 0) + G::OOFF + k.l2));
+      s = f2add(s, ld2(rp(sm, r, 0, -1) + G::OOFF + k.l2));
+      return f2add(s, ld2(rp(sm, r, 0, 1) + G::OOFF + k.l2));
+    }
   }
-  // face centres, normal k: fine row (2a+1, 2b+1), E(c)
-  static RN_HD void face_k_row(const VolLevel& L, float* sm, const LaneK& k, const Row& r)
+  template <int CLS>
+  static RN_HD void row_put(const VolLevel& L, float* sm, const LaneK& k, const Row& r, F2 s)
   {
-    float* own = rw(sm, r, 1, 1);
-    F2 s = ld2(rp(sm, r, 0, 0) + G::EOFF + k.l2);
-    s = f2add(s, ld2(rp(sm, r, 0, 2) + G::EOFF + k.l2));
-    s = f2add(s, ld2(rp(sm, r, 2, 0) + G::EOFF + k.l2));
-    s = f2add(s, ld2(rp(sm, r, 2, 2) + G::EOFF + k.l2));
-    s = f2add(s, ldu(own + G::OOFF + k.l2 - 1));
-    s = f2add(s, ld2(own + G::OOFF + k.l2));
-    st2(own + G::EOFF + k.l2, finish(L, s, rc_e(r, k), r.fh ^ k.fE0, r.fh ^ k.fE1));
-  }
-  // face centres, normal i: fine row (2a, 2b+1), O(c)
-  static RN_HD void face_i_row(const VolLevel& L, float* sm, const LaneK& k, const Row& r)
-  {
-    const float* r0 = rp(sm, r, 0, 0) + G::EOFF + k.l2;
-    const float* r1 = rp(sm, r, 0, 2) + G::EOFF + k.l2;
-    F2 s = ld2(r0);
-    s = f2add(s, ldu(r0 + 1));
-    s = f2add(s, ld2(r1));
-    s = f2add(s, ldu(r1 + 1));
-    s = f2add(s, ld2(rp(sm, r, -1, 1) + G::OOFF + k.l2));
-    s = f2add(s, ld2(rp(sm, r, 1, 1) + G::OOFF + k.l2));
-    st2(rw(sm, r, 0, 1) + G::OOFF + k.l2, finish(L, s, rc_o(r), r.fh ^ k.fO0, r.fh ^ k.fO1));
-  }
-  // face centres, normal j: fine row (2a+1, 2b), O(c)
-  static RN_HD void face_j_row(const VolLevel& L, float* sm, const LaneK& k, const Row& r)
-  {
-    const float* r0 = rp(sm, r, 0, 0) + G::EOFF + k.l2;
-    const float* r1 = rp(sm, r, 2, 0) + G::EOFF + k.l2;
-    F2 s = ld2(r0);
-    s = f2add(s, ldu(r0 + 1));
-    s = f2add(s, ld2(r1));
-    s = f2add(s, ldu(r1 + 1));
-    s = f2add(s, ld2(rp(sm, r, 1, -1) + G::OOFF + k.l2));
-    s = f2add(s, ld2(rp(sm, r, 1, 1) + G::OOFF + k.l2));
-    st2(rw(sm, r, 1, 0) + G::OOFF + k.l2, finish(L, s, rc_o(r), r.fh ^ k.fO0, r.fh ^ k.fO1));
-  }
-  // edge midpoints along i: fine row (2a+1, 2b), E(c)
-  static RN_HD void edge_i_row(const VolLevel& L, float* sm, const LaneK& k, const Row& r)
-  {
-    float* own = rw(sm, r, 1, 0);
-    F2 s = ld2(rp(sm, r, 0, 0) + G::EOFF + k.l2);
-    s = f2add(s, ld2(rp(sm, r, 2, 0) + G::EOFF + k.l2));
-    s = f2add(s, ld2(rp(sm, r, 1, -1) + G::EOFF + k.l2));
-    s = f2add(s, ld2(rp(sm, r, 1, 1) + G::EOFF + k.l2));
-    s = f2add(s, ldu(own + G::OOFF + k.l2 - 1));
-    s = f2add(s, ld2(own + G::OOFF + k.l2));
-    st2(own + G::EOFF + k.l2, finish(L, s, rc_e(r, k), r.fh ^ k.fE0, r.fh ^ k.fE1));
-  }
-  // edge midpoints along j: fine row (2a, 2b+1), E(c)
-  static RN_HD void edge_j_row(const VolLevel& L, float* sm, const LaneK& k, const Row& r)
-  {
-    float* own = rw(sm, r, 0, 1);
-    F2 s = ld2(rp(sm, r, 0, 0) + G::EOFF + k.l2);
-    s = f2add(s, ld2(rp(sm, r, 0, 2) + G::EOFF + k.l2));
-    s = f2add(s, ld2(rp(sm, r, -1, 1) + G::EOFF + k.l2));
-    s = f2add(s, ld2(rp(sm, r, 1, 1) + G::EOFF + k.l2));
-    s = f2add(s, ldu(own + G::OOFF + k.l2 - 1));
-    s = f2add(s, ld2(own + G::OOFF + k.l2));
-    st2(own + G::EOFF + k.l2, finish(L, s, rc_e(r, k), r.fh ^ k.fE0, r.fh ^ k.fE1));
-  }
-  // edge midpoints along k: fine row (2a, 2b), O(c)
-  static RN_HD void edge_k_row(const VolLevel& L, float* sm, const LaneK& k, const Row& r)
-  {
-    float* own = rw(sm, r, 0, 0);
-    F2 s = ld2(own + G::EOFF + k.l2);
-    s = f2add(s, ldu(own + G::EOFF + k.l2 + 1));
-    s = f2add(s, ld2(rp(sm, r, -1, 0) + G::OOFF + k.l2));
-    s = f2add(s, ld2(rp(sm, r, 1, 0) + G::OOFF + k.l2));
-    s = f2add(s, ld2(rp(sm, r, 0, -1) + G::OOFF + k.l2));
-    s = f2add(s, ld2(rp(sm, r, 0, 1) + G::OOFF + k.l2));
-    st2(own + G::OOFF + k.l2, finish(L, s, rc_o(r), r.fh ^ k.fO0, r.fh ^ k.fO1));
+    constexpr int di = (CLS == J_CUBE || CLS == J_FK || CLS == J_FJ || CLS == J_EI) ? 1 : 0;  // the row's own fine (i, j) relative to (2a, 2b)
+    constexpr int dj = (CLS == J_CUBE || CLS == J_FK || CLS == J_FI || CLS == J_EJ) ? 1 : 0;
+    constexpr bool e_class = CLS == J_FK || CLS == J_EI || CLS == J_EJ;                        // even fine k: E(c)
+    float* own = rw(sm, r, di, dj);
+    if constexpr (e_class) st2(own + G::EOFF + k.l2, finish(L, s, rc_e(r, k), r.fh ^ k.fE0, r.fh ^ k.fE1));
+    else st2(own + G::OOFF + k.l2, finish(L, s, CLS == J_CUBE ? f2s(0.125f) : rc_o(r), r.fh ^ k.fO0, r.fh ^ k.fO1));
   }
 
   // ------------------------------------------------------------------ phases 1 .. 3 ----
@@ -454,16 +457,16 @@ struct VolRows {
   static RN_HD void cubes(const VolLevel& L, const Tile& t, float* sm, const Jobs& jobs, int warp, int lane, int nw, int tid)
   {
     const LaneK k = lane_k(L, t, lane);
-    for_jobs(t, sm, jobs, J_CUBE, warp, nw, [&](const Row& r) { cube_row(L, sm, k, r); });
+    run_jobs<J_CUBE>(L, t, sm, jobs, k, warp, nw);
     const int ct = nw * 32 - 1 - tid;
     if (ct < NC) halo_column<1, 1>(L, t, sm, 2 * (ct / (TJ + 1) - 1) + 1, 2 * (ct % (TJ + 1) - 1) + 1);
   }
   static RN_HD void faces(const VolLevel& L, const Tile& t, float* sm, const Jobs& jobs, int warp, int lane, int nw, int tid)
   {
     const LaneK k = lane_k(L, t, lane);
-    for_jobs(t, sm, jobs, J_FK, warp, nw, [&](const Row& r) { face_k_row(L, sm, k, r); });
-    for_jobs(t, sm, jobs, J_FI, warp, nw, [&](const Row& r) { face_i_row(L, sm, k, r); });
-    for_jobs(t, sm, jobs, J_FJ, warp, nw, [&](const Row& r) { face_j_row(L, sm, k, r); });
+    run_jobs<J_FK>(L, t, sm, jobs, k, warp, nw);
+    run_jobs<J_FI>(L, t, sm, jobs, k, warp, nw);
+    run_jobs<J_FJ>(L, t, sm, jobs, k, warp, nw);
     // column jobs: O(-1) of the normal-i and normal-j faces, E(64) of the normal-k faces on the closing plane
     const int ct = nw * 32 - 1 - tid;
     if (ct < NFI) {
@@ -480,9 +483,9 @@ struct VolRows {
   static RN_HD void edges(const VolLevel& L, const Tile& t, float* sm, const Jobs& jobs, int warp, int lane, int nw, int tid)
   {
     const LaneK k = lane_k(L, t, lane);
-    for_jobs(t, sm, jobs, J_EI, warp, nw, [&](const Row& r) { edge_i_row(L, sm, k, r); });
-    for_jobs(t, sm, jobs, J_EJ, warp, nw, [&](const Row& r) { edge_j_row(L, sm, k, r); });
-    for_jobs(t, sm, jobs, J_EK, warp, nw, [&](const Row& r) { edge_k_row(L, sm, k, r); });
+    run_jobs<J_EI>(L, t, sm, jobs, k, warp, nw);
+    run_jobs<J_EJ>(L, t, sm, jobs, k, warp, nw);
+    run_jobs<J_EK>(L, t, sm, jobs, k, warp, nw);
     if (t.k_last) {  // E(64) of the edges along i and along j on the closing plane
       const int ct = nw * 32 - 1 - tid;
       if (ct < NEI) {

@@ -174,12 +174,21 @@ struct VolRows {
   }
 
   // ---- the generic form of the rule for ONE sample at fine tile coordinates (fi, fj, fk) of parities (PI, PJ, PK) (column
-  //      jobs): neighbours in the specification's order, existence tested on the global coordinates
-  template <int PI, int PJ, int PK_>
+  //      jobs): neighbours in the specification's order, existence tested on the global coordinates.  KPOS says where along k the
+  //      caller put the sample: 1 = the halo column fk = -1 of a tile that does not start on the face k = 0 (both neighbours along
+  //      k exist), 2 = the closing plane fk = 2 TK = the face k = W (no neighbour at fk + 1); in a lean tile every neighbour along i
+  //      and j exists, so there all the tests -- and with them the divisor -- are compile-time constants.
+  template <int PI, int PJ, int PK_, int KPOS>
   static RN_HD void generic_sample(const VolLevel& L, const Tile& t, float* sm, int fi, int fj, int fk)
   {
     const int gi = 2 * t.A0 + fi, gj = 2 * t.B0 + fj, gk = 2 * t.C0 + fk, N2 = 2 * t.n;
-    if (gi < 0 || gi > N2 || gj < 0 || gj > N2 || gk < 0 || gk > N2) return;
+    if (EDGE && (gi < 0 || gi > N2 || gj < 0 || gj > N2 || gk < 0 || gk > N2)) return;
+    auto exists = [&](int axis, int g, int sgn) -> bool {  // the neighbour at g + sgn along `axis`
+      if (!EDGE && axis < 2) return true;
+      if (!EDGE && KPOS == 1) return true;
+      if (!EDGE && KPOS == 2) return sgn < 0;
+      return !(g + sgn < 0 || g + sgn > N2);
+    };
     constexpr int odd = PI + PJ + PK_;
     float sum = 0.0f;
     int cnt = 0;
@@ -199,7 +208,7 @@ struct VolRows {
       cnt = 4;
       const int ga = a == 0 ? gi : (a == 1 ? gj : gk);
       for (int sgn = -1; sgn <= 1; sgn += 2) {
-        if (ga + sgn < 0 || ga + sgn > N2) continue;
+        if (!exists(a, ga, sgn)) continue;
         sum += a == 0 ? at(sm, fi + sgn, fj, fk) : (a == 1 ? at(sm, fi, fj + sgn, fk) : at(sm, fi, fj, fk + sgn));
         cnt++;
       }
@@ -212,7 +221,7 @@ struct VolRows {
         if (b == a) continue;
         const int gb = b == 0 ? gi : (b == 1 ? gj : gk);
         for (int sgn = -1; sgn <= 1; sgn += 2) {
-          if (gb + sgn < 0 || gb + sgn > N2) continue;
+          if (!exists(b, gb, sgn)) continue;
           sum += b == 0 ? at(sm, fi + sgn, fj, fk) : (b == 1 ? at(sm, fi, fj + sgn, fk) : at(sm, fi, fj, fk + sgn));
           cnt++;
         }
@@ -227,7 +236,7 @@ struct VolRows {
   static RN_HD void halo_column(const VolLevel& L, const Tile& t, float* sm, int fi, int fj)
   {
     if (t.k_first) *slot(sm, fi, fj, -1) = 0.0f;
-    else generic_sample<PI, PJ, 1>(L, t, sm, fi, fj, -1);
+    else generic_sample<PI, PJ, 1, 1>(L, t, sm, fi, fj, -1);
   }
 
   // ------------------------------------------------------------------ phase 0: the input lattice, the hash tables ----
@@ -468,16 +477,17 @@ struct VolRows {
     run_jobs<J_FI>(L, t, sm, jobs, k, warp, nw);
     run_jobs<J_FJ>(L, t, sm, jobs, k, warp, nw);
     // column jobs: O(-1) of the normal-i and normal-j faces, E(64) of the normal-k faces on the closing plane
-    const int ct = nw * 32 - 1 - tid;
-    if (ct < NFI) {
-      const int a = ct / (TJ + 1), b = ct % (TJ + 1) - 1;
+    // (one class per warp, from the last warp down: a warp runs one branch only)
+    static_assert(NFI <= 32 && NFJ <= 32 && NC <= 32, "a column-job class fits one warp");
+    const int ct = nw * 32 - 1 - tid, cw = ct >> 5, q = ct & 31;
+    if (cw == 0 && q < NFI) {
+      const int a = q / (TJ + 1), b = q % (TJ + 1) - 1;
       if (!(EDGE && a == TI && !t.close_i)) halo_column<0, 1>(L, t, sm, 2 * a, 2 * b + 1);
-    } else if (ct < NFI + NFJ) {
-      const int q = ct - NFI, a = q / (TJ + X) - 1, b = q % (TJ + X);
+    } else if (cw == 1 && q < NFJ) {
+      const int a = q / (TJ + X) - 1, b = q % (TJ + X);
       if (!(EDGE && b == TJ && !t.close_j)) halo_column<1, 0>(L, t, sm, 2 * a + 1, 2 * b);
-    } else if (ct < NFI + NFJ + NC) {
-      const int q = ct - NFI - NFJ;
-      if (t.k_last) generic_sample<1, 1, 0>(L, t, sm, 2 * (q / (TJ + 1) - 1) + 1, 2 * (q % (TJ + 1) - 1) + 1, 2 * G::TK);
+    } else if (cw == 2 && q < NC) {
+      if (t.k_last) generic_sample<1, 1, 0, 2>(L, t, sm, 2 * (q / (TJ + 1) - 1) + 1, 2 * (q % (TJ + 1) - 1) + 1, 2 * G::TK);
     }
   }
   static RN_HD void edges(const VolLevel& L, const Tile& t, float* sm, const Jobs& jobs, int warp, int lane, int nw, int tid)
@@ -487,13 +497,14 @@ struct VolRows {
     run_jobs<J_EJ>(L, t, sm, jobs, k, warp, nw);
     run_jobs<J_EK>(L, t, sm, jobs, k, warp, nw);
     if (t.k_last) {  // E(64) of the edges along i and along j on the closing plane
-      const int ct = nw * 32 - 1 - tid;
-      if (ct < NEI) {
-        const int a = ct / (TJ + X), b = ct % (TJ + X);
-        if (!(EDGE && b == TJ && !t.close_j)) generic_sample<1, 0, 0>(L, t, sm, 2 * a + 1, 2 * b, 2 * G::TK);
-      } else if (ct < NEI + NEJ) {
-        const int q = ct - NEI, a = q / TJ, b = q % TJ;
-        if (!(EDGE && a == TI && !t.close_i)) generic_sample<0, 1, 0>(L, t, sm, 2 * a, 2 * b + 1, 2 * G::TK);
+      static_assert(NEI <= 32 && NEJ <= 32, "a column-job class fits one warp");
+      const int ct = nw * 32 - 1 - tid, cw = ct >> 5, q = ct & 31;
+      if (cw == 0 && q < NEI) {
+        const int a = q / (TJ + X), b = q % (TJ + X);
+        if (!(EDGE && b == TJ && !t.close_j)) generic_sample<1, 0, 0, 2>(L, t, sm, 2 * a + 1, 2 * b, 2 * G::TK);
+      } else if (cw == 1 && q < NEJ) {
+        const int a = q / TJ, b = q % TJ;
+        if (!(EDGE && a == TI && !t.close_i)) generic_sample<0, 1, 0, 2>(L, t, sm, 2 * a, 2 * b + 1, 2 * G::TK);
       }
     }
   }

@@ -515,21 +515,23 @@ struct VolRows {
     const size_t M = 2 * (size_t)t.n + 1;
     constexpr int SJ = 2 * TJ + X;
     const int src0 = (lane & 1) ? G::OOFF + (lane >> 1) : G::EOFF + (lane >> 1);
-    if (!EDGE && nw == 2 * TJ) {  // a warp keeps its fine j and walks down i: running pointers
-      const int lo = L.out_lo - 2 * t.A0 > 0 ? L.out_lo - 2 * t.A0 : 0;
+    if (!EDGE && nw % (2 * TJ) == 0) {  // a warp keeps its fine j and walks down i (every (nw / 2 TJ)-th row): running pointers
+      const int per = nw / (2 * TJ), fj = warp % (2 * TJ), part = warp / (2 * TJ);
+      const int lo = (L.out_lo - 2 * t.A0 > 0 ? L.out_lo - 2 * t.A0 : 0) + part;
       const int hi = L.out_hi - 2 * t.A0 < 2 * TI - 1 ? L.out_hi - 2 * t.A0 : 2 * TI - 1;
-      const float* src = sm + G::row(lo, warp) + src0;
+      const float* src = sm + G::row(lo, fj) + src0;
       const size_t plane = M * M;
-      float* dst = L.gout + ((size_t)(2 * t.A0 + lo - L.out_lo) * plane + (size_t)(2 * t.B0 + warp) * M + (size_t)(2 * t.C0) + (size_t)lane);
-      for (int fi = lo; fi <= hi; fi++) {
+      float* dst = L.gout + ((size_t)(2 * t.A0 + lo - L.out_lo) * plane + (size_t)(2 * t.B0 + fj) * M + (size_t)(2 * t.C0) + (size_t)lane);
+      for (int fi = lo; fi <= hi; fi += per) {
 #pragma unroll
         for (int q = 0; q < 4; q++) dst[32 * q] = src[16 * q];
-        src += G::NJ * G::PK;
-        dst += plane;
+        src += per * G::NJ * G::PK;
+        dst += per * plane;
       }
-      if (t.k_last && lane <= hi - lo) {  // the closing column k = W: lane q stores it for fine row lo + q
-        const float* cs = sm + G::row(lo + lane, warp) + G::EOFF + G::TK;
-        L.gout[(size_t)(2 * t.A0 + lo + lane - L.out_lo) * plane + (size_t)(2 * t.B0 + warp) * M + (size_t)(2 * t.C0) + (size_t)(2 * G::TK)] = *cs;
+      if (t.k_last && lo + per * lane <= hi) {  // the closing column k = W: lane q stores it for the warp's q-th row
+        const int fi = lo + per * lane;
+        const float* cs = sm + G::row(fi, fj) + G::EOFF + G::TK;
+        L.gout[(size_t)(2 * t.A0 + fi - L.out_lo) * plane + (size_t)(2 * t.B0 + fj) * M + (size_t)(2 * t.C0) + (size_t)(2 * G::TK)] = *cs;
       }
       return;
     }

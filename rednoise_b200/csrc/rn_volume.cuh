@@ -257,7 +257,10 @@ RN_HD void vol_tile(const VolLevel& L, float* sm, int A0, int B0, int C0)
 
 constexpr int kVolTI = 8, kVolTJ = 8, kVolTK = 16, kVolThreads = 256;
 // the warp-row kernel (rn_volrow.cuh): levels with at least kRowMinN cells per axis
-constexpr int kRowTI = 4, kRowTJ = 4, kRowTK = 64, kRowWarps = 8;
+#ifndef RN_VOL_ROW_WARPS
+#define RN_VOL_ROW_WARPS 8   // warps per CTA of the warp-row kernel (a power of two)
+#endif
+constexpr int kRowTI = 4, kRowTJ = 4, kRowTK = 64, kRowWarps = RN_VOL_ROW_WARPS;
 constexpr int kRowMinN = 64;
 
 // tile extent along i of the level whose input grid has n cells per axis

@@ -543,8 +543,7 @@ def run_ours(args):
 
         def e2e_step():
             if ni_e:
-                ctx.volume3d_ptr(BASE_SEED, depth, 0.3, vol.data_ptr(), i0=i0, ni=ni_e)  # blocking
-                host[:ni_e].copy_(vol[:ni_e])                                             # the slab's planes are contiguous
+                ctx.volume3d_to_host_ptr(BASE_SEED, depth, 0.3, host.data_ptr(), i0=i0, ni=ni_e)  # rn_volume3d_host: blocking, chunked synthesis + D2H
                 return float(host[ni_e // 2, S3 // 2, S3 // 2])
             return 0.0
     elif args.workload == "batch":
@@ -624,10 +623,12 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": my_samples * bytes_per_sample,
                          "samples_per_s_bound_hbm": peak * 1e9 / bytes_per_sample / 1e9},
             "e2e": {"value": all_e2e_samples / e2e_s / 1e9, "unit": "Gsamples/s",
-                    "h2d_bytes_per_step": 48 + (4 * len(seeds[:32]) if args.workload == "batch" else 0),
+                    "h2d_bytes_per_step": 12 if args.workload == "volume" else 48 + (4 * len(seeds[:32]) if args.workload == "batch" else 0),
                     "d2h_bytes_per_step": e2e_samples * (4 if args.workload == "volume" else ELEM_BYTES), "ms_per_step": e2e_s * 1e3,
-                    "note": "rn_terrain2d()/rn_terrain2d_batch() with a pinned HOST destination: synthesis + D2H of the samples + host read; "
-                            "the only inputs are the 48-byte rn_params (and the seeds of a batch)",
+                    "note": ("rn_volume3d_host() with a pinned HOST destination: synthesis + D2H of the samples + host read; the only input is the 12-byte rn_volume_params"
+                             if args.workload == "volume" else
+                             "rn_terrain2d()/rn_terrain2d_batch() with a pinned HOST destination: synthesis + D2H of the samples + host read; "
+                             "the only inputs are the 48-byte rn_params (and the seeds of a batch)"),
                     "pageable_destination": None if e2e_pageable_s is None else
                     {"value_rank0": my_samples / e2e_pageable_s / 1e9, "ms_per_step": e2e_pageable_s * 1e3,
                      "note": "same call, destination from plain malloc (rank 0's own figure)"}},

@@ -254,6 +254,10 @@ typedef struct rn_volume_params {
   float amplitude;
 } rn_volume_params;
 int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, float* slab, void* stream);
+/* The same planes into HOST memory (pinned or pageable; same layout).  Blocking.  The slab is generated in chunks of planes
+ * into two context-owned staging halves, so that the generation of chunk k+1 overlaps the device-to-host copy of chunk k
+ * (the copy is the bottleneck: 4 B per sample over PCIe). */
+int rn_volume3d_host(rn_context* ctx, const rn_volume_params* p, int i0, int ni, float* host_slab);
 uint64_t rn_volume3d_slab_elems(int depth, int ni);
 
 /* ---- memory helpers ---------------------------------------------------------------------------

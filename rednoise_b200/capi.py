@@ -22,7 +22,7 @@ SYMBOLS = [
     "rn_version", "rn_last_error_string", "rn_status_string", "rn_params_default", "rn_terrain2d_side",
     "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
     "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_set_pipelining", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device", "rn_selftest_math",
-    "rn_terrain2d_cell_count", "rn_terrain2d_cell_level_offset", "rn_terrain2d_cells", "rn_volume3d", "rn_volume3d_slab_elems",
+    "rn_terrain2d_cell_count", "rn_terrain2d_cell_level_offset", "rn_terrain2d_cells", "rn_volume3d", "rn_volume3d_host", "rn_volume3d_slab_elems",
     "rn_rock_draw_count", "rn_rock", "rn_rock_batch", "rn_cloud_draw_count", "rn_cloud",
     "rn_device_count", "rn_device_alloc", "rn_device_free", "rn_host_alloc", "rn_host_free", "rn_copy_to_host",
     "rn_create_multi", "rn_destroy_multi", "rn_multi_size", "rn_multi_context", "rn_slab_rows", "rn_slab_window",
@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
     L.rn_terrain2d_cell_level_offset.argtypes = [i32]
     L.rn_terrain2d_cells.argtypes = [vp, C.POINTER(Params), vp, sz, i32, vp, i32, vp]
     L.rn_volume3d.argtypes = [vp, C.POINTER(VolumeParams), i32, i32, vp, vp]
+    L.rn_volume3d_host.argtypes = [vp, C.POINTER(VolumeParams), i32, i32, vp]
     L.rn_volume3d_slab_elems.restype = u64
     L.rn_volume3d_slab_elems.argtypes = [i32, i32]
     L.rn_rock_draw_count.restype = C.c_uint64
@@ -269,6 +270,12 @@ class Context:
         side = (1 << depth) + 1
         _check(lib().rn_volume3d(self._h, C.byref(vp_), i0, side - i0 if ni is None else ni, C.c_void_p(ptr),
                                  C.c_void_p(stream) if stream else None))
+
+    def volume3d_to_host_ptr(self, seed: int, depth: int, amplitude: float, host_ptr: int, *, i0: int = 0, ni: int | None = None):
+        """3D extension: the same planes into HOST memory at `host_ptr` (blocking; generation and D2H copy overlap chunk by chunk)."""
+        vp_ = VolumeParams(seed & 0xFFFFFFFF, depth, amplitude)
+        side = (1 << depth) + 1
+        _check(lib().rn_volume3d_host(self._h, C.byref(vp_), i0, side - i0 if ni is None else ni, C.c_void_p(host_ptr)))
 
     def rock_ptr(self, state: int, depth: int, amplitude: float, faces_ptr: int, cells_ptr: int, *, dst_is_device: bool = True, stream: int = 0,
                  cloud: bool = False) -> int:

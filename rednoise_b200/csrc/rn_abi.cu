@@ -679,6 +679,52 @@ int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, floa
   return RN_OK;
 }
 
+int rn_volume3d_host(rn_context* ctx, const rn_volume_params* p, int i0, int ni, float* host_slab)
+{
+  if (!ctx) return fail(RN_ERR_BAD_PARAM, "ctx is NULL");
+  if (!p || !host_slab) return fail(RN_ERR_BAD_PARAM, "params/host_slab is NULL");
+  if (p->depth < RN_VOLUME_MIN_DEPTH || p->depth > RN_VOLUME_MAX_DEPTH) return fail(RN_ERR_BAD_PARAM, "volume depth out of range [2,11]");
+  const int side = (1 << p->depth) + 1;
+  if (i0 < 0 || ni <= 0 || i0 > side - ni) return fail(RN_ERR_BAD_PARAM, "slab does not lie inside the volume");
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
+  const size_t plane = (size_t)side * (size_t)side;
+  int planes = (int)(((size_t)64 << 20) / (plane * sizeof(float)));  // ~64 MB per chunk, at least 4 planes (a level reaches 3 planes beyond a slab)
+  planes = planes < 4 ? 4 : planes;
+  planes = planes > ni ? ni : planes;
+  const size_t half = (size_t)planes * plane;
+  int st = ensure(&ctx->field, &ctx->field_bytes, sizeof(float) * 2 * half);
+  if (st != RN_OK) return st;
+  size_t scratch = 0;  // the largest cone of any chunk, allocated once (the chunks follow each other on one stream)
+  for (int r0 = 0; r0 < ni; r0 += planes) {
+    const size_t b = volume_scratch_bytes(p->depth, i0 + r0, ni - r0 < planes ? ni - r0 : planes);
+    scratch = b > scratch ? b : scratch;
+  }
+  st = ensure(&ctx->plane, &ctx->plane_bytes, scratch);
+  if (st != RN_OK) return st;
+  cudaStream_t stream = ctx->stream;
+  int k = 0;
+  for (int r0 = 0; r0 < ni; r0 += planes, k++) {
+    const int nr = ni - r0 < planes ? ni - r0 : planes;
+    const int h = k & 1;
+    float* stage = reinterpret_cast<float*>(ctx->field) + (size_t)h * half;
+    if (k >= 2) RN_CUDA(cudaStreamWaitEvent(stream, ctx->chunk_copied[h], 0));  // the staging half is free again
+    RN_CUDA(volume_generate(stage, ctx->plane, p->depth, p->seed, p->amplitude, i0 + r0, nr, stream, &ctx->launches));
+    RN_CUDA(cudaEventRecord(ctx->chunk_ready[h], stream));
+    if (ctx->copy_stream) {
+      RN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ready[h], 0));
+      RN_CUDA(cudaMemcpyAsync(host_slab + (size_t)r0 * plane, stage, (size_t)nr * plane * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+      RN_CUDA(cudaEventRecord(ctx->chunk_copied[h], ctx->copy_stream));
+    } else {
+      RN_CUDA(cudaMemcpyAsync(host_slab + (size_t)r0 * plane, stage, (size_t)nr * plane * sizeof(float), cudaMemcpyDeviceToHost, stream));
+      RN_CUDA(cudaEventRecord(ctx->chunk_copied[h], stream));
+    }
+  }
+  if (ctx->copy_stream) RN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  RN_CUDA(cudaStreamSynchronize(stream));
+  return RN_OK;
+}
+
 uint64_t rn_volume3d_slab_elems(int depth, int ni)
 {
   if (depth < RN_VOLUME_MIN_DEPTH || depth > RN_VOLUME_MAX_DEPTH || ni <= 0) return 0;

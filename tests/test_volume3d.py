@@ -176,6 +176,27 @@ def test_gpu_thin_slabs_of_the_2049_cubed_volume(ctx, rnlib, oracle, i0, ni):
 
 
 @pytest.mark.gpu
+def test_gpu_volume_host_destination(ctx, rnlib, oracle):
+    """rn_volume3d_host: the chunked, pipelined host path (pinned and pageable destinations, a slab that needs several chunks)
+    equals the specification."""
+    import torch
+    depth, seed = 8, 77
+    S = (1 << depth) + 1
+    want = oracle.volume3d(seed, depth, 0.3)
+    for pinned in (True, False):
+        host = torch.empty((S, S, S), dtype=torch.float32, pin_memory=pinned)
+        ctx.volume3d_to_host_ptr(seed, depth, 0.3, host.data_ptr())
+        assert np.array_equal(host.numpy().view(np.uint32), want.view(np.uint32))
+    part = torch.empty((5, S, S), dtype=torch.float32)
+    ctx.volume3d_to_host_ptr(seed, depth, 0.3, part.data_ptr(), i0=100, ni=5)
+    assert np.array_equal(part.numpy().view(np.uint32), want[100:105].view(np.uint32))
+    L = rnlib.lib()
+    p = rnlib.VolumeParams(seed, depth, 0.3)
+    assert L.rn_volume3d_host(ctx._h, C.byref(p), 0, S + 1, C.c_void_p(part.data_ptr())) == rnlib.RN_ERR_BAD_PARAM
+    assert L.rn_volume3d_host(ctx._h, C.byref(p), 0, 1, None) == rnlib.RN_ERR_BAD_PARAM
+
+
+@pytest.mark.gpu
 def test_gpu_volume_bad_arguments(ctx, rnlib):
     import torch
     L = rnlib.lib()

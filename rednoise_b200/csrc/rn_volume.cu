@@ -36,6 +36,29 @@ __global__ void __launch_bounds__(NT) k_vol_level(const __grid_constant__ VolLev
   else vol_tile<TI, TJ, TK, NT, false>(L, sm, A0, B0, C0);
 }
 
+// levels n = 2, 4, 8 in one CTA, each as ONE whole-volume tile; a level reads what the level before wrote to global memory
+// (same block: ordered by the barrier)
+struct VolCoarse {
+  VolLevel lv[kVolFusedLevels];
+};
+constexpr int kVolCoarseThreads = 256;
+__global__ void __launch_bounds__(kVolCoarseThreads) k_vol_coarse(const __grid_constant__ VolCoarse C)
+{
+  extern __shared__ __align__(16) float sm[];
+  vol_tile<2, 2, 2, kVolCoarseThreads, true>(C.lv[0], sm, 0, 0, 0);
+  __threadfence_block();
+  __syncthreads();
+  vol_tile<4, 4, 4, kVolCoarseThreads, true>(C.lv[1], sm, 0, 0, 0);
+  __threadfence_block();
+  __syncthreads();
+  vol_tile<8, 8, 8, kVolCoarseThreads, true>(C.lv[2], sm, 0, 0, 0);
+}
+cudaError_t launch_coarse(const VolCoarse& C, cudaStream_t stream)
+{
+  k_vol_coarse<<<1, kVolCoarseThreads, VolGeo<8, 8, 8>::BYTES, stream>>>(C);
+  return cudaGetLastError();
+}
+
 template <int TI, int TJ, int TK, int NT>
 cudaError_t launch_level(const VolLevel& L, int tiles_i, cudaStream_t stream)
 {
@@ -59,11 +82,24 @@ cudaError_t launch_level(const VolLevel& L, int tiles_i, cudaStream_t stream)
 // constant memory (a warp reads its job with a warp-uniform index).
 __constant__ constexpr RowJobs<kRowTI, kRowTJ, false> g_jobs_lean = make_row_jobs<kRowTI, kRowTJ, false>();
 __constant__ constexpr RowJobs<kRowTI, kRowTJ, true> g_jobs_edge = make_row_jobs<kRowTI, kRowTJ, true>();
+__constant__ constexpr RowJobs<kRowSmallT, kRowSmallT, false> g_jobs_small_lean = make_row_jobs<kRowSmallT, kRowSmallT, false>();
+__constant__ constexpr RowJobs<kRowSmallT, kRowSmallT, true> g_jobs_small_edge = make_row_jobs<kRowSmallT, kRowSmallT, true>();
+template <int TI, int TJ, bool EDGE>
+__device__ __forceinline__ const RowJobs<TI, TJ, EDGE>& row_jobs()
+{
+  static_assert((TI == kRowTI && TJ == kRowTJ) || (TI == kRowSmallT && TJ == kRowSmallT), "one job table per tile shape");
+  if constexpr (TI == kRowTI && TJ == kRowTJ) {
+    if constexpr (EDGE) return g_jobs_edge;
+    else return g_jobs_lean;
+  } else {
+    if constexpr (EDGE) return g_jobs_small_edge;
+    else return g_jobs_small_lean;
+  }
+}
 
 template <int TI, int TJ, int NW>
 __global__ void __launch_bounds__(NW * 32) k_vol_rows(const __grid_constant__ VolLevel L)
 {
-  static_assert(TI == kRowTI && TJ == kRowTJ, "one job table per tile shape");
   extern __shared__ __align__(16) float sm[];
   const int A0 = (L.tile_i0 + (int)blockIdx.z) * TI, B0 = (int)blockIdx.y * TJ, C0 = (int)blockIdx.x * kRowTK;
   const int tid = (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -75,11 +111,11 @@ __global__ void __launch_bounds__(NW * 32) k_vol_rows(const __grid_constant__ Vo
     __syncthreads();
     V::load(L, t, sm, warp, lane, NW, tid);
     __syncthreads();
-    V::cubes(L, t, sm, g_jobs_edge, warp, lane, NW, tid);
+    V::cubes(L, t, sm, row_jobs<TI, TJ, true>(), warp, lane, NW, tid);
     __syncthreads();
-    V::faces(L, t, sm, g_jobs_edge, warp, lane, NW, tid);
+    V::faces(L, t, sm, row_jobs<TI, TJ, true>(), warp, lane, NW, tid);
     __syncthreads();
-    V::edges(L, t, sm, g_jobs_edge, warp, lane, NW, tid);
+    V::edges(L, t, sm, row_jobs<TI, TJ, true>(), warp, lane, NW, tid);
     __syncthreads();
     V::store(L, t, sm, warp, lane, NW);
   } else {
@@ -87,11 +123,11 @@ __global__ void __launch_bounds__(NW * 32) k_vol_rows(const __grid_constant__ Vo
     const typename V::Tile t = V::tile(L, A0, B0, C0);
     V::load(L, t, sm, warp, lane, NW, tid);
     __syncthreads();
-    V::cubes(L, t, sm, g_jobs_lean, warp, lane, NW, tid);
+    V::cubes(L, t, sm, row_jobs<TI, TJ, false>(), warp, lane, NW, tid);
     __syncthreads();
-    V::faces(L, t, sm, g_jobs_lean, warp, lane, NW, tid);
+    V::faces(L, t, sm, row_jobs<TI, TJ, false>(), warp, lane, NW, tid);
     __syncthreads();
-    V::edges(L, t, sm, g_jobs_lean, warp, lane, NW, tid);
+    V::edges(L, t, sm, row_jobs<TI, TJ, false>(), warp, lane, NW, tid);
     __syncthreads();
     V::store(L, t, sm, warp, lane, NW);
   }
@@ -149,12 +185,27 @@ cudaError_t volume_generate(float* slab, void* scratch, int depth, uint32_t seed
   cudaError_t e = cudaMemsetAsync(grid[1], 0, (size_t)(hi[1] - lo[1] + 1) * 9 * sizeof(float), stream);
   if (e != cudaSuccess) return e;
   if (events && (e = cudaEventRecord(events[0], stream)) != cudaSuccess) return e;
+  int first = 1;
+  if (vol_coarse_fused(depth, lo, hi)) {
+    VolCoarse C;
+    for (int l = 1; l <= kVolFusedLevels; l++) {
+      int tiles_i = 0;
+      C.lv[l - 1] = vol_level_make(depth, l, lo, hi, grid[l], grid[l + 1], seed, amplitude, &tiles_i);
+      C.lv[l - 1].tile_i0 = 0;
+    }
+    if ((e = launch_coarse(C, stream)) != cudaSuccess) return e;
+    for (int l = 1; l <= kVolFusedLevels; l++)  // (one launch: the levels' events coincide)
+      if (events && (e = cudaEventRecord(events[l], stream)) != cudaSuccess) return e;
+    if (launches) *launches += 1;
+    first = kVolFusedLevels + 1;
+  }
   if (nstages) *nstages = depth - 1;
-  for (int l = 1; l < depth; l++) {
+  for (int l = first; l < depth; l++) {
     const int n = 1 << l;
     int tiles_i = 0;
     const VolLevel L = vol_level_make(depth, l, lo, hi, grid[l], grid[l + 1], seed, amplitude, &tiles_i);
-    if (n >= kRowMinN) e = launch_rows<kRowTI, kRowTJ, kRowWarps>(L, tiles_i, stream);
+    if (n >= kRowBigN) e = launch_rows<kRowTI, kRowTJ, kRowWarps>(L, tiles_i, stream);
+    else if (n >= kRowMinN) e = launch_rows<kRowSmallT, kRowSmallT, kRowWarps>(L, tiles_i, stream);
     else switch (n) {
       case 2: e = launch_level<2, 2, 2, 64>(L, tiles_i, stream); break;
       case 4: e = launch_level<4, 4, 4, 128>(L, tiles_i, stream); break;

@@ -262,6 +262,10 @@ constexpr int kVolTI = 8, kVolTJ = 8, kVolTK = 16, kVolThreads = 256;
 #endif
 constexpr int kRowTI = 4, kRowTJ = 4, kRowTK = 64, kRowWarps = RN_VOL_ROW_WARPS;
 constexpr int kRowMinN = 64;
+// levels with kRowMinN <= n < kRowBigN run the warp-row kernel on 2 x 2 x 64-cell tiles: the n = 64 level has only 256 of the
+// 4 x 4 tiles (less than one wave), so its duration is one CTA's latency, and a 2 x 2 tile has a third of the row jobs
+constexpr int kRowSmallT = 2, kRowBigN = 128;
+inline int vol_row_tile(int n) { return n >= kRowBigN ? kRowTI : kRowSmallT; }
 
 // tile extent along i of the level whose input grid has n cells per axis
 // the coarse levels (8 <= n < kRowMinN) are latency-bound -- a handful of CTAs, each walking its tile phase by phase: 4 x 4 x 4-cell tiles
@@ -269,7 +273,7 @@ constexpr int kRowMinN = 64;
 #ifndef RN_VOL_COARSE_TILE
 #define RN_VOL_COARSE_TILE 4
 #endif
-inline int vol_tile_i(int n) { return n >= kRowMinN ? kRowTI : (n <= 4 ? n : (RN_VOL_COARSE_TILE == 4 ? 4 : (n >= 16 ? kVolTI : n))); }
+inline int vol_tile_i(int n) { return n >= kRowMinN ? vol_row_tile(n) : (n <= 4 ? n : (RN_VOL_COARSE_TILE == 4 ? 4 : (n >= 16 ? kVolTI : n))); }
 
 
 // Plane ranges: lo[l], hi[l] = the planes (lattice index along i) of the level-l grid (side 2^l + 1) that the slab
@@ -289,6 +293,18 @@ inline void volume_ranges(int depth, int i0, int ni, int* lo, int* hi)
   }
 }
 
+
+// The three coarsest levels (n = 2, 4, 8: 5^3, 9^3, 17^3 samples) cost a launch each and nothing else; when the slab's cone
+// holds their grids completely (every slab of a volume up to 513^3, thick slabs beyond) ONE CTA runs them back to back, each level
+// as a single whole-volume tile (rn_volume.cu: k_vol_coarse).
+constexpr int kVolFusedLevels = 3;
+inline bool vol_coarse_fused(int depth, const int* lo, const int* hi)
+{
+  if (depth < kVolFusedLevels + 1) return false;
+  for (int l = 1; l <= kVolFusedLevels; l++)
+    if (lo[l] != 0 || hi[l] != (1 << l)) return false;
+  return true;
+}
 
 // Parameters of the launch that refines the level-l grid into the level-(l+1) grid (lo/hi from volume_ranges).
 inline VolLevel vol_level_make(int depth, int l, const int* lo, const int* hi, const float* gin, float* gout, uint32_t seed, float amplitude,

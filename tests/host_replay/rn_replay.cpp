@@ -344,11 +344,24 @@ int replay_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, f
   }
   grid[depth] = slab;
   for (size_t q = 0; q < grids[1].size(); q++) grids[1][q] = 0.0f;  // the 27 undisplaced points
-  for (int l = 1; l < depth; l++) {
+  int first = 1;
+  if (vol_coarse_fused(depth, lo, hi)) {  // rn_volume.cu: k_vol_coarse, every level as one whole-volume tile
+    for (int l = 1; l <= kVolFusedLevels; l++) {
+      int tiles_i = 0;
+      VolLevel L = vol_level_make(depth, l, lo, hi, grid[l], grid[l + 1], seed, amplitude, &tiles_i);
+      L.tile_i0 = 0;
+      if (l == 1) vol_level_host<2, 2, 2>(L, 1, poison);
+      else if (l == 2) vol_level_host<4, 4, 4>(L, 1, poison);
+      else vol_level_host<8, 8, 8>(L, 1, poison);
+    }
+    first = kVolFusedLevels + 1;
+  }
+  for (int l = first; l < depth; l++) {
     const int n = 1 << l;
     int tiles_i = 0;
     const VolLevel L = vol_level_make(depth, l, lo, hi, grid[l], grid[l + 1], seed, amplitude, &tiles_i);
-    if (n >= kRowMinN) vol_rows_host<kRowTI, kRowTJ, kRowWarps>(L, tiles_i, poison);
+    if (n >= kRowBigN) vol_rows_host<kRowTI, kRowTJ, kRowWarps>(L, tiles_i, poison);
+    else if (n >= kRowMinN) vol_rows_host<kRowSmallT, kRowSmallT, kRowWarps>(L, tiles_i, poison);
     else switch (n) {
       case 2: vol_level_host<2, 2, 2>(L, tiles_i, poison); break;
       case 4: vol_level_host<4, 4, 4>(L, tiles_i, poison); break;

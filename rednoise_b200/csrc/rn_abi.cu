@@ -103,6 +103,7 @@ Law law_of(const rn_params* p)
   l.band_lo = 0.5f / p->feature_scale;
   l.bulgy = p->bulgy_rocks != 0;
   l.one = 1.0f;
+  l.flat_ok = law_flat_ok(l);
   return l;
 }
 

@@ -41,6 +41,9 @@
 namespace rn {
 
 constexpr int kMarchCols = 60;  // cell columns a warp finishes
+#ifndef RN_EXP
+#define RN_EXP 0           // timing experiments only (results are wrong): bit 0 no global stores, bit 1 no addVolcano
+#endif
 #ifndef RN_MARCH_CARRY
 #define RN_MARCH_CARRY 0   // values kept in registers from phase to phase instead of being re-read from shared memory (lean
                            // instantiation): bit 0 K(u-1, k0/k1) P2 -> P3, bit 1 C(u-1, k0/k1) P2 -> P3, bit 2 K(u, .) P1 -> P2
@@ -156,6 +159,10 @@ RN_HD MarchCtx march_ctx(const StreamParams& sp, int id, unsigned f)
   cx.col_lean = cx.L0 >= 0 && cx.L0 + 64 <= n && fast;
   cx.lean_lo = imax_(cx.a0 - 1, 1);
   cx.lean_hi = cx.a1e <= n - 1 ? cx.a1e : n - 2;
+  // a lean step stores both output rows 2a, 2a + 1 of its cell row a = u - 1 without looking at the window
+  const int a_in_lo = (sp.win_i0 + 1) >> 1, a_in_hi = (sp.win_i0 + sp.win_ni - 2) >> 1;
+  if (a_in_lo > cx.a0) cx.lean_lo = imax_(cx.lean_lo, a_in_lo + 1);
+  cx.lean_hi = imin_(cx.lean_hi, a_in_hi + 1);
   cx.ubase = cx.a0 - 1;
   return cx;
 }
@@ -217,25 +224,61 @@ RN_HD void st256(E4* p, const E4& a, const E4& b)  // p is 32-byte aligned: one 
   p[1] = b;
 #endif
 }
-// Two samples displaced at once from their averaged elements and direction vectors (the tail of generateSquare /
-// generateDiamond, Terrain.cpp:185-213,230-257): displace2 + the shade terms, bit for bit what mid_interior2 does.
-RN_HD void displaced_pair(const Law& law, F2 a_xy, F2 a_zw, F2 b_xy, F2 b_zw, const V3P& dir1, const V3P& dir2, float blah, uint32_t draw_a,
-                          uint32_t draw_b, E4* out_a, E4* out_b, float* loss_a, float* loss_b)
+// A vote of the warp (device) / the lane's own value (host replay: the two tails it chooses between are bit-identical wherever both
+// apply, so a per-lane choice replays the same field and exercises both).
+RN_HD bool warp_all(bool pred)
 {
-  const Displaced2 dp = displace2(law, f2lo(a_xy), f2hi(a_xy), f2lo(b_xy), f2hi(b_xy), dir1, dir2, blah, draw_a, draw_b);
-  const F2 rs = f2s(law.radiosity_strength);
-  const F2 gain = f2mul(dp.offset, rs);
-  const F2 loss = f2mul(f2mul(f2s(0.25f), dp.offset), rs);
-  *loss_a = f2lo(loss);
-  *loss_b = f2hi(loss);
-  *out_a = E4{f2lo(a_xy) + f2lo(dp.shift.x), f2hi(a_xy) + f2lo(dp.shift.y), f2lo(a_zw) + f2lo(dp.shift.z), f2hi(a_zw) + f2lo(gain)};
-  *out_b = E4{f2lo(b_xy) + f2hi(dp.shift.x), f2hi(b_xy) + f2hi(dp.shift.y), f2lo(b_zw) + f2hi(dp.shift.z), f2hi(b_zw) + f2hi(gain)};
+#if defined(__CUDA_ARCH__)
+  return __all_sync(0xffffffffu, pred) != 0;
+#else
+  return pred;
+#endif
 }
 
-// averageSquare + generateSquare (Terrain.cpp:216-258) for the two cells of a lane: cell A has corners a00 (u, k), a10 (u+1, k),
-// a01 (u, k+1), a11 (u+1, k+1); cell B likewise.  Same operand order as the scalar form in rn_stream.cuh interval1.
-RN_HD void centre_pair(const Law& law, const E4& a00, const E4& a10, const E4& a01, const E4& a11, const E4& b00, const E4& b10, const E4& b01,
-                       const E4& b11, float blah, uint32_t draw_a, uint32_t draw_b, E4* out_a, E4* out_b, float* loss_a, float* loss_b)
+// Two samples displaced at once from their averaged elements and direction vectors (the tail of generateSquare /
+// generateDiamond, Terrain.cpp:185-213,230-257), in two halves so that a step evaluates the independent halves of several pairs
+// side by side and decides ONCE, for the whole warp, between the general tail (unit normal by square root and reciprocal) and the
+// flat one: at the last levels of a deep field every |dir1 x dir2|^2 is below the 1e-10 threshold of Vector3::normalise and the
+// normal is (0, 0, 1) -- only z moves (rn_math.cuh shift_flat2_z).  Bit for bit what mid_interior2 / displace2 do.
+struct PairWork {
+  F2 a_xy, a_zw, b_xy, b_zw;  // averaged elements of sample A and sample B
+  V3P c;                      // dir1 x dir2
+  F2 f;                       // |c|^2
+  Offset2 o;
+};
+RN_HD PairWork pair_begin(const Law& law, F2 a_xy, F2 a_zw, F2 b_xy, F2 b_zw, const V3P& dir1, const V3P& dir2, float blah, uint32_t draw_a,
+                          uint32_t draw_b)
+{
+  PairWork w;
+  w.a_xy = a_xy; w.a_zw = a_zw; w.b_xy = b_xy; w.b_zw = b_zw;
+  w.c = vcross2(dir1, dir2, law.one);
+  w.f = vnorm2_sq(w.c, law.one);
+  w.o = offset2(law, f2lo(a_xy), f2hi(a_xy), f2lo(b_xy), f2hi(b_xy), blah, draw_a, draw_b);
+  return w;
+}
+template <bool FLAT>
+RN_HD void pair_finish(const Law& law, const PairWork& w, float blah, E4* out_a, E4* out_b, float* loss_a, float* loss_b)
+{
+  const F2 rs = f2s(law.radiosity_strength);
+  const F2 gain = f2mul(w.o.offset, rs);
+  const F2 loss = f2mul(f2mul(f2s(0.25f), w.o.offset), rs);
+  *loss_a = f2lo(loss);
+  *loss_b = f2hi(loss);
+  if (FLAT) {
+    const F2 sz = shift_flat2_z(blah, w.o);
+    *out_a = E4{f2lo(w.a_xy), f2hi(w.a_xy), f2lo(w.a_zw) + f2lo(sz), f2hi(w.a_zw) + f2lo(gain)};
+    *out_b = E4{f2lo(w.b_xy), f2hi(w.b_xy), f2lo(w.b_zw) + f2hi(sz), f2hi(w.b_zw) + f2hi(gain)};
+  } else {
+    const V3P sh = shift_general2(w.c, w.f, blah, w.o);
+    *out_a = E4{f2lo(w.a_xy) + f2lo(sh.x), f2hi(w.a_xy) + f2lo(sh.y), f2lo(w.a_zw) + f2lo(sh.z), f2hi(w.a_zw) + f2lo(gain)};
+    *out_b = E4{f2lo(w.b_xy) + f2hi(sh.x), f2hi(w.b_xy) + f2hi(sh.y), f2lo(w.b_zw) + f2hi(sh.z), f2hi(w.b_zw) + f2hi(gain)};
+  }
+}
+
+// First half of averageSquare + generateSquare (Terrain.cpp:216-258) for the two cells of a lane: cell A has corners a00 (u, k),
+// a10 (u+1, k), a01 (u, k+1), a11 (u+1, k+1); cell B likewise.  Same operand order as the scalar form in rn_stream.cuh interval1.
+RN_HD PairWork centre_pair_begin(const Law& law, const E4& a00, const E4& a10, const E4& a01, const E4& a11, const E4& b00, const E4& b10,
+                                 const E4& b01, const E4& b11, float blah, uint32_t draw_a, uint32_t draw_b)
 {
   const F2 q = f2s(0.25f);
   const F2 a_xy = f2mul(f2add(f2add(f2add(e4_xy(a00), e4_xy(a10)), e4_xy(a01)), e4_xy(a11)), q);
@@ -244,7 +287,21 @@ RN_HD void centre_pair(const Law& law, const E4& a00, const E4& a10, const E4& a
   const F2 b_zw = f2mul(f2add(f2add(f2add(e4_zw(b00), e4_zw(b10)), e4_zw(b01)), e4_zw(b11)), q);
   const V3P dir1 = v3p(vsub(pos4(a11), pos4(a00)), vsub(pos4(b11), pos4(b00)));
   const V3P dir2 = v3p(vsub(pos4(a10), pos4(a01)), vsub(pos4(b10), pos4(b01)));
-  displaced_pair(law, a_xy, a_zw, b_xy, b_zw, dir1, dir2, blah, draw_a, draw_b, out_a, out_b, loss_a, loss_b);
+  return pair_begin(law, a_xy, a_zw, b_xy, b_zw, dir1, dir2, blah, draw_a, draw_b);
+}
+// First half of averageDiamond + generateDiamond for two interior midpoints (rn_tile.cuh mid_interior2: x neighbours ax0, ax1,
+// y neighbours ay0, ay1 of sample A; likewise B)
+RN_HD PairWork mid_pair_begin(const Law& law, const E4& ax0, const E4& ax1, const E4& ay0, const E4& ay1, const E4& bx0, const E4& bx1,
+                              const E4& by0, const E4& by1, float blah, uint32_t draw_a, uint32_t draw_b)
+{
+  const F2 q = f2s(0.25f);
+  const F2 a_xy = f2mul(f2add(f2add(f2add(e4_xy(ax0), e4_xy(ax1)), e4_xy(ay0)), e4_xy(ay1)), q);
+  const F2 a_zw = f2mul(f2add(f2add(f2add(e4_zw(ax0), e4_zw(ax1)), e4_zw(ay0)), e4_zw(ay1)), q);
+  const F2 b_xy = f2mul(f2add(f2add(f2add(e4_xy(bx0), e4_xy(bx1)), e4_xy(by0)), e4_xy(by1)), q);
+  const F2 b_zw = f2mul(f2add(f2add(f2add(e4_zw(bx0), e4_zw(bx1)), e4_zw(by0)), e4_zw(by1)), q);
+  const V3P dir1 = v3p(vsub(pos4(ax0), pos4(ax1)), vsub(pos4(bx0), pos4(bx1)));
+  const V3P dir2 = v3p(vsub(pos4(ay1), pos4(ay0)), vsub(pos4(by1), pos4(by0)));
+  return pair_begin(law, a_xy, a_zw, b_xy, b_zw, dir1, dir2, blah, draw_a, draw_b);
 }
 
 // addVolcano (Terrain.cpp:129-137) for two samples at once, crater branch included: volcano_height_r2<false> lane by lane
@@ -340,7 +397,9 @@ struct March {
     L.sS = jump_apply(sp.jn, L.sS);
     if (!EDGE) {
       if (RN_MARCH_CARRY & 4) { L.c_ka[0] = ka[0]; L.c_ka[1] = ka[1]; L.c_ka[2] = ka[2]; }
-      centre_pair(sp.law, ka[0], kb[0], ka[1], kb[1], ka[1], kb[1], ka[2], kb[2], sp.lev.blahS, draw_a, draw_b, &L.cen[1], &L.cen[2], &L.ts[1], &L.ts[2]);
+      const PairWork w = centre_pair_begin(sp.law, ka[0], kb[0], ka[1], kb[1], ka[1], kb[1], ka[2], kb[2], sp.lev.blahS, draw_a, draw_b);
+      if (warp_all(sp.law.flat_ok && vnorm2_both_degenerate(w.f))) pair_finish<true>(sp.law, w, sp.lev.blahS, &L.cen[1], &L.cen[2], &L.ts[1], &L.ts[2]);
+      else pair_finish<false>(sp.law, w, sp.lev.blahS, &L.cen[1], &L.cen[2], &L.ts[1], &L.ts[2]);
     } else {
       const int n = sp.lev.n;
       const int k0 = cx.L0 + 2 * lane;
@@ -404,10 +463,19 @@ struct March {
     L.sD2 = jump_apply(sp.jn1, L.sD2);
     if (!EDGE) {
       // loop 1: M1(u, k) at output (2u, 2k+1): x neighbours C(u-1, k), C(u, k); y neighbours K'(u, k), K'(u, k+1)
-      mid_interior2(sp.law, cenm[1], cenc[1], K0, K1, cenm[2], cenc[2], K1, K2, sp.lev.blahD, d1a, d1b, &L.m1[0], &L.m1[1], &L.td1[1], &L.td1[2]);
+      const PairWork w1 = mid_pair_begin(sp.law, cenm[1], cenc[1], K0, K1, cenm[2], cenc[2], K1, K2, sp.lev.blahD, d1a, d1b);
       // loop 2: M2(u-1, k) at output (2u-1, 2k): x neighbours K'(u-1, k), K'(u, k); y neighbours C(u-1, k-1), C(u-1, k)
-      mid_interior2(sp.law, kcm[0], K0, cenm[0], cenm[1], kcm[1], K1, cenm[1], cenm[2], sp.lev.blahD, d2a, d2b, &L.out[1][0], &L.out[1][2], &L.td2[0],
-                    &L.td2[1]);
+      const PairWork w2 = mid_pair_begin(sp.law, kcm[0], K0, cenm[0], cenm[1], kcm[1], K1, cenm[1], cenm[2], sp.lev.blahD, d2a, d2b);
+      // one decision for the four midpoints and the whole warp.  Lane 0's M2(u-1, k0) is built on C(u-1, k0-1), which a halo lane does
+      // not have (its sample is never stored nor passed on): it does not vote.
+      const bool flat2 = f2hi(w2.f) < 1e-10f && (lane == 0 || f2lo(w2.f) < 1e-10f);
+      if (warp_all(sp.law.flat_ok && vnorm2_both_degenerate(w1.f) && flat2)) {
+        pair_finish<true>(sp.law, w1, sp.lev.blahD, &L.m1[0], &L.m1[1], &L.td1[1], &L.td1[2]);
+        pair_finish<true>(sp.law, w2, sp.lev.blahD, &L.out[1][0], &L.out[1][2], &L.td2[0], &L.td2[1]);
+      } else {
+        pair_finish<false>(sp.law, w1, sp.lev.blahD, &L.m1[0], &L.m1[1], &L.td1[1], &L.td1[2]);
+        pair_finish<false>(sp.law, w2, sp.lev.blahD, &L.out[1][0], &L.out[1][2], &L.td2[0], &L.td2[1]);
+      }
     } else {
       const int n = sp.lev.n;
       const int k0 = cx.L0 + 2 * lane;
@@ -471,7 +539,7 @@ struct March {
     L.out[0][3] = *state_at(wsm, pb, S_M1B, lane);
     L.out[1][1] = e0;
     L.out[1][3] = e1;
-    if (sp.volcano) {  // uniform
+    if (sp.volcano && !(RN_EXP & 2)) {  // uniform
       const int Wout = 1 << sp.dout;
       const float gain_w = sp.volcano_gain * (float)Wout;
       const E4 fy2 = wsm[kConstE4 + lane];
@@ -517,11 +585,11 @@ struct March {
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       const int gi = 2 * a + r;
-      if ((unsigned)(gi - sp.win_i0) >= (unsigned)sp.win_ni || gi > Wout) continue;  // uniform
+      if (EDGE && ((unsigned)(gi - sp.win_i0) >= (unsigned)sp.win_ni || gi > Wout)) continue;  // uniform; lean steps: march_ctx
       E4* row = r == 0 ? dst : dst + sp.gout_pitch;
       const E4* v = L.out[r];
       if (!EDGE) {  // lean warps own 60 whole cell columns inside the window
-        const bool mine = lane >= 1 && lane <= 30;
+        const bool mine = lane >= 1 && lane <= 30 && (!(RN_EXP & 1) || sp.law.one != 1.0f);
         if ((reinterpret_cast<uintptr_t>(row) & 16u) == 0) {  // uniform: the lane's four samples are two whole sectors
           if (mine) {
             st256(row, v[0], v[1]);

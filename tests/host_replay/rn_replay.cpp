@@ -410,6 +410,7 @@ int replay_terrain2d(const rn_params* p, const rn_window* win, rn_element* dst, 
   law.band_lo = 0.5f / p->feature_scale;
   law.bulgy = p->bulgy_rocks != 0;
   law.one = 1.0f;
+  law.flat_ok = law_flat_ok(law);
   const size_t sbytes = chain_scratch_bytes(p->depth, 1);
   void* scratch = nullptr;
   if (sbytes && posix_memalign(&scratch, 256, sbytes) != 0) return RN_ERR_OOM;

@@ -667,15 +667,22 @@ int rn_volume3d(rn_context* ctx, const rn_volume_params* p, int i0, int ni, floa
   DeviceGuard guard(ctx->device);
   if (!guard.ok) return fail(RN_ERR_CUDA, "cudaSetDevice failed");
   cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
-  // the coarser level grids of the slab's dependency cone (context-owned, grow-only; consecutive calls on one context are
-  // ordered by the stream they are given)
-  int st = ensure(&ctx->plane, &ctx->plane_bytes, volume_scratch_bytes(p->depth, i0, ni));
+  // The coarser level grids of the slab's dependency cone live in one of the two context-owned scratch slots (grow-only, shared
+  // with the 2D path and ordered by the same events).  Call pipelining as in synth_window_fused: every level but the last runs on
+  // the high-priority side stream, so the latency-bound coarse levels of this call overlap the last level of the call before.
+  const int sl = (int)(ctx->seq & 1);
+  ctx->seq++;
+  int st = ensure(&ctx->slot[sl], &ctx->slot_bytes[sl], volume_scratch_bytes(p->depth, i0, ni));
   if (st != RN_OK) return st;
   if (ctx->profiling && !ctx->ev[0])
     for (int k = 0; k < 17; k++) RN_CUDA(cudaEventCreate(&ctx->ev[k]));
   ctx->ev_stages = 0;
-  RN_CUDA(volume_generate(slab, ctx->plane, p->depth, p->seed, p->amplitude, i0, ni, stream, &ctx->launches, ctx->profiling ? ctx->ev : nullptr,
-                          ctx->profiling ? &ctx->ev_stages : nullptr));
+  const bool overlap = ctx->overlap && !ctx->profiling && ctx->coarse_stream;
+  if (ctx->slot_used[sl]) RN_CUDA(cudaStreamWaitEvent(overlap ? ctx->coarse_stream : stream, ctx->slot_free[sl], 0));
+  RN_CUDA(volume_generate(slab, ctx->slot[sl], p->depth, p->seed, p->amplitude, i0, ni, stream, &ctx->launches, ctx->profiling ? ctx->ev : nullptr,
+                          ctx->profiling ? &ctx->ev_stages : nullptr, overlap ? ctx->coarse_stream : nullptr, overlap ? ctx->coarse_done[sl] : nullptr));
+  RN_CUDA(cudaEventRecord(ctx->slot_free[sl], stream));
+  ctx->slot_used[sl] = true;
   if (!stream_v) RN_CUDA(cudaStreamSynchronize(stream));
   return RN_OK;
 }

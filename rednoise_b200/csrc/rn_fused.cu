@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(NT, MINB) k_stream(const __grid_constant__ Str
 }
 
 // Warp-synchronous march (rn_march.cuh): every warp is an independent (strip, segment) unit; no block barriers.
-template <bool EDGE>
+#ifndef RN_MARCH_VM
+#define RN_MARCH_VM 1   // lean steps instantiated per addVolcano mode (off / far from the crater / with the crater branch)
+#endif
+template <bool EDGE, int VM>
 __device__ __forceinline__ void march_step(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* wsm, int u, int lane)
 {
   using M = March<EDGE>;
@@ -161,7 +164,7 @@ __device__ __forceinline__ void march_step(const StreamParams& sp, const MarchCt
   M::x1(cx, L, wsm, u, lane, nullptr, nullptr);
   M::p2(sp, cx, L, wsm, u, lane);
   M::x2(cx, L, wsm, u, lane, nullptr, nullptr);
-  M::p3(sp, cx, L, wsm, u, lane);
+  M::template p3<VM>(sp, cx, L, wsm, u, lane);
   M::store(sp, cx, L, u, lane, nullptr);
 }
 
@@ -171,9 +174,12 @@ __global__ void __launch_bounds__(32 * WPB, MINB) k_march(const __grid_constant_
   extern __shared__ __align__(16) float sm[];
   RN_TL_SCOPE(sp.tl_slot);
   const int lane = (int)threadIdx.x & 31;
-  const int id = (int)blockIdx.x * WPB + ((int)threadIdx.x >> 5);
+  // one warp per CTA (the shipped configuration): the unit index -- and with it the whole MarchCtx and the loop control -- is a
+  // function of blockIdx alone, which lets the compiler keep them in uniform registers and prove the warp convergent
+  const int wib = WPB == 1 ? 0 : ((int)threadIdx.x >> 5);
+  const int id = (int)blockIdx.x * WPB + wib;
   if (id >= nunits) return;
-  E4* wsm = reinterpret_cast<E4*>(sm) + ((int)threadIdx.x >> 5) * kWarpE4;  // this warp's ring, carried state and constants
+  E4* wsm = reinterpret_cast<E4*>(sm) + wib * kWarpE4;  // this warp's ring, carried state and constants
   const MarchCtx cx = march_ctx(sp, id, blockIdx.z);
 #ifdef RN_STREAM_TRACE
   if (lane == 0 && id < 8192) {
@@ -186,9 +192,19 @@ __global__ void __launch_bounds__(32 * WPB, MINB) k_march(const __grid_constant_
   MarchLane L;
   March<true>::init(sp, cx, L, wsm, lane, false);
   const int last = cx.a1e;
+#if RN_MARCH_VM
+  const int vm = !sp.volcano ? 0 : cx.far ? 1 : 2;  // addVolcano mode of the warp's lean steps (rn_march.cuh p3)
+#endif
   for (int u = cx.a0 - 1; u <= last; u++) {
-    if (march_step_is_lean(cx, u)) march_step<false>(sp, cx, L, wsm, u, lane);  // uniform per warp
-    else march_step<true>(sp, cx, L, wsm, u, lane);
+    if (march_step_is_lean(cx, u)) {  // uniform per warp
+#if RN_MARCH_VM
+      if (vm == 1) march_step<false, 1>(sp, cx, L, wsm, u, lane);
+      else if (vm == 0) march_step<false, 0>(sp, cx, L, wsm, u, lane);
+      else march_step<false, 2>(sp, cx, L, wsm, u, lane);
+#else
+      march_step<false, -1>(sp, cx, L, wsm, u, lane);
+#endif
+    } else march_step<true, -1>(sp, cx, L, wsm, u, lane);
   }
 #ifdef RN_STREAM_TRACE
   if (lane == 0 && id < 8192) {

@@ -43,7 +43,8 @@ cudaError_t rock_small_batch(int n, const int* depths, const uint32_t* states, f
 // planes [i0, i0+ni) of the (W+1)^3 float volume into `slab` (ni x (W+1) x (W+1), dense); scratch: volume_scratch_bytes() bytes.
 size_t volume_scratch_bytes(int depth, int i0, int ni);
 cudaError_t volume_generate(float* slab, void* scratch, int depth, uint32_t seed, float amplitude, int i0, int ni, cudaStream_t stream,
-                            uint64_t* launches, cudaEvent_t* events = nullptr, int* nstages = nullptr);
+                            uint64_t* launches, cudaEvent_t* events = nullptr, int* nstages = nullptr, cudaStream_t coarse = nullptr,
+                            cudaEvent_t coarse_done = nullptr);
 
 // Epilogues / utilities (rn_util.cu).
 // addVolcano (Terrain.cpp:121-141) over the window [i0,i0+ni) x [j0,j0+nj) of a depth-`depth` field

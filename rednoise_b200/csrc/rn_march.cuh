@@ -516,8 +516,14 @@ struct March {
   }
 
   // ------------------------------------------------------------------ P3: G(u-1), addVolcano ----
+  // VM: what the caller knows about addVolcano at compile time -- -1 nothing (sp.volcano and cx.far decide), 0 off, 1 on and every
+  // sample of the warp outside the crater, 2 on with the crater branch.  Known modes leave no branch between the shade sums and
+  // the reciprocal square roots, so the compiler interleaves the two dependent chains.
+  template <int VM>
   static RN_HD void p3(const StreamParams& sp, const MarchCtx& cx, MarchLane& L, E4* wsm, int u, int lane)
   {
+    const bool volcano_on = VM < 0 ? (sp.volcano != 0) : VM > 0;
+    const bool far_away = VM < 0 ? (cx.far != 0) : VM == 1;
     const int pb = bank_of(cx, u) ^ 1;
     const E4 tdm = L.tdm;  // TD1(u-1; k0-1, k0, k1), sg(u-1, k0)
     const E4 tem = L.tem;  // TD2(u-2; k0, k1, .), sg(u-1, k1)
@@ -539,7 +545,7 @@ struct March {
     L.out[0][3] = *state_at(wsm, pb, S_M1B, lane);
     L.out[1][1] = e0;
     L.out[1][3] = e1;
-    if (sp.volcano && !(RN_EXP & 2)) {  // uniform
+    if (volcano_on && !(RN_EXP & 2)) {  // uniform
       const int Wout = 1 << sp.dout;
       const float gain_w = sp.volcano_gain * (float)Wout;
       const E4 fy2 = wsm[kConstE4 + lane];
@@ -550,7 +556,7 @@ struct March {
         if (!EDGE) {  // two columns at once (packed pair); the few warps that touch the crater evaluate its branch as a select
           const F2 r01 = f2add(f2s(fx2), f2(fy2.x, fy2.y)), r23 = f2add(f2s(fx2), f2(fy2.z, fy2.w));
           F2 h01, h23;
-          if (cx.far) {  // uniform
+          if (far_away) {  // uniform
             h01 = f2mul(rcp_rn_normal2(sqrt_rn_normal2(r01)), f2s(gain_w));
             h23 = f2mul(rcp_rn_normal2(sqrt_rn_normal2(r23)), f2s(gain_w));
           } else {

@@ -168,9 +168,14 @@ size_t volume_scratch_bytes(int depth, int i0, int ni)
 // Planes [i0, i0+ni) of the (W+1)^3 volume into `slab` (device memory, ni x (W+1) x (W+1) floats, dense); scratch:
 // volume_scratch_bytes(depth, i0, ni) bytes of device memory.
 // events (optional, depth entries): events[0] is recorded before the first level, events[l] after level l; *nstages = depth - 1.
-cudaError_t volume_generate(float* slab, void* scratch, int depth, uint32_t seed, float amplitude, int i0, int ni, cudaStream_t stream,
-                            uint64_t* launches, cudaEvent_t* events, int* nstages)
+// coarse / coarse_done (optional): every level but the last runs on the side stream `coarse` and records coarse_done, which
+// `stream` waits for before the last level -- so that the latency-bound coarse levels of a call overlap the last level of
+// the call before (rn_abi.cu: two scratch slots).
+cudaError_t volume_generate(float* slab, void* scratch, int depth, uint32_t seed, float amplitude, int i0, int ni, cudaStream_t out_stream,
+                            uint64_t* launches, cudaEvent_t* events, int* nstages, cudaStream_t coarse, cudaEvent_t coarse_done)
 {
+  const bool split = coarse && coarse_done && depth >= 3;
+  cudaStream_t stream = split ? coarse : out_stream;
   int lo[32], hi[32];
   volume_ranges(depth, i0, ni, lo, hi);
   float* grid[32] = {};
@@ -204,6 +209,11 @@ cudaError_t volume_generate(float* slab, void* scratch, int depth, uint32_t seed
     const int n = 1 << l;
     int tiles_i = 0;
     const VolLevel L = vol_level_make(depth, l, lo, hi, grid[l], grid[l + 1], seed, amplitude, &tiles_i);
+    if (split && l == depth - 1) {  // the last level: on the caller's stream, behind the coarse levels
+      if ((e = cudaEventRecord(coarse_done, coarse)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(out_stream, coarse_done, 0)) != cudaSuccess) return e;
+      stream = out_stream;
+    }
     if (n >= kRowBigN) e = launch_rows<kRowTI, kRowTJ, kRowWarps>(L, tiles_i, stream);
     else if (n >= kRowMinN) e = launch_rows<kRowSmallT, kRowSmallT, kRowWarps>(L, tiles_i, stream);
     else switch (n) {
@@ -219,6 +229,10 @@ cudaError_t volume_generate(float* slab, void* scratch, int depth, uint32_t seed
     if (e != cudaSuccess) return e;
     if (events && (e = cudaEventRecord(events[l], stream)) != cudaSuccess) return e;
     if (launches) *launches += 1;
+  }
+  if (split && stream != out_stream) {  // every level was part of the fused coarse launch
+    if ((e = cudaEventRecord(coarse_done, coarse)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(out_stream, coarse_done, 0)) != cudaSuccess) return e;
   }
   return cudaSuccess;
 }

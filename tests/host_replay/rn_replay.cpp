@@ -186,7 +186,7 @@ void march_step_host(const StreamParams& sp, const MarchCtx& cx, std::vector<Mar
   RN_LANES(M::x1(cx, L[l], wsm, u, l, l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
   RN_LANES(M::p2(sp, cx, L[l], wsm, u, l))
   RN_LANES(M::x2(cx, L[l], wsm, u, l, l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
-  RN_LANES(M::p3(sp, cx, L[l], wsm, u, l))
+  RN_LANES(M::template p3<-1>(sp, cx, L[l], wsm, u, l))
   RN_LANES(M::store(sp, cx, L[l], u, l, l > 0 ? &L[l - 1] : nullptr))
 #undef RN_LANES
 }

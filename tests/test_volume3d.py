@@ -176,6 +176,34 @@ def test_gpu_thin_slabs_of_the_2049_cubed_volume(ctx, rnlib, oracle, i0, ni):
 
 
 @pytest.mark.gpu
+def test_gpu_back_to_back_async_volume_calls_do_not_mix(ctx, rnlib, oracle):
+    """Call pipelining (rn_abi.cu rn_volume3d): the coarse levels of call k+1 run on a side stream into the other scratch slot while
+    call k's last level is still running.  Five asynchronous calls with different seeds, depths and slabs on one stream, no
+    synchronisation in between, interleaved with a 2D field that shares the scratch slots; every result against the specification."""
+    import torch
+    from tests import oracle_lib
+    st = torch.cuda.Stream()
+    jobs = [(11, 7, 0, None), (12, 7, 0, None), (13, 6, 0, None), (14, 7, 40, 50), (15, 5, 0, None), (16, 7, 0, None)]
+    outs = []
+    field = torch.empty((257, 257, 4), device="cuda", dtype=torch.float32)
+    with torch.cuda.stream(st):
+        for n, (seed, depth, i0, ni) in enumerate(jobs):
+            S = (1 << depth) + 1
+            o = torch.empty((S - i0 if ni is None else ni, S, S), device="cuda", dtype=torch.float32)
+            ctx.volume3d_ptr(seed, depth, 0.3, o.data_ptr(), i0=i0, ni=ni, stream=st.cuda_stream)
+            outs.append(o)
+            if n == 2:
+                ctx.terrain2d_ptr(rnlib.default_params(seed=5, depth=8, apply_volcano=1), field.data_ptr(), dst_is_device=True, stream=st.cuda_stream)
+    st.synchronize()
+    for (seed, depth, i0, ni), o in zip(jobs, outs):
+        S = (1 << depth) + 1
+        want = oracle.volume3d(seed, depth, 0.3, i0, S - i0 if ni is None else ni)
+        assert np.array_equal(bits(o.cpu().numpy()), bits(want)), (seed, depth, i0, ni)
+    want2d = oracle.terrain2d(oracle_lib.params(seed=5, depth=8, apply_volcano=1))
+    assert np.array_equal(bits(field.cpu().numpy()), bits(want2d))
+
+
+@pytest.mark.gpu
 def test_gpu_volume_host_destination(ctx, rnlib, oracle):
     """rn_volume3d_host: the chunked, pipelined host path (pinned and pageable destinations, a slab that needs several chunks)
     equals the specification."""

@@ -26,3 +26,9 @@ PY
   ncu --set full --clock-control none --import-source on -k regex:k_vol_rows -s 2 -c 1 -f -o gpurun_out/${TAG}_vol python bench.py --workload volume --depth 9 --steps 2 --warmup 1 --no-cpu > gpurun_out/${TAG}_ncu_vol.log 2>&1
   tail -2 gpurun_out/${TAG}_ncu_vol.log
 fi
+if [ "$2" = "launches" ] || [ "$3" = "launches" ] || [ "$4" = "launches" ]; then
+  # launch list of the bench command (cold-cache, serialised per-launch times: shares, not absolutes)
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-strong > gpurun_out/${TAG}_launches.log 2>&1
+  tail -1 gpurun_out/${TAG}_launches.log
+  python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err; cat gpurun_out/${TAG}_bench_ref.json | cut -c1-300
+fi

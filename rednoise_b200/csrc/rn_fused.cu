@@ -162,10 +162,18 @@ __device__ __forceinline__ void march_step(const StreamParams& sp, const MarchCt
   using M = March<EDGE>;
   M::p1(sp, cx, L, wsm, u, lane);
   M::x1(cx, L, wsm, u, lane, nullptr, nullptr);
-  M::p2(sp, cx, L, wsm, u, lane);
-  M::x2(cx, L, wsm, u, lane, nullptr, nullptr);
-  M::template p3<VM>(sp, cx, L, wsm, u, lane);
-  M::store(sp, cx, L, u, lane, nullptr);
+  if (march_runs_p2(cx, u)) {  // uniform; false in the first warm-up step only
+    M::p2(sp, cx, L, wsm, u, lane);
+    M::x2(cx, L, wsm, u, lane, nullptr, nullptr);
+  } else {
+    M::skip_p2(sp, L);
+  }
+  if (march_runs_p3(cx, u)) {  // uniform; false in both warm-up steps
+    M::template p3<VM>(sp, cx, L, wsm, u, lane);
+    M::store(sp, cx, L, u, lane, nullptr);
+  } else {
+    M::skip_p3(sp, L);
+  }
 }
 
 template <int WPB, int MINB>

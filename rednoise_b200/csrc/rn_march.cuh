@@ -166,6 +166,19 @@ RN_HD MarchCtx march_ctx(const StreamParams& sp, int id, unsigned f)
   cx.ubase = cx.a0 - 1;
   return cx;
 }
+// The two warm-up steps of a unit (u = a0 - 1, a0) exist for what its first OWNED cell row a0 takes from the row above: the centres
+// C(a0 - 1) (P1 of step a0 - 1: their generateSquare losses reach the corners K(a0), their positions the midpoints M2(a0 - 1) and
+// M1(a0)) and the loss terms of M2(a0 - 1) (P2 of step a0).  Everything else those steps would compute -- M1(a0 - 1) and M2(a0 - 2)
+// in P2 of step a0 - 1, the final shades, addVolcano and store of the rows a0 - 2 and a0 - 1 in P3 -- only ever reaches samples
+// the unit does not own, so it is skipped (the LCG states and the output pointer still advance).
+// Measured (per-unit %globaltimer trace, profiles/micro/cta_trace.py, four A/B pairs): with the skip the units of the output kernel take
+// 71.6 us (median) against 69.5 us without it and the kernel 78.5-79.7 against 77.8-78.3 us -- less work, no gain -- so the shipped
+// build runs every phase in every step.
+#ifndef RN_MARCH_WARMUP_SKIP
+#define RN_MARCH_WARMUP_SKIP 0
+#endif
+RN_HD bool march_runs_p2(const MarchCtx& cx, int u) { return !RN_MARCH_WARMUP_SKIP || u >= cx.a0; }
+RN_HD bool march_runs_p3(const MarchCtx& cx, int u) { return !RN_MARCH_WARMUP_SKIP || u > cx.a0; }
 RN_HD bool march_step_is_lean(const MarchCtx& cx, int u) { return cx.col_lean && u >= cx.lean_lo && u <= cx.lean_hi; }
 
 // ---------------------------------------------------------------- lane <-> lane and lane <-> memory ----
@@ -503,6 +516,12 @@ struct March {
     L.sg[0] = K0.w;
     L.sg[1] = K1.w;
   }
+  static RN_HD void skip_p2(const StreamParams& sp, MarchLane& L)
+  {
+    L.sD1 = jump_apply(sp.jn, L.sD1);
+    L.sD2 = jump_apply(sp.jn1, L.sD2);
+  }
+  static RN_HD void skip_p3(const StreamParams& sp, MarchLane& L) { L.dst += 2 * sp.gout_pitch; }
   // X2 + the step's loop-1 mids, generateDiamond losses and corner shades go to the bank of step u
   static RN_HD void x2(const MarchCtx& cx, MarchLane& L, E4* wsm, int u, int lane, const MarchLane* left, const MarchLane* right)
   {

@@ -184,10 +184,18 @@ void march_step_host(const StreamParams& sp, const MarchCtx& cx, std::vector<Mar
 #define RN_LANES(call) for (int q = 0; q < 32; q++) { const int l = g_reverse ? 31 - q : q; call; }
   RN_LANES(M::p1(sp, cx, L[l], wsm, u, l))
   RN_LANES(M::x1(cx, L[l], wsm, u, l, l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
-  RN_LANES(M::p2(sp, cx, L[l], wsm, u, l))
-  RN_LANES(M::x2(cx, L[l], wsm, u, l, l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
-  RN_LANES(M::template p3<-1>(sp, cx, L[l], wsm, u, l))
-  RN_LANES(M::store(sp, cx, L[l], u, l, l > 0 ? &L[l - 1] : nullptr))
+  if (march_runs_p2(cx, u)) {  // (rn_fused.cu march_step)
+    RN_LANES(M::p2(sp, cx, L[l], wsm, u, l))
+    RN_LANES(M::x2(cx, L[l], wsm, u, l, l > 0 ? &L[l - 1] : nullptr, l < 31 ? &L[l + 1] : nullptr))
+  } else {
+    RN_LANES(M::skip_p2(sp, L[l]))
+  }
+  if (march_runs_p3(cx, u)) {
+    RN_LANES(M::template p3<-1>(sp, cx, L[l], wsm, u, l))
+    RN_LANES(M::store(sp, cx, L[l], u, l, l > 0 ? &L[l - 1] : nullptr))
+  } else {
+    RN_LANES(M::skip_p3(sp, L[l]))
+  }
 #undef RN_LANES
 }
 

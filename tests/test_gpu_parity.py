@@ -83,6 +83,22 @@ def test_nondefault_params(ctx, rnlib, oracle, algo):
         assert_bitwise(got, want, f"non-default params depth {depth}")
 
 
+@pytest.mark.parametrize("kw", [
+    dict(persistence=0.6, sideways_scale=0.3, radiosity_strength=0.7, feature_scale=50.0, amplitude_variation=0.25, amplitude=0.35, bulgy_rocks=0),
+    dict(amplitude=5.0),                 # |amplitude| > 4: Law::flat_ok is off, every warp takes the general tail
+    dict(amplitude=0.02, size=80.0),     # a smooth field: the flat tail at every streamed level
+    dict(amplitude=1.5, persistence=0.8, amplitude_variation=-0.9, sideways_scale=-0.5),  # rough: flat and general tails mixed
+])
+def test_deep_fields_with_nondefault_params(ctx, rnlib, oracle, kw):
+    """The streamed levels' kernel (k_march, depth >= 10) on both tails of its per-warp decision (rn_march.cuh pair_finish): fields
+    whose normals are all degenerate at the last levels, fields where none are, and parameters for which the flat tail is not allowed."""
+    ctx.set_algorithm(0)
+    for depth, seed in ((10, 31), (11, 4)):
+        got = ctx.terrain2d_host(rnlib.default_params(seed=seed, depth=depth, apply_volcano=1, **kw))
+        want = oracle.terrain2d(oracle_lib.params(seed=seed, depth=depth, apply_volcano=1, **kw))
+        assert_bitwise(got, want, f"{kw} depth {depth}")
+
+
 @pytest.mark.parametrize("algo", ALGOS)
 def test_windows_are_seam_exact(ctx, rnlib, oracle, algo):
     """'grid extent and origin': any sub-window equals the same indices of the full field."""

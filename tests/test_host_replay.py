@@ -86,6 +86,19 @@ def test_replay_nondefault_params(replay, oracle):
         assert np.array_equal(run(replay, p).view(np.uint32), oracle.terrain2d(p).view(np.uint32))
 
 
+@pytest.mark.parametrize("kw", [
+    dict(amplitude=5.0),                 # |amplitude| > 4: Law::flat_ok is off, the general tail everywhere
+    dict(amplitude=0.02, size=80.0),     # a smooth field: the flat tail at every streamed level
+    dict(amplitude=1.5, persistence=0.8, amplitude_variation=-0.9, sideways_scale=-0.5),  # rough: both tails
+])
+def test_replay_march_tails_with_nondefault_params(replay, oracle, kw):
+    """rn_march.cuh pair_finish<true/false>: the flat tail (only z moves) and the general one reproduce the oracle for parameters
+    that make every normal of the streamed levels degenerate, none of them, or that forbid the flat tail."""
+    for depth, seed in ((10, 31), (11, 4)):
+        p = oracle_lib.params(seed=seed, depth=depth, apply_volcano=1, **kw)
+        assert np.array_equal(run(replay, p).view(np.uint32), oracle.terrain2d(p).view(np.uint32)), (kw, depth)
+
+
 def test_replay_windows_are_seam_exact(replay, oracle):
     depth = 9
     S = (1 << depth) + 1

@@ -65,7 +65,8 @@ constexpr int kStreamSmallCols = RN_STREAM_SMALL_COLS;    // levels with fewer c
 #define RN_MARCH_FREE 2         // warps per SM the output launch leaves to the next call's small coarse stages
 #endif
 #ifndef RN_MARCH_EDGE_COST
-#define RN_MARCH_EDGE_COST 1.3f // duration of a border-strip warp relative to an interior one with the same rows
+#define RN_MARCH_EDGE_COST 1.22f // duration of a border-strip warp relative to an interior one with the same rows (unit trace: 2.0 vs
+                                 // 1.66 us per row); at depth 12 it gives 1772 units of 41 (border: 34) rows for the 1776 warp slots
 #endif
 #ifndef RN_MARCH_MIN_SEG_ROWS
 #define RN_MARCH_MIN_SEG_ROWS 8
@@ -313,7 +314,10 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
         };
         st.edge_first = strip_is_edge(0);
         st.edge_last = st.nstrips > 1 && strip_is_edge(st.nstrips - 1);
-        ctas_target = sm_count * (kMarchWarpsPerSM - ((small_chain && last) ? RN_MARCH_FREE : 0));
+#ifndef RN_MARCH_FREE_COARSE
+#define RN_MARCH_FREE_COARSE 2   // the same for the streamed levels before the last one (12 warps per SM = 3 per scheduler: 1025^2 -> 2049^2 in 30.2 instead of 32.4 us)
+#endif
+        ctas_target = sm_count * (kMarchWarpsPerSM - (small_chain ? (last ? RN_MARCH_FREE : RN_MARCH_FREE_COARSE) : 0));
         min_rows = RN_MARCH_MIN_SEG_ROWS;
         edge_cost = RN_MARCH_EDGE_COST;
       } else {

@@ -414,6 +414,15 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # one disjoint set of host cores per rank: a timed region is a few milliseconds of asynchronous enqueues (40 us of host time
+        # per 120 us step), and a rank whose enqueue thread is descheduled for a millisecond starves its GPU (max over ranks)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = len(cores) // world
+            if per >= 2:
+                os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]))
+        except (AttributeError, OSError):
+            pass
     build.build()  # no-op when the in-tree .so is fresh
     ctx = capi.Context(local_rank)
     ctx.set_algorithm(args.algo)
@@ -490,6 +499,9 @@ def run_ours(args):
         sampler.start()
     launches0 = ctx.launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    import gc
+    gc.collect()
+    gc.disable()  # no collector pause inside the timed region
     barrier()
     ev[0].record()
     t_host0 = time.perf_counter()
@@ -498,6 +510,7 @@ def run_ours(args):
         ev[k + 1].record()
     host_enqueue_us = (time.perf_counter() - t_host0) / args.steps * 1e6  # host time per step of the asynchronous calls
     barrier()
+    gc.enable()
     clocks = sampler.stop() if rank == 0 else None  # sampled during the timed region only
     total_ms = ev[0].elapsed_time(ev[-1])
     own_total_ms = total_ms

@@ -317,7 +317,10 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
 #ifndef RN_MARCH_FREE_COARSE
 #define RN_MARCH_FREE_COARSE 2   // the same for the streamed levels before the last one (12 warps per SM = 3 per scheduler: 1025^2 -> 2049^2 in 30.2 instead of 32.4 us)
 #endif
-        ctas_target = sm_count * (kMarchWarpsPerSM - (small_chain ? (last ? RN_MARCH_FREE : RN_MARCH_FREE_COARSE) : 0));
+#ifndef RN_MARCH_FREE_ALWAYS
+#define RN_MARCH_FREE_ALWAYS 0   // the same without a small chain (batches, depth 10): measured worse (64 depth-10 tiles: output level 438 vs 413-420 us)
+#endif
+        ctas_target = sm_count * (kMarchWarpsPerSM - ((small_chain || RN_MARCH_FREE_ALWAYS) ? (last ? RN_MARCH_FREE : RN_MARCH_FREE_COARSE) : 0));
         min_rows = RN_MARCH_MIN_SEG_ROWS;
         edge_cost = RN_MARCH_EDGE_COST;
       } else {

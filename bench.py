@@ -525,8 +525,7 @@ def run_ours(args):
         if args.workload == "batch" and seeds:
             # the library cuts a batch into chunks (1 GB of intermediate grids) and reports the launches of the LAST chunk: profile
             # a sub-batch that is one chunk, and take the roofline bytes from it
-            per_field = side * side * ELEM_BYTES // 3 + 1
-            prof_tiles = max(1, min(len(seeds), 64, (1 << 30) // per_field // 2))
+            prof_tiles = max(1, min(len(seeds), ctx.batch_chunk(p, len(seeds))))
             prof_samples = prof_tiles * side * side
 
             def prof_step():

@@ -145,6 +145,11 @@ int rn_terrain2d(rn_context* ctx, const rn_params* p, const rn_window* win, rn_e
 int rn_terrain2d_batch(rn_context* ctx, const rn_params* p, const uint32_t* seeds, int ntiles,
                        rn_element* dst, size_t tile_stride_elems, int dst_is_device, void* stream);
 
+/* A batch is generated in chunks of whole fields (one launch chain per chunk; bounded intermediate grids, and a field count for
+ * which the (strip, segment) units of the output level fill the GPU's warp slots evenly): the number of fields per chunk that
+ * rn_terrain2d_batch uses for a device destination, 0 on bad arguments.  Informational (scratch sizing, profiling). */
+int rn_terrain2d_batch_chunk(rn_context* ctx, const rn_params* p, int ntiles);
+
 /* The integer part of the path, exposed for bit-exact parity tests: writes the
  * 15-bit draws k = first .. first+n-1 of srand(seed) as uint16. */
 int rn_lcg_draws_device(rn_context* ctx, uint32_t seed, uint64_t first, uint64_t n, uint16_t* dst,

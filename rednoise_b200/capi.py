@@ -21,7 +21,7 @@ RN_MIN_DEPTH, RN_MAX_DEPTH = 3, 14
 SYMBOLS = [
     "rn_version", "rn_last_error_string", "rn_status_string", "rn_params_default", "rn_terrain2d_side",
     "rn_terrain2d_draw_count", "rn_terrain2d_call_index", "rn_lcg_state_after", "rn_lcg_draw", "rn_create",
-    "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_set_pipelining", "rn_terrain2d", "rn_terrain2d_batch", "rn_lcg_draws_device", "rn_selftest_math",
+    "rn_destroy", "rn_launch_count", "rn_set_algorithm", "rn_set_profiling", "rn_last_stage_times", "rn_set_pipelining", "rn_terrain2d", "rn_terrain2d_batch", "rn_terrain2d_batch_chunk", "rn_lcg_draws_device", "rn_selftest_math",
     "rn_terrain2d_cell_count", "rn_terrain2d_cell_level_offset", "rn_terrain2d_cells", "rn_volume3d", "rn_volume3d_host", "rn_volume3d_slab_elems",
     "rn_rock_draw_count", "rn_rock", "rn_rock_batch", "rn_cloud_draw_count", "rn_cloud",
     "rn_device_count", "rn_device_alloc", "rn_device_free", "rn_host_alloc", "rn_host_free", "rn_copy_to_host",
@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
     L.rn_last_stage_times.argtypes = [vp, C.POINTER(C.c_float), i32]
     L.rn_terrain2d.argtypes = [vp, C.POINTER(Params), C.POINTER(Window), vp, sz, i32, vp, C.POINTER(C.c_float)]
     L.rn_terrain2d_batch.argtypes = [vp, C.POINTER(Params), C.POINTER(u32), i32, vp, sz, i32, vp]
+    L.rn_terrain2d_batch_chunk.argtypes = [vp, C.POINTER(Params), i32]
     L.rn_lcg_draws_device.argtypes = [vp, u32, u64, u64, vp, i32, vp]
     L.rn_selftest_math.argtypes = [vp, C.POINTER(u64)]
     L.rn_terrain2d_cell_count.restype = u64
@@ -218,6 +219,10 @@ class Context:
                                   C.c_void_p(ptr), pitch_elems, 1 if dst_is_device else 0,
                                   C.c_void_p(stream) if stream else None, vpos))
         return tuple(vpos) if want_volcano_pos else None
+
+    def batch_chunk(self, p: Params, ntiles: int) -> int:
+        """Fields per chunk that rn_terrain2d_batch uses for a device destination (include/rednoise.h)."""
+        return int(lib().rn_terrain2d_batch_chunk(self._h, C.byref(p), ntiles))
 
     def terrain2d_batch_ptr(self, p: Params, seeds, ptr: int, *, tile_stride_elems: int = 0,
                             dst_is_device: bool = True, stream: int = 0, seeds_ptr: int = 0):

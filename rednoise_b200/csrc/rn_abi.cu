@@ -6,6 +6,7 @@
 // implementation behind any compute entry point.
 #include "../../include/rednoise.h"
 #include "rn_kernels.h"
+#include <cstdlib>
 #include <stdio.h>
 #include <string.h>
 #include <string>
@@ -182,6 +183,28 @@ int synth_window_fused(rn_context* ctx, const rn_params* p, const rn_window& w, 
   RN_CUDA(cudaEventRecord(ctx->slot_free[sl], stream));
   ctx->slot_used[sl] = true;
   return RN_OK;
+}
+
+// Fields per chunk of a batch: staging (host destination) and the intermediate grids (two scratch slots) stay bounded -- the
+// scratch of a chunk scales with its field count (21 MB per depth-11 field, 84 MB per depth-12 field) -- and, for a device
+// destination, the field count is one for which the output level's units fill the warp slots evenly (rn_plan.h march_batch_chunk).
+size_t batch_chunk(const rn_context* ctx, const rn_params* p, int ntiles, bool direct)
+{
+  const size_t side = (size_t)(1 << p->depth) + 1;
+  const size_t field_bytes = side * side * sizeof(Elem);
+  const size_t scratch_per_field = fused_scratch_bytes(p->depth, 2) / 2;
+  const size_t budget = (size_t)1 << 30;
+  size_t chunk = direct ? budget / (scratch_per_field ? scratch_per_field : 1) : budget / field_bytes;
+  if (chunk < 1) chunk = 1;
+  if (chunk > 32768) chunk = 32768;  // gridDim.z
+  if (direct && ntiles > 1) {
+    const char* forced = getenv("RN_BATCH_CHUNK");  // experiments
+    const int want = forced ? atoi(forced) : fused_batch_chunk(p->depth, (int)chunk, ctx->sm_count);
+    if (want >= 1 && (size_t)want < chunk) chunk = (size_t)want;
+  }
+  // (equal chunks were measured and are worse: the planner gives every field of a chunk the same whole number of (strip, segment)
+  //  units, and 229 depth-10 fields x 9 units fill the 2072 warp slots where 128 x 11 do not -- 256 tiles: 115 vs 84 Gsamples/s)
+  return chunk;
 }
 
 // Large host destination: the window is produced in row chunks through two staging halves, so that synthesis of chunk k+1
@@ -564,15 +587,7 @@ int rn_terrain2d_batch(rn_context* ctx, const rn_params* p, const uint32_t* seed
   cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
   const bool direct = dst_is_device && (reinterpret_cast<uintptr_t>(dst) % 16 == 0);
   const size_t field_bytes = side * side * sizeof(Elem);
-  // chunk so that staging (host destination) and the intermediate grids (two scratch slots) stay bounded: the scratch of a
-  // chunk scales with its field count (21 MB per depth-11 field, 84 MB per depth-12 field)
-  const size_t scratch_per_field = fused_scratch_bytes(p->depth, 2) / 2;
-  const size_t budget = (size_t)1 << 30;
-  size_t chunk = direct ? budget / (scratch_per_field ? scratch_per_field : 1) : budget / field_bytes;
-  if (chunk < 1) chunk = 1;
-  if (chunk > 32768) chunk = 32768;  // gridDim.z
-  // (equal chunks were measured and are worse: the planner gives every field of a chunk the same whole number of (strip, segment)
-  //  units, and 229 depth-10 fields x 9 units fill the 2072 warp slots where 128 x 11 do not -- 256 tiles: 115 vs 84 Gsamples/s)
+  const size_t chunk = batch_chunk(ctx, p, ntiles, direct);
   const int sb = (int)(ctx->batch_seq++ & 1);
   st = ensure(&ctx->seeds[sb], &ctx->seeds_bytes[sb], sizeof(uint32_t) * (size_t)ntiles);
   if (st != RN_OK) return st;
@@ -600,6 +615,13 @@ int rn_terrain2d_batch(rn_context* ctx, const rn_params* p, const uint32_t* seed
   ctx->seeds_used[sb] = true;
   if (!(stream_v && dst_is_device)) RN_CUDA(cudaStreamSynchronize(stream));
   return RN_OK;
+}
+
+int rn_terrain2d_batch_chunk(rn_context* ctx, const rn_params* p, int ntiles)
+{
+  if (!ctx || check_params(p) != RN_OK || ntiles < 1) return 0;
+  const size_t c = batch_chunk(ctx, p, ntiles, true);
+  return (int)(c < (size_t)ntiles ? c : (size_t)ntiles);
 }
 
 uint64_t rn_terrain2d_cell_count(int depth)

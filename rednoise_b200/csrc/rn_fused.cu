@@ -322,6 +322,7 @@ extern "C" int rn_debug_timeline(unsigned long long* host, int reset)
 #endif
 
 size_t fused_scratch_bytes(int depth, int nfields) { return chain_scratch_bytes(depth, nfields); }
+int fused_batch_chunk(int depth, int cmax, int sm_count) { return march_batch_chunk(depth, cmax, sm_count); }
 
 // Synthesizes the window [i0,i0+ni) x [j0,j0+nj) of `nfields` depth-`depth` fields.
 //   dst     element (i0, j0) of field 0; row pitch `pitch`, field stride `field_stride` (elements)

@@ -14,6 +14,7 @@ cudaError_t levelsync_generate(Elem* g, float* off, size_t pitch, int depth, int
 // Algorithm 2 (rn_fused.cu): fused tile kernels + streamed last levels, 2-6 launches per field; writes only the requested window.
 // march: streamed levels run the warp-synchronous kernel (rn_march.cuh), else the round-1 block kernel (rn_stream.cuh).
 size_t fused_scratch_bytes(int depth, int nfields);
+int fused_batch_chunk(int depth, int cmax, int sm_count);  // fields per chunk of a batch (rn_plan.h march_batch_chunk)
 cudaError_t fused_generate(Elem* dst, size_t pitch, size_t field_stride, int depth, int i0, int j0, int ni, int nj, const Law& law,
                            float persistence, uint32_t seed, const uint32_t* seeds, int nfields, int volcano, float amplitude,
                            void* scratch, cudaStream_t stream, uint64_t* launches, cudaEvent_t* events = nullptr, int* nstages = nullptr,

@@ -64,6 +64,12 @@ constexpr int kStreamSmallCols = RN_STREAM_SMALL_COLS;    // levels with fewer c
 #ifndef RN_MARCH_FREE
 #define RN_MARCH_FREE 2         // warps per SM the output launch leaves to the next call's small coarse stages
 #endif
+#ifndef RN_MARCH_FREE_COARSE
+#define RN_MARCH_FREE_COARSE 2   // the same for the streamed levels before the last one (12 warps per SM = 3 per scheduler: 1025^2 -> 2049^2 in 30.2 instead of 32.4 us)
+#endif
+#ifndef RN_MARCH_FREE_ALWAYS
+#define RN_MARCH_FREE_ALWAYS 0   // the same without a small chain (batches, depth 10): measured worse (64 depth-10 tiles: output level 438 vs 413-420 us)
+#endif
 #ifndef RN_MARCH_EDGE_COST
 #define RN_MARCH_EDGE_COST 1.22f // duration of a border-strip warp relative to an interior one with the same rows (unit trace: 2.0 vs
                                  // 1.66 us per row); at depth 12 it gives 1772 units of 41 (border: 34) rows for the 1776 warp slots
@@ -222,6 +228,48 @@ inline size_t chain_scratch_bytes(int depth, int nfields)
   return total;
 }
 
+// Row segments of a streamed level: the smallest interior segment length r (>= min_rows) whose unit count -- ni interior strips
+// and ne border strips per field -- fits per_field units; border strips get r / edge_cost rows.
+inline void segment_rows(int per_field, int rows, int ni, int ne, int min_rows, float edge_cost, int* r_out, int* re_out)
+{
+  int r = min_rows < rows ? min_rows : rows, re = r;
+  for (;; r++) {
+    re = (int)((float)r / edge_cost + 0.5f);
+    re = re < min_rows ? (min_rows < rows ? min_rows : rows) : re;
+    if (r >= rows || ni * ((rows + r - 1) / r) + ne * ((rows + re - 1) / re) <= per_field) break;
+  }
+  *r_out = r;
+  *re_out = re;
+}
+
+// How many whole fields a batch chunk of the warp march should hold (at most cmax): every field of a chunk gets the same whole number
+// of (strip, segment) units, so the duration of the output level per field is a sawtooth in the chunk size -- 229 depth-10 fields
+// x 9 full-height units fill the warp slots, but the two border strips of every field then run 1.22x as long as the rest; 103
+// fields x 20 units (2 segments per interior strip, 3 per border strip) finish together.  Model: the longest unit of the chunk
+// (rows + 3 steps of start-up, border rows x edge cost) per field; the smallest chunk within 2 % of the best wins (less scratch).
+inline int march_batch_chunk(int depth, int cmax, int sm_count)
+{
+  if (!RN_MARCH || !plan_uses_streaming(depth) || cmax <= 1) return cmax;
+  const int n = 1 << (depth - 1);
+  const int nstrips = (n + 1 + kMarchCols - 1) / kMarchCols;
+  const int ne = nstrips > 1 ? 2 : 1, ni = nstrips - ne;
+  const int target = sm_count * (kMarchWarpsPerSM - (RN_MARCH_FREE_ALWAYS ? RN_MARCH_FREE : 0));
+  float best = 0.0f;
+  int best_c = cmax;
+  for (int pass = 0; pass < 2; pass++)
+    for (int c = cmax; c >= 1; c--) {
+      int r, re;
+      segment_rows(target / c > 0 ? target / c : 1, n, ni, ne, RN_MARCH_MIN_SEG_ROWS, RN_MARCH_EDGE_COST, &r, &re);
+      const int units = ni * ((n + r - 1) / r) + ne * ((n + re - 1) / re);
+      const float waves = (float)(units * c) / (float)target;  // > 1 when even whole strips do not fit
+      const float longest = (float)(r + 3) > (float)(re + 3) * RN_MARCH_EDGE_COST ? (float)(r + 3) : (float)(re + 3) * RN_MARCH_EDGE_COST;
+      const float cost = longest * (waves > 1.0f ? waves : 1.0f) / (float)c;
+      if (pass == 0) { if (best == 0.0f || cost < best) best = cost; }
+      else if (cost <= best * 1.02f) best_c = c;  // descending c: ends at the smallest chunk that is good enough
+    }
+  return best_c;
+}
+
 // Builds the launches that synthesize the window [i0,i0+ni) x [j0,j0+nj) of `nfields` depth-`depth`
 // fields into dst (element (i0,j0) of field 0; row pitch / field stride in elements).  Earlier
 // stages only compute the tiles the window's dependency cone touches.  Returns the launch count.
@@ -314,12 +362,6 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
         };
         st.edge_first = strip_is_edge(0);
         st.edge_last = st.nstrips > 1 && strip_is_edge(st.nstrips - 1);
-#ifndef RN_MARCH_FREE_COARSE
-#define RN_MARCH_FREE_COARSE 2   // the same for the streamed levels before the last one (12 warps per SM = 3 per scheduler: 1025^2 -> 2049^2 in 30.2 instead of 32.4 us)
-#endif
-#ifndef RN_MARCH_FREE_ALWAYS
-#define RN_MARCH_FREE_ALWAYS 0   // the same without a small chain (batches, depth 10): measured worse (64 depth-10 tiles: output level 438 vs 413-420 us)
-#endif
         ctas_target = sm_count * (kMarchWarpsPerSM - ((small_chain || RN_MARCH_FREE_ALWAYS) ? (last ? RN_MARCH_FREE : RN_MARCH_FREE_COARSE) : 0));
         min_rows = RN_MARCH_MIN_SEG_ROWS;
         edge_cost = RN_MARCH_EDGE_COST;
@@ -341,13 +383,8 @@ inline int build_chain(StageLaunch* out, int depth, int i0, int j0, int ni, int 
       // with 24-row segments).  A border strip takes edge_cost times as long per row (measured), so it
       // gets that much fewer rows.
       const int per_field = ctas_target / (nfields > 0 ? nfields : 1);
-      // smallest interior segment length r (>= min_rows) whose unit count fits; border strips get r / edge_cost rows
-      int r = min_rows < rows ? min_rows : rows, re = r;
-      for (;; r++) {
-        re = (int)((float)r / edge_cost + 0.5f);
-        re = re < min_rows ? (min_rows < rows ? min_rows : rows) : re;
-        if (r >= rows || ni * ((rows + r - 1) / r) + ne * ((rows + re - 1) / re) <= per_field) break;
-      }
+      int r, re;
+      segment_rows(per_field, rows, ni, ne, min_rows, edge_cost, &r, &re);
       st.seg_rows = r;
       st.nseg = (rows + r - 1) / r;
       st.seg_rows_edge = re;

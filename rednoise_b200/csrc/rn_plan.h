@@ -246,7 +246,8 @@ inline void segment_rows(int per_field, int rows, int ni, int ne, int min_rows, 
 // of (strip, segment) units, so the duration of the output level per field is a sawtooth in the chunk size -- 229 depth-10 fields
 // x 9 full-height units fill the warp slots, but the two border strips of every field then run 1.22x as long as the rest; 103
 // fields x 20 units (2 segments per interior strip, 3 per border strip) finish together.  Model: the longest unit of the chunk
-// (rows + 3 steps of start-up, border rows x edge cost) per field; the smallest chunk within 2 % of the best wins (less scratch).
+// (rows + 3 steps of start-up, border rows x edge cost) per field; the smallest chunk of at least 4 fields within 2 % of the best
+// wins (less scratch).  Depth 11, 32 tiles: chunks of 2 / 4 / 8 / 14 / 28 give 102 / 123 / 134 / 135 / 131; depth 12, 8 tiles: 2 / 4 / 8: 143 / 149 / 146.  Measured, 1024 depth-10 tiles: chunks of 229 / 103 / 69 / 27 / 14 fields give 111 / 109 / 119 / 120 / 108 Gsamples/s.
 inline int march_batch_chunk(int depth, int cmax, int sm_count)
 {
   if (!RN_MARCH || !plan_uses_streaming(depth) || cmax <= 1) return cmax;
@@ -257,7 +258,7 @@ inline int march_batch_chunk(int depth, int cmax, int sm_count)
   float best = 0.0f;
   int best_c = cmax;
   for (int pass = 0; pass < 2; pass++)
-    for (int c = cmax; c >= 1; c--) {
+    for (int c = cmax; c >= (cmax < 4 ? 1 : 4); c--) {
       int r, re;
       segment_rows(target / c > 0 ? target / c : 1, n, ni, ne, RN_MARCH_MIN_SEG_ROWS, RN_MARCH_EDGE_COST, &r, &re);
       const int units = ni * ((n + r - 1) / r) + ne * ((n + re - 1) / re);
@@ -265,7 +266,8 @@ inline int march_batch_chunk(int depth, int cmax, int sm_count)
       const float longest = (float)(r + 3) > (float)(re + 3) * RN_MARCH_EDGE_COST ? (float)(r + 3) : (float)(re + 3) * RN_MARCH_EDGE_COST;
       const float cost = longest * (waves > 1.0f ? waves : 1.0f) / (float)c;
       if (pass == 0) { if (best == 0.0f || cost < best) best = cost; }
-      else if (cost <= best * 1.02f) best_c = c;  // descending c: ends at the smallest chunk that is good enough
+      else if (cost <= best * 1.02f && (c >= 4 || cmax < 4)) best_c = c;  // descending c: ends at the smallest chunk (of at least 4
+                                                                            // fields: the fixed cost of a chunk) that is good enough
     }
   return best_c;
 }

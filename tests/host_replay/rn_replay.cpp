@@ -384,6 +384,9 @@ int replay_volume3d(uint32_t seed, int depth, float amplitude, int i0, int ni, f
   return 0;
 }
 
+// Fields per chunk of a batch (rn_plan.h march_batch_chunk, what rn_terrain2d_batch_chunk reports on the device side).
+int replay_batch_chunk(int depth, int cmax, int sm_count) { return march_batch_chunk(depth, cmax, sm_count); }
+
 // kinds[k] of the launches that synthesize a whole depth-`depth` field (0 tile stage, 1 block streaming, 2 warp march).
 int replay_chain_kinds(int depth, int march, int* kinds)
 {

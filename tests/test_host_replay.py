@@ -168,6 +168,19 @@ def test_replay_block_streaming_kernel_agrees(replay, oracle, depth, seed):
     assert np.array_equal(run(replay, p, poison=1).view(np.uint32), want.view(np.uint32))
 
 
+def test_batch_chunk_rule(replay):
+    """rn_plan.h march_batch_chunk: a chunk holds a field count for which every field's (strip, segment) units fill the warp slots and
+    finish together -- never more than the memory bound allows, at least 4 fields when it allows that many, all of them for shallow fields."""
+    f = replay.replay_batch_chunk
+    assert f(10, 229, 148) == 27          # 7 interior strips x 8 segments + 2 border strips x 10 = 76 units x 27 fields = 2052 of 2072 slots
+    for depth in (10, 11, 12, 13):
+        for cmax in (1, 2, 3, 4, 7, 12, 50, 229, 1000):
+            c = f(depth, cmax, 148)
+            assert 1 <= c <= cmax and (c >= 4 or cmax < 4), (depth, cmax, c)
+    assert f(9, 500, 148) == 500 and f(5, 32768, 148) == 32768   # tile stages only: the memory bound decides
+    assert f(10, 229, 132) <= 229
+
+
 def test_replay_march_is_the_default_for_deep_fields(replay):
     k = (C.c_int * 16)()
     for depth in (10, 12, 14):

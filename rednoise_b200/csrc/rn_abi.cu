@@ -13,6 +13,8 @@
 #include <new>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 
 using namespace rn;
 
@@ -51,6 +53,7 @@ struct rn_context {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t chunk_ready[2] = {nullptr, nullptr};   // synthesis of the chunk in staging half h has finished
   cudaEvent_t chunk_copied[2] = {nullptr, nullptr};  // its device-to-host copy has finished
+  void* bounce = nullptr;  size_t bounce_bytes = 0;  // pinned host halves a PAGEABLE destination is filled through (grow-only)
   // stage profiling
   int profiling = 0;
   cudaEvent_t ev[17] = {};
@@ -217,24 +220,100 @@ int enqueue_window_to_host(rn_context* ctx, const rn_params* p, const rn_window&
   const size_t half = (size_t)rows * (size_t)w.nj;
   int st = ensure(&ctx->field, &ctx->field_bytes, sizeof(Elem) * 2 * half);
   if (st != RN_OK) return st;
-  int k = 0;
-  for (int r0 = 0; r0 < w.ni; r0 += rows, k++) {
+  // A PAGEABLE destination (what `new TerrainElement[]`, Terrain.cpp:45-49, gives an unmodified caller): the runtime would stage such a
+  // copy itself, at ~18 GB/s.  Instead every chunk crosses PCIe into one of two pinned halves at the full rate and a few host threads
+  // move it on into the destination while the next chunk is in flight.
+  cudaPointerAttributes attr{};
+  const bool pageable = cudaPointerGetAttributes(&attr, dst) != cudaSuccess || attr.type == cudaMemoryTypeUnregistered;
+  cudaGetLastError();
+  if (pageable) {
+    if (ctx->bounce_bytes < sizeof(Elem) * 2 * half) {
+      if (ctx->bounce) cudaFreeHost(ctx->bounce);
+      ctx->bounce = nullptr;
+      ctx->bounce_bytes = 0;
+      cudaError_t e = cudaHostAlloc(&ctx->bounce, sizeof(Elem) * 2 * half, cudaHostAllocDefault);
+      if (e != cudaSuccess) return fail_cuda(e, "cudaHostAlloc(bounce)");
+      ctx->bounce_bytes = sizeof(Elem) * 2 * half;
+    }
+  }
+  const int nchunks = (w.ni + rows - 1) / rows;
+  // host side of the pageable path: chunk k may be moved once `landed` > k; `moved` counts the workers that finished a chunk
+  const unsigned hc = std::thread::hardware_concurrency();
+  const int nworkers = pageable ? (int)std::min<unsigned>(8u, hc > 1 ? hc / 2 : 1u) : 0;
+  std::atomic<int> landed{0};
+  std::vector<std::atomic<int>> moved(pageable ? (size_t)nchunks : 0);
+  for (auto& m : moved) m.store(0);
+  std::vector<std::thread> workers;
+  auto move_chunk = [&](int k, int part, int parts) {
+    const int r0 = k * rows, nr = (w.ni - r0 < rows) ? w.ni - r0 : rows;
+    const Elem* src = reinterpret_cast<const Elem*>(ctx->bounce) + (size_t)(k & 1) * half;
+    const int a = (int)((long long)nr * part / parts), b = (int)((long long)nr * (part + 1) / parts);
+    for (int r = a; r < b; r++) memcpy(dst + (size_t)(r0 + r) * pitch_elems, src + (size_t)r * (size_t)w.nj, (size_t)w.nj * sizeof(Elem));
+  };
+  for (int t = 0; t < nworkers; t++)
+    workers.emplace_back([&, t] {
+      for (int k = 0; k < nchunks; k++) {
+        while (landed.load(std::memory_order_acquire) <= k) {
+          if (landed.load(std::memory_order_acquire) < 0) return;  // the call failed
+          std::this_thread::yield();
+        }
+        move_chunk(k, t, nworkers);
+        moved[(size_t)k].fetch_add(1, std::memory_order_release);
+      }
+    });
+  auto fail_workers = [&](int status) {
+    landed.store(-1, std::memory_order_release);
+    for (auto& t : workers) t.join();
+    return status;
+  };
+  auto chunk_landed = [&](int k) -> int {  // the host waits for chunk k's transfer and releases it to the workers
+    cudaError_t e = cudaEventSynchronize(ctx->chunk_copied[k & 1]);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaEventSynchronize(chunk)");
+    landed.store(k + 1, std::memory_order_release);
+    return RN_OK;
+  };
+#define RN_CUDA_W(call)                                                            \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) return fail_workers(fail_cuda(e_, #call));              \
+  } while (0)
+  for (int k = 0; k < nchunks; k++) {
+    const int r0 = k * rows;
     const int nr = (w.ni - r0 < rows) ? w.ni - r0 : rows;
     const int h = k & 1;
     Elem* stage = reinterpret_cast<Elem*>(ctx->field) + (size_t)h * half;
-    if (k >= 2) RN_CUDA(cudaStreamWaitEvent(stream, ctx->chunk_copied[h], 0));  // the staging half is free again
+    if (pageable && k >= 2) {
+      // the pinned half is free again once chunk k - 2 has left it: release chunk k - 1 first, then wait for the workers
+      // (the copy queued for chunk k - 1 is already running)
+      st = chunk_landed(k - 1);
+      if (st != RN_OK) return fail_workers(st);
+      while (moved[(size_t)(k - 2)].load(std::memory_order_acquire) < nworkers) std::this_thread::yield();
+    }
+    if (k >= 2) RN_CUDA_W(cudaStreamWaitEvent(stream, ctx->chunk_copied[h], 0));  // the staging half is free again
     const rn_window cw{w.i0 + r0, w.j0, nr, w.nj};
     st = synth_window_fused(ctx, p, cw, stage, (size_t)w.nj, 0, nullptr, 1, stream);
-    if (st != RN_OK) return st;
-    RN_CUDA(cudaEventRecord(ctx->chunk_ready[h], stream));
-    RN_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ready[h], 0));
-    if (pitch_elems == (size_t)w.nj)  // dense rows: one linear copy
-      RN_CUDA(cudaMemcpyAsync(dst + (size_t)r0 * pitch_elems, stage, (size_t)nr * (size_t)w.nj * sizeof(Elem), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (st != RN_OK) return fail_workers(st);
+    RN_CUDA_W(cudaEventRecord(ctx->chunk_ready[h], stream));
+    RN_CUDA_W(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ready[h], 0));
+    if (pageable)
+      RN_CUDA_W(cudaMemcpyAsync(reinterpret_cast<Elem*>(ctx->bounce) + (size_t)h * half, stage, (size_t)nr * (size_t)w.nj * sizeof(Elem),
+                                cudaMemcpyDeviceToHost, ctx->copy_stream));
+    else if (pitch_elems == (size_t)w.nj)  // dense rows: one linear copy
+      RN_CUDA_W(cudaMemcpyAsync(dst + (size_t)r0 * pitch_elems, stage, (size_t)nr * (size_t)w.nj * sizeof(Elem), cudaMemcpyDeviceToHost, ctx->copy_stream));
     else
-      RN_CUDA(cudaMemcpy2DAsync(dst + (size_t)r0 * pitch_elems, pitch_elems * sizeof(Elem), stage, (size_t)w.nj * sizeof(Elem),
-                                (size_t)w.nj * sizeof(Elem), (size_t)nr, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    RN_CUDA(cudaEventRecord(ctx->chunk_copied[h], ctx->copy_stream));
+      RN_CUDA_W(cudaMemcpy2DAsync(dst + (size_t)r0 * pitch_elems, pitch_elems * sizeof(Elem), stage, (size_t)w.nj * sizeof(Elem),
+                                  (size_t)w.nj * sizeof(Elem), (size_t)nr, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    RN_CUDA_W(cudaEventRecord(ctx->chunk_copied[h], ctx->copy_stream));
   }
+  if (pageable) {
+    for (int k = std::max(0, nchunks - 2); k < nchunks; k++) {  // (for k >= 2 the loop released chunks 0 .. k - 1)
+      if (landed.load(std::memory_order_acquire) > k) continue;
+      st = chunk_landed(k);
+      if (st != RN_OK) return fail_workers(st);
+    }
+    for (auto& t : workers) t.join();
+  }
+#undef RN_CUDA_W
   return RN_OK;
 }
 
@@ -386,6 +465,7 @@ int rn_destroy(rn_context* ctx)
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
   }
+  if (ctx->bounce) cudaFreeHost(ctx->bounce);
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);

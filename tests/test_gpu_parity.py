@@ -99,6 +99,28 @@ def test_deep_fields_with_nondefault_params(ctx, rnlib, oracle, kw):
         assert_bitwise(got, want, f"{kw} depth {depth}")
 
 
+def test_large_host_destinations_pageable_and_pinned(ctx, rnlib, oracle):
+    """rn_abi.cu enqueue_window_to_host: windows of >= 2^22 samples reach host memory in row chunks -- a pinned destination straight
+    from the device, a PAGEABLE one (numpy / malloc / `new TerrainElement[]`) through two pinned halves and host copy threads.  Padded
+    pitch, a window whose rows are no multiple of the chunk, several chunks, and the volcano position read back from the host copy."""
+    import torch
+    ctx.set_algorithm(0)
+    depth, seed = 12, 2718
+    S = (1 << depth) + 1
+    full, wpos = oracle.terrain2d(oracle_lib.params(seed=seed, depth=depth, apply_volcano=1), want_volcano_pos=True)
+    p = rnlib.default_params(seed=seed, depth=depth, apply_volcano=1)
+    for (i0, j0, ni, nj, pad) in ((0, 0, S, S, 0), (3, 5, S - 10, S - 7, 9), (1000, 0, 1301, S, 0)):
+        for pinned in (False, True):
+            host = torch.full((ni, nj + pad, 4), -3.0, dtype=torch.float32, pin_memory=pinned)
+            whole = (i0, j0, ni, nj) == (0, 0, S, S)
+            vpos = ctx.terrain2d_ptr(p, host.data_ptr(), window=None if whole else rnlib.Window(i0, j0, ni, nj), pitch_elems=nj + pad,
+                                     dst_is_device=False, want_volcano_pos=True)
+            got = host.numpy()
+            assert_bitwise(got[:, :nj], full[i0:i0 + ni, j0:j0 + nj], f"window {(i0, j0, ni, nj)} pinned={pinned}")
+            assert (got[:, nj:] == -3.0).all()
+            assert vpos == wpos
+
+
 @pytest.mark.parametrize("algo", ALGOS)
 def test_windows_are_seam_exact(ctx, rnlib, oracle, algo):
     """'grid extent and origin': any sub-window equals the same indices of the full field."""
